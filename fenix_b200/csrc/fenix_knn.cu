@@ -1,0 +1,589 @@
+// fenix_knn.cu — C ABI of libfenix_knn.so (declared in include/fenix_knn.h).
+//
+// Host side of the B200 exact k-NN path: device shard ownership, pinned staging, kernel
+// dispatch and the certificate/fallback logic. Kernels live in exact_scan.cuh (fp64 CUDA-core
+// scan, merges, row norms) and tc_filter.cuh (tcgen05/TMEM TF32 filter + rerank).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fenix_knn.h"
+#include "exact_scan.cuh"
+#include "tc_filter.cuh"
+
+// ----------------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define FX_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(_e == cudaErrorMemoryAllocation ? FX_ENOMEM : FX_ECUDA, "%s failed: %s (%s:%d)", \
+                  #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define FX_TRY(expr)              \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != FX_OK) return _r;   \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------
+// objects
+// ----------------------------------------------------------------------------------------
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return FX_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(FX_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+    cap = want;
+    return FX_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {  // grow-only pinned staging
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return FX_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(FX_ENOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); }
+    cap = want;
+    return FX_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct fx_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;   // compute
+  cudaStream_t upload = nullptr;   // H2D of corpus chunks
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  std::mutex mu;                   // one search at a time per device context
+  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc;
+  HostBuf h_q, h_rows, h_dist, h_flags;
+  int64_t launches = 0;
+  fx::TcState tc;                  // driver entry points / kernel attributes of the TC path
+};
+
+constexpr size_t RING_BYTES = size_t(32) << 20;
+
+struct fx_corpus {
+  fx_ctx* ctx = nullptr;
+  int64_t cap = 0, n = 0, row_base = 0;
+  int dim = 0, pitch = 0;
+  float* X = nullptr;
+  float* hx = nullptr;
+  float* rx = nullptr;
+  unsigned int* max_n2_bits = nullptr;
+  float max_norm = 0.f;            // max |x| over the shard (host copy, set by finalize)
+  bool finalized = false;
+  void* ring[2] = {nullptr, nullptr};
+  cudaEvent_t ring_ev[2] = {nullptr, nullptr};
+  int ring_next = 0;
+  fx_stats stats{};
+  fx::TcCorpus tc;                 // tensor map of the shard for the TC path
+};
+
+static int bind(fx_ctx* ctx) {
+  FX_CUDA(cudaSetDevice(ctx->device));
+  return FX_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// lifetime
+// ----------------------------------------------------------------------------------------
+extern "C" int fx_abi_version(void) { return FX_ABI_VERSION; }
+extern "C" const char* fx_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int fx_init(int device, fx_ctx** out) {
+  if (!out) return fail(FX_EINVAL, "fx_init: out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(FX_ECUDA, "fx_init: no CUDA device visible (%s); libfenix_knn has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= n_dev) return fail(FX_EINVAL, "fx_init: device %d out of range [0,%d)", device, n_dev);
+  fx_ctx* ctx = new (std::nothrow) fx_ctx();
+  if (!ctx) return fail(FX_ENOMEM, "fx_init: out of host memory");
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return fail(FX_ECUDA, "fx_init: cannot bind device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+  if (prop.major != 10) {
+    delete ctx;
+    return fail(FX_EUNSUP, "fx_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                device, prop.major, prop.minor);
+  }
+  FX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  FX_CUDA(cudaStreamCreateWithFlags(&ctx->upload, cudaStreamNonBlocking));
+  FX_CUDA(cudaEventCreate(&ctx->ev_start));
+  FX_CUDA(cudaEventCreate(&ctx->ev_stop));
+  FX_CUDA(cudaEventCreate(&ctx->ev_k0));
+  FX_CUDA(cudaEventCreate(&ctx->ev_k1));
+  FX_CUDA(cudaFuncSetAttribute(fx::exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  FX_CUDA(cudaFuncSetAttribute(fx::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  FX_CUDA(cudaFuncSetAttribute(fx::merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  {
+    std::string err;
+    if (!fx::tc_init(&ctx->tc, ctx->sm_count, &err)) {
+      delete ctx;
+      return fail(FX_ECUDA, "fx_init: %s", err.c_str());
+    }
+  }
+  *out = ctx;
+  return FX_OK;
+}
+
+extern "C" int fx_shutdown(fx_ctx* ctx) {
+  if (!ctx) return fail(FX_EINVAL, "fx_shutdown: ctx is NULL");
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->upload);
+  ctx->d_q.release(); ctx->d_rows.release(); ctx->d_dist.release(); ctx->d_mask.release();
+  ctx->d_partial.release(); ctx->d_qlist.release(); ctx->d_tc.release();
+  ctx->h_q.release(); ctx->h_rows.release(); ctx->h_dist.release(); ctx->h_flags.release();
+  cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_stop);
+  cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
+  cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->upload);
+  delete ctx;
+  return FX_OK;
+}
+
+extern "C" int fx_corpus_create(fx_ctx* ctx, int64_t capacity_rows, int32_t dim, int32_t dtype,
+                                int64_t row_base, fx_corpus** out) {
+  if (!ctx || !out) return fail(FX_EINVAL, "fx_corpus_create: NULL argument");
+  *out = nullptr;
+  if (capacity_rows < 0) return fail(FX_EINVAL, "fx_corpus_create: negative capacity %lld", (long long)capacity_rows);
+  if (dim < 1) return fail(FX_EINVAL, "fx_corpus_create: dim must be >= 1 (got %d)", dim);
+  if (dtype != FX_DTYPE_F32) return fail(FX_EUNSUP, "fx_corpus_create: only float32 rows are supported (dtype=%d)", dtype);
+  if (capacity_rows > int64_t(0xfffffff0ll)) return fail(FX_EUNSUP, "fx_corpus_create: a shard holds at most 2^32-16 rows; shard the corpus");
+  if (dim > 16384) return fail(FX_EUNSUP, "fx_corpus_create: dim %d exceeds 16384", dim);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  fx_corpus* c = new (std::nothrow) fx_corpus();
+  if (!c) return fail(FX_ENOMEM, "fx_corpus_create: out of host memory");
+  c->ctx = ctx; c->cap = capacity_rows; c->dim = dim; c->pitch = (dim + 3) & ~3; c->row_base = row_base;
+  size_t rows_alloc = size_t(std::max<int64_t>(capacity_rows, 1));
+  // the tensor-core tiles read whole 256-row boxes; TMA clips to the tensor bounds, no padding needed
+  cudaError_t e = cudaMalloc(&c->X, rows_alloc * c->pitch * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->hx, rows_alloc * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->rx, rows_alloc * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->max_n2_bits, sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (c->X) cudaFree(c->X);
+    if (c->hx) cudaFree(c->hx);
+    if (c->rx) cudaFree(c->rx);
+    delete c;
+    return fail(FX_ENOMEM, "fx_corpus_create: cannot allocate %zu rows x %d floats on device %d: %s",
+                rows_alloc, c ? ((dim + 3) & ~3) : 0, ctx->device, cudaGetErrorString(e));
+  }
+  if (c->pitch != c->dim) FX_CUDA(cudaMemsetAsync(c->X, 0, rows_alloc * c->pitch * sizeof(float), ctx->upload));
+  c->stats.dim = dim; c->stats.pitch = c->pitch;
+  c->stats.device_bytes = int64_t(rows_alloc * (c->pitch + 2) * sizeof(float));
+  *out = c;
+  return FX_OK;
+}
+
+static int ensure_ring(fx_corpus* c) {
+  for (int i = 0; i < 2; ++i) {
+    if (!c->ring[i]) {
+      FX_CUDA(cudaMallocHost(&c->ring[i], RING_BYTES));
+      FX_CUDA(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
+    }
+  }
+  return FX_OK;
+}
+
+static int append_impl(fx_corpus* c, const void* rows, int64_t n_rows, bool on_device) {
+  if (!c) return fail(FX_EINVAL, "fx_corpus_append: corpus is NULL");
+  if (n_rows < 0) return fail(FX_EINVAL, "fx_corpus_append: negative row count");
+  if (n_rows == 0) return FX_OK;
+  if (!rows) return fail(FX_EINVAL, "fx_corpus_append: rows is NULL");
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (c->finalized) return fail(FX_ESTATE, "fx_corpus_append: shard is already finalized");
+  if (c->n + n_rows > c->cap)
+    return fail(FX_EINVAL, "fx_corpus_append: %lld rows would exceed capacity %lld (have %lld)",
+                (long long)n_rows, (long long)c->cap, (long long)c->n);
+  FX_TRY(bind(ctx));
+  const size_t src_pitch = size_t(c->dim) * sizeof(float), dst_pitch = size_t(c->pitch) * sizeof(float);
+  float* dst = c->X + size_t(c->n) * c->pitch;
+  if (on_device) {
+    FX_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, rows, src_pitch, src_pitch, size_t(n_rows), cudaMemcpyDeviceToDevice, ctx->upload));
+    FX_CUDA(cudaStreamSynchronize(ctx->upload));  // caller may free its buffer on return
+  } else {
+    // pageable Arrow buffer -> pinned ring (CPU copy) -> async H2D, double buffered
+    FX_TRY(ensure_ring(c));
+    const int64_t rows_per_slot = std::max<int64_t>(1, int64_t(RING_BYTES / src_pitch));
+    const char* src = static_cast<const char*>(rows);
+    for (int64_t done = 0; done < n_rows;) {
+      int64_t take = std::min(rows_per_slot, n_rows - done);
+      int slot = c->ring_next;
+      c->ring_next ^= 1;
+      FX_CUDA(cudaEventSynchronize(c->ring_ev[slot]));
+      std::memcpy(c->ring[slot], src + size_t(done) * src_pitch, size_t(take) * src_pitch);
+      FX_CUDA(cudaMemcpy2DAsync(dst + size_t(done) * c->pitch, dst_pitch, c->ring[slot], src_pitch, src_pitch,
+                                size_t(take), cudaMemcpyHostToDevice, ctx->upload));
+      FX_CUDA(cudaEventRecord(c->ring_ev[slot], ctx->upload));
+      done += take;
+    }
+  }
+  c->n += n_rows;
+  return FX_OK;
+}
+
+extern "C" int fx_corpus_append(fx_corpus* c, const void* host_rows, int64_t n_rows) {
+  return append_impl(c, host_rows, n_rows, false);
+}
+extern "C" int fx_corpus_append_device(fx_corpus* c, const void* device_rows, int64_t n_rows) {
+  return append_impl(c, device_rows, n_rows, true);
+}
+
+extern "C" int fx_corpus_finalize(fx_corpus* c) {
+  if (!c) return fail(FX_EINVAL, "fx_corpus_finalize: corpus is NULL");
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (c->finalized) return FX_OK;
+  FX_TRY(bind(ctx));
+  FX_CUDA(cudaStreamSynchronize(ctx->upload));
+  FX_CUDA(cudaMemsetAsync(c->max_n2_bits, 0, sizeof(unsigned int), ctx->stream));
+  if (c->n > 0) {
+    int blocks = int(std::min<int64_t>((c->n + 7) / 8, int64_t(ctx->sm_count) * 8));
+    fx::row_norms_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->hx, c->rx, c->max_n2_bits);
+    FX_CUDA(cudaGetLastError());
+    ctx->launches++; c->stats.kernel_launches++;
+  }
+  unsigned int bits = 0;
+  FX_CUDA(cudaMemcpyAsync(&bits, c->max_n2_bits, sizeof bits, cudaMemcpyDeviceToHost, ctx->stream));
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  float n2; std::memcpy(&n2, &bits, sizeof n2);
+  c->max_norm = std::sqrt(n2) * (1.0f + 1e-6f);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ring[i]) { cudaFreeHost(c->ring[i]); c->ring[i] = nullptr; cudaEventDestroy(c->ring_ev[i]); c->ring_ev[i] = nullptr; }
+  }
+  {
+    std::string err;
+    if (!fx::tc_bind_corpus(&ctx->tc, &c->tc, c->X, c->n, c->dim, c->pitch, &err))
+      return fail(FX_ECUDA, "fx_corpus_finalize: %s", err.c_str());
+  }
+  c->stats.n_rows = c->n;
+  c->finalized = true;
+  return FX_OK;
+}
+
+extern "C" int fx_corpus_destroy(fx_corpus* c) {
+  if (!c) return fail(FX_EINVAL, "fx_corpus_destroy: corpus is NULL");
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->upload);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ring[i]) { cudaFreeHost(c->ring[i]); cudaEventDestroy(c->ring_ev[i]); }
+  }
+  if (c->X) cudaFree(c->X);
+  if (c->hx) cudaFree(c->hx);
+  if (c->rx) cudaFree(c->rx);
+  if (c->max_n2_bits) cudaFree(c->max_n2_bits);
+  delete c;
+  return FX_OK;
+}
+
+extern "C" int fx_get_stats(fx_corpus* c, fx_stats* out) {
+  if (!c || !out) return fail(FX_EINVAL, "fx_get_stats: NULL argument");
+  std::lock_guard<std::mutex> lock(c->ctx->mu);
+  c->stats.n_rows = c->n;
+  *out = c->stats;
+  return FX_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// exact scan dispatch
+// ----------------------------------------------------------------------------------------
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Runs the fp64 scan for `n_list` queries (all of them when d_qlist == null) and writes the
+// (row, distance) top-k of each into the output slots of the listed queries.
+static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_qlist, int n_list,
+                          int metric, int k, const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist) {
+  fx_ctx* ctx = c->ctx;
+  if (n_list == 0) return FX_OK;
+  const int buf = next_pow2(k + fx::SCAN_THREADS);
+  const size_t per_q = size_t(c->pitch) * 8 + 8 + 8 + size_t(buf) * 8 + 4;
+  const size_t smem_limit = 200 * 1024;
+  int qb = int(std::min<size_t>(fx::SCAN_MAX_QB, smem_limit / per_q));
+  if (qb < 1) return fail(FX_EUNSUP, "exact scan: dim %d with k %d needs %zu B of shared memory per query", c->dim, k, per_q);
+  qb = std::min(qb, n_list);
+  const int groups = (n_list + qb - 1) / qb;
+  const int64_t tiles = std::max<int64_t>(1, (c->n + fx::SCAN_THREADS - 1) / fx::SCAN_THREADS);
+  int W = int(std::min<int64_t>(tiles, std::max<int64_t>(1, (2 * int64_t(ctx->sm_count) + groups - 1) / groups)));
+  W = std::max(1, std::min(W, 8192 / std::max(k, 1)));
+  if (groups > 65535) {
+    // grid.y limit: process in slabs of 65535 groups
+    int done = 0;
+    while (done < n_list) {
+      int take = std::min(n_list - done, 65535 * qb);
+      if (d_qlist) {
+        FX_TRY(run_exact_scan(c, d_q, n_q, d_qlist + done, take, metric, k, d_mask, d_out_rows, d_out_dist));
+      } else {
+        // build an explicit list for the slab
+        std::vector<int> idx(take);
+        for (int i = 0; i < take; ++i) idx[i] = done + i;
+        DevBuf tmp;
+        FX_TRY(tmp.ensure(size_t(take) * sizeof(int)));
+        FX_CUDA(cudaMemcpyAsync(tmp.p, idx.data(), size_t(take) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        int r = run_exact_scan(c, d_q, n_q, static_cast<int*>(tmp.p), take, metric, k, d_mask, d_out_rows, d_out_dist);
+        cudaStreamSynchronize(ctx->stream);
+        tmp.release();
+        FX_TRY(r);
+      }
+      done += take;
+    }
+    return FX_OK;
+  }
+  FX_TRY(ctx->d_partial.ensure(size_t(n_list) * W * k * sizeof(uint64_t)));
+  fx::ScanParams p{};
+  p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.Q = d_q; p.n_q = n_q;
+  p.metric = metric; p.mask = d_mask; p.q_list = d_qlist; p.n_list = n_list; p.k = k; p.buf = buf; p.qb = qb;
+  p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.dist_out = nullptr;
+  const size_t smem = per_q * qb + 16;
+  fx::exact_scan_kernel<<<dim3(W, groups), fx::SCAN_THREADS, smem, ctx->stream>>>(p);
+  FX_CUDA(cudaGetLastError());
+  const int n_sort = next_pow2(std::max(W * k, 2));
+  fx::merge_keys_kernel<<<n_list, 256, size_t(n_sort) * 8, ctx->stream>>>(
+      p.partial, W, k, n_sort, d_qlist, c->row_base, d_out_rows, d_out_dist);
+  FX_CUDA(cudaGetLastError());
+  ctx->launches += 2; c->stats.kernel_launches += 2;
+  return FX_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// search
+// ----------------------------------------------------------------------------------------
+static int check_search_args(fx_corpus* c, const void* q, int64_t n_q, int metric, int k, int precision,
+                             const void* out_rows, const void* out_dist) {
+  if (!c) return fail(FX_EINVAL, "fx_search: corpus is NULL");
+  if (!c->finalized) return fail(FX_ESTATE, "fx_search: corpus is not finalized");
+  if (n_q < 0) return fail(FX_EINVAL, "fx_search: negative query count");
+  if (n_q > 0 && (!q || !out_rows || !out_dist)) return fail(FX_EINVAL, "fx_search: NULL buffer");
+  if (n_q > int64_t(1) << 24) return fail(FX_EUNSUP, "fx_search: at most 2^24 queries per call");
+  if (metric < 0 || metric > 2) return fail(FX_EINVAL, "fx_search: unknown metric %d", metric);
+  if (k < 1) return fail(FX_EINVAL, "fx_search: k must be >= 1 (got %d)", k);
+  if (k > 2048) return fail(FX_EUNSUP, "fx_search: k = %d exceeds the supported maximum of 2048", k);
+  if (precision != FX_PREC_FP32 && precision != FX_PREC_TF32 && precision != FX_PREC_EXACT_SCAN)
+    return fail(FX_EINVAL, "fx_search: unknown precision mode %d", precision);
+  return FX_OK;
+}
+
+static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int metric, int k, int precision,
+                                const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist) {
+  fx_ctx* ctx = c->ctx;
+  FX_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+  int path = 0;
+  const bool want_tc = precision != FX_PREC_EXACT_SCAN && d_mask == nullptr &&
+                       fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q));
+  if (c->n == 0) {
+    // empty shard: all pads
+    fx::fill_pad_kernel<<<int(std::min<int64_t>((n_q * k + 255) / 256, 65535)), 256, 0, ctx->stream>>>(d_out_rows, d_out_dist, n_q * k);
+    FX_CUDA(cudaGetLastError());
+    ctx->launches++; c->stats.kernel_launches++;
+  } else if (want_tc) {
+    path = 1;
+    fx::TcSearch s{};
+    s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
+    s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = d_q; s.n_q = int(n_q); s.metric = metric; s.k = k;
+    s.certify = precision == FX_PREC_FP32; s.out_rows = d_out_rows; s.out_dist = d_out_dist;
+    s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1;
+    std::string err;
+    size_t need = fx::tc_scratch_bytes(&ctx->tc, s);
+    FX_TRY(ctx->d_tc.ensure(need));
+    int launched = 0;
+    if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err)) return fail(FX_ECUDA, "fx_search: %s", err.c_str());
+    ctx->launches += launched; c->stats.kernel_launches += launched;
+    if (s.certify) {
+      // queries whose certificate failed are recomputed by the exact scan
+      FX_TRY(ctx->h_flags.ensure(size_t(n_q) * sizeof(int)));
+      int* h_flags = static_cast<int*>(ctx->h_flags.p);
+      const int* d_flags = fx::tc_flags(&ctx->tc, s, ctx->d_tc.p);
+      FX_CUDA(cudaMemcpyAsync(h_flags, d_flags, size_t(n_q) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      FX_CUDA(cudaStreamSynchronize(ctx->stream));
+      std::vector<int> bad;
+      for (int64_t i = 0; i < n_q; ++i) if (h_flags[i]) bad.push_back(int(i));
+      if (!bad.empty()) {
+        FX_TRY(ctx->d_qlist.ensure(bad.size() * sizeof(int)));
+        FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), bad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        FX_TRY(run_exact_scan(c, d_q, int(n_q), static_cast<int*>(ctx->d_qlist.p), int(bad.size()), metric, k,
+                              nullptr, d_out_rows, d_out_dist));
+        FX_CUDA(cudaStreamSynchronize(ctx->stream));  // `bad` must outlive the H2D copy
+        c->stats.fallback_queries += int64_t(bad.size());
+      }
+    }
+  } else {
+    FX_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    FX_TRY(run_exact_scan(c, d_q, int(n_q), nullptr, int(n_q), metric, k, d_mask, d_out_rows, d_out_dist));
+    FX_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+  }
+  FX_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f, kms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+  if (c->n > 0) cudaEventElapsedTime(&kms, ctx->ev_k0, ctx->ev_k1);
+  c->stats.last_search_ms = ms; c->stats.last_main_kernel_ms = kms; c->stats.last_path = path;
+  c->stats.searches++; c->stats.queries += n_q;
+  return FX_OK;
+}
+
+extern "C" int fx_search_device(fx_corpus* c, const float* d_queries, int64_t n_q, int32_t metric, int32_t k,
+                                int32_t precision, const uint8_t* d_row_mask, int64_t* d_out_rows, float* d_out_dist) {
+  FX_TRY(check_search_args(c, d_queries, n_q, metric, k, precision, d_out_rows, d_out_dist));
+  if (n_q == 0) return FX_OK;
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  return search_device_locked(c, d_queries, n_q, metric, k, precision, d_row_mask, d_out_rows, d_out_dist);
+}
+
+extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, int32_t k,
+                         int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist) {
+  FX_TRY(check_search_args(c, queries, n_q, metric, k, precision, out_rows, out_dist));
+  if (n_q == 0) return FX_OK;
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  const size_t q_bytes = size_t(n_q) * c->dim * sizeof(float);
+  const size_t r_bytes = size_t(n_q) * k * sizeof(int64_t), d_bytes = size_t(n_q) * k * sizeof(float);
+  FX_TRY(ctx->d_q.ensure(q_bytes));
+  FX_TRY(ctx->d_rows.ensure(r_bytes));
+  FX_TRY(ctx->d_dist.ensure(d_bytes));
+  // queries: direct DMA when the caller's buffer is pinned, otherwise through pinned staging
+  cudaPointerAttributes attr{};
+  bool pinned = cudaPointerGetAttributes(&attr, queries) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const void* q_src = queries;
+  if (!pinned) {
+    FX_TRY(ctx->h_q.ensure(q_bytes));
+    std::memcpy(ctx->h_q.p, queries, q_bytes);
+    q_src = ctx->h_q.p;
+  }
+  FX_CUDA(cudaMemcpyAsync(ctx->d_q.p, q_src, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const uint8_t* d_mask = nullptr;
+  if (row_mask && c->n > 0) {
+    FX_TRY(ctx->d_mask.ensure(size_t(c->n)));
+    FX_CUDA(cudaMemcpyAsync(ctx->d_mask.p, row_mask, size_t(c->n), cudaMemcpyHostToDevice, ctx->stream));
+    d_mask = static_cast<const uint8_t*>(ctx->d_mask.p);
+  }
+  FX_TRY(search_device_locked(c, static_cast<const float*>(ctx->d_q.p), n_q, metric, k, precision, d_mask,
+                              static_cast<int64_t*>(ctx->d_rows.p), static_cast<float*>(ctx->d_dist.p)));
+  // results: straight into the caller's buffers when pinned, else via pinned staging
+  bool out_pinned = cudaPointerGetAttributes(&attr, out_rows) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  bool outd_pinned = cudaPointerGetAttributes(&attr, out_dist) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (out_pinned && outd_pinned) {
+    FX_CUDA(cudaMemcpyAsync(out_rows, ctx->d_rows.p, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FX_CUDA(cudaMemcpyAsync(out_dist, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else {
+    FX_TRY(ctx->h_rows.ensure(r_bytes));
+    FX_TRY(ctx->h_dist.ensure(d_bytes));
+    FX_CUDA(cudaMemcpyAsync(ctx->h_rows.p, ctx->d_rows.p, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FX_CUDA(cudaMemcpyAsync(ctx->h_dist.p, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FX_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
+    std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
+  }
+  return FX_OK;
+}
+
+extern "C" int fx_distances(fx_corpus* c, const float* query, int32_t metric, float* out_dist) {
+  if (!c) return fail(FX_EINVAL, "fx_distances: corpus is NULL");
+  if (!c->finalized) return fail(FX_ESTATE, "fx_distances: corpus is not finalized");
+  if (metric < 0 || metric > 2) return fail(FX_EINVAL, "fx_distances: unknown metric %d", metric);
+  if (c->n == 0) return FX_OK;
+  if (!query || !out_dist) return fail(FX_EINVAL, "fx_distances: NULL buffer");
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  const size_t q_bytes = size_t(c->dim) * sizeof(float), d_bytes = size_t(c->n) * sizeof(float);
+  FX_TRY(ctx->d_q.ensure(q_bytes));
+  FX_TRY(ctx->d_dist.ensure(d_bytes));
+  FX_CUDA(cudaMemcpyAsync(ctx->d_q.p, query, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t per_q = size_t(c->pitch) * 8 + 8 + 8 + 2 * 8 + 4;
+  if (per_q > 200 * 1024) return fail(FX_EUNSUP, "fx_distances: dim %d too large", c->dim);
+  fx::ScanParams p{};
+  p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.Q = static_cast<const float*>(ctx->d_q.p);
+  p.n_q = 1; p.metric = metric; p.mask = nullptr; p.q_list = nullptr; p.n_list = 1; p.k = 0; p.buf = 2; p.qb = 1;
+  p.partial = nullptr; p.dist_out = static_cast<float*>(ctx->d_dist.p);
+  const int64_t tiles = (c->n + fx::SCAN_THREADS - 1) / fx::SCAN_THREADS;
+  int W = int(std::min<int64_t>(tiles, int64_t(ctx->sm_count) * 8));
+  fx::exact_scan_kernel<<<dim3(W, 1), fx::SCAN_THREADS, per_q + 16, ctx->stream>>>(p);
+  FX_CUDA(cudaGetLastError());
+  ctx->launches++; c->stats.kernel_launches++;
+  FX_TRY(ctx->h_dist.ensure(d_bytes));
+  FX_CUDA(cudaMemcpyAsync(ctx->h_dist.p, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
+  return FX_OK;
+}
+
+extern "C" int fx_merge_topk(fx_ctx* ctx, const int64_t* d_rows, const float* d_dist, int32_t n_lists,
+                             int64_t n_q, int32_t k, int64_t* d_out_rows, float* d_out_dist) {
+  if (!ctx) return fail(FX_EINVAL, "fx_merge_topk: ctx is NULL");
+  if (n_lists < 1 || n_q < 0 || k < 1) return fail(FX_EINVAL, "fx_merge_topk: bad sizes (lists=%d, n_q=%lld, k=%d)", n_lists, (long long)n_q, k);
+  if (n_q == 0) return FX_OK;
+  if (!d_rows || !d_dist || !d_out_rows || !d_out_dist) return fail(FX_EINVAL, "fx_merge_topk: NULL buffer");
+  const int n_sort = next_pow2(std::max(n_lists * k, 2));
+  if (size_t(n_sort) * 12 > 128 * 1024) return fail(FX_EUNSUP, "fx_merge_topk: lists*k = %d exceeds 8192", n_lists * k);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  for (int64_t q0 = 0; q0 < n_q; q0 += 1 << 30) {  // grid.x is effectively unbounded for our sizes
+    fx::merge_pairs_kernel<<<unsigned(n_q), 256, size_t(n_sort) * 12, ctx->stream>>>(
+        d_rows, d_dist, n_lists, n_q, k, n_sort, d_out_rows, d_out_dist);
+    break;
+  }
+  FX_CUDA(cudaGetLastError());
+  ctx->launches++;
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FX_OK;
+}

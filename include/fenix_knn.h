@@ -1,0 +1,150 @@
+/* fenix_knn.h — C ABI of libfenix_knn.so: exact k-NN search over device-resident corpus shards.
+ *
+ * This is the drop-in boundary for the one hot path of nrlugg/fenix that this repository
+ * replaces: exact brute-force search = distance(query, every corpus row) + top-k.
+ * Reference seam (citations relative to the reference tree):
+ *   src/fenix/io/index/index.py:133-168   UDF `dist` + select_k_unstable + take   (replaced)
+ *   src/fenix/io/coder/coder.py:38-50     distance(): l2 / cosine / dot            (replaced)
+ *   src/fenix/io/torch/torch.py:6-10      from_arrow(): Arrow values buffer view   (replaced by
+ *                                         fx_corpus_append: host buffer -> pinned ring -> HBM)
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FX_E* code on failure; the message
+ *     is available (thread-local) from fx_last_error().
+ *   - plain pointers and sizes only; no torch / Arrow types cross this boundary.
+ *   - "row" always means the position of a vector in the corpus in append order
+ *     (the reference has no id column of its own: Arrow `take` indices are row positions,
+ *     index.py:166-167).
+ *   - distances use the reference's conventions (coder.py:38-50): smaller is better;
+ *       FX_METRIC_L2     Euclidean distance WITH sqrt              (torch.cdist, coder.py:40)
+ *       FX_METRIC_COSINE 0.5 - 0.5 * cos(q, x), eps 1e-12 on norms (coder.py:43-45)
+ *       FX_METRIC_IP     -<q, x>                                   (coder.py:48)
+ *   - results are ordered by (distance ascending, row ascending); lists shorter than k are
+ *     padded with (row = -1, distance = +inf).
+ *   - there is no CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef FENIX_KNN_H_
+#define FENIX_KNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FX_ABI_VERSION 1
+
+/* error codes */
+#define FX_OK 0
+#define FX_EINVAL (-1)   /* bad argument (NULL, negative size, unknown metric, k < 1 ...) */
+#define FX_ECUDA (-2)    /* a CUDA runtime / driver call failed */
+#define FX_ENOMEM (-3)   /* host or device allocation failed */
+#define FX_ESTATE (-4)   /* call not valid in this state (append after finalize, search before) */
+#define FX_EUNSUP (-5)   /* valid request this build does not support (dtype, huge dim) */
+
+/* metrics: the five reference names map to three arithmetic forms (coder.py:39,42,47) */
+#define FX_METRIC_L2 0     /* "l2", "euclidean" */
+#define FX_METRIC_COSINE 1 /* "cosine" */
+#define FX_METRIC_IP 2     /* "dot", "inner_product" */
+
+/* precision modes of fx_search
+ *   FP32: exact. A TF32 tensor-core pass filters candidates under a rigorous error bound,
+ *         survivors are re-ranked with fp64-accumulated arithmetic, the result is certified
+ *         (or recomputed by the exact scan kernel when the certificate fails).
+ *   TF32: the same tensor-core pass without slack/certificate; distances of the returned
+ *         rows are still exact, membership is approximate (recall reported by bench.py).
+ *   EXACT_SCAN: forces the fp64-accumulating CUDA-core scan kernel (checker / fallback path).
+ */
+#define FX_PREC_FP32 0
+#define FX_PREC_TF32 1
+#define FX_PREC_EXACT_SCAN 3
+
+/* dtype of corpus rows */
+#define FX_DTYPE_F32 0
+
+typedef struct fx_ctx fx_ctx;       /* one CUDA device + its streams and scratch */
+typedef struct fx_corpus fx_corpus; /* one device-resident, row-major corpus shard */
+
+typedef struct fx_stats {
+  int64_t n_rows;            /* rows resident in the shard */
+  int32_t dim;               /* vector width D */
+  int32_t pitch;             /* floats per stored row (D rounded up to a multiple of 4) */
+  int64_t device_bytes;      /* HBM held by this shard (rows + norms) */
+  int64_t searches;          /* fx_search* calls completed */
+  int64_t queries;           /* queries answered */
+  int64_t fallback_queries;  /* queries whose certificate failed -> exact scan recompute */
+  int64_t kernel_launches;   /* kernels of this library launched so far */
+  double last_search_ms;     /* device time of the last search (CUDA events) */
+  double last_main_kernel_ms;/* device time of the dominant kernel of the last search */
+  int32_t last_path;         /* 0 = exact scan, 1 = tcgen05 filter + rerank */
+  int32_t reserved;
+} fx_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Bind a context to CUDA device `device`. Replaces nothing in the reference (it never
+ * touches a device); one context per process-visible GPU. */
+int fx_init(int device, fx_ctx** out);
+int fx_shutdown(fx_ctx* ctx);
+
+/* Create an empty shard able to hold `capacity_rows` vectors of width `dim`.
+ * `row_base` is the global row position of local row 0 (multi-GPU row sharding: the value is
+ * added to every row this shard reports). Replaces the per-call mmap view of
+ * table.py:12-21 / arrow.py:6-8 with a resident copy owned by the library. */
+int fx_corpus_create(fx_ctx* ctx, int64_t capacity_rows, int32_t dim, int32_t dtype,
+                     int64_t row_base, fx_corpus** out);
+
+/* Append `n_rows` row-major vectors (tightly packed, `dim` floats each) from HOST memory.
+ * Called once per Arrow record-batch values buffer (the buffer torch.py:8-10 would have
+ * wrapped). Pageable memory is fine: rows are staged through an internal pinned ring and
+ * copied asynchronously. */
+int fx_corpus_append(fx_corpus* c, const void* host_rows, int64_t n_rows);
+
+/* Same, source already in DEVICE memory of the context's device. */
+int fx_corpus_append_device(fx_corpus* c, const void* device_rows, int64_t n_rows);
+
+/* Seal the shard: waits for uploads, computes and caches per-row squared norms (the work
+ * cdist / F.normalize redo on every call in the reference, coder.py:40,44). */
+int fx_corpus_finalize(fx_corpus* c);
+
+int fx_corpus_destroy(fx_corpus* c);
+
+/* ---- search ---------------------------------------------------------------------------- */
+
+/* k-NN of `n_q` queries (HOST, row-major n_q x dim floats) against the shard.
+ * `row_mask` (HOST, one byte per shard row, non-zero = row participates) or NULL; it is the
+ * device form of index.py:161 `data.filter(expr)`.
+ * out_rows [n_q*k] global row positions (row_base + local), out_dist [n_q*k] distances.
+ * Replaces index.py:162 (distance column) + index.py:165-168 (select_k + take indices). */
+int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, int32_t k,
+              int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist);
+
+/* Same with every pointer in DEVICE memory; enqueued on the context's stream and
+ * synchronised before return. Used by the multi-GPU path so the shard-local top-k stays
+ * in HBM for the NCCL all-gather. */
+int fx_search_device(fx_corpus* c, const float* d_queries, int64_t n_q, int32_t metric,
+                     int32_t k, int32_t precision, const uint8_t* d_row_mask,
+                     int64_t* d_out_rows, float* d_out_dist);
+
+/* Full distance column of ONE query against every shard row (HOST in / HOST out,
+ * out_dist[n_rows]). This is the `maxval is None or len(data) <= maxval` branch of
+ * index.py:162-165, where the reference returns all rows with __DISTANCE__ attached. */
+int fx_distances(fx_corpus* c, const float* query, int32_t metric, float* out_dist);
+
+/* Merge `n_lists` per-shard results (DEVICE, each [n_q*k], laid out list-major:
+ * rows[l*n_q*k + q*k + j]) into the global top-k ordered by (distance, row).
+ * The step after the NCCL all-gather of the k*world candidates. */
+int fx_merge_topk(fx_ctx* ctx, const int64_t* d_rows, const float* d_dist, int32_t n_lists,
+                  int64_t n_q, int32_t k, int64_t* d_out_rows, float* d_out_dist);
+
+/* ---- introspection --------------------------------------------------------------------- */
+
+int fx_get_stats(fx_corpus* c, fx_stats* out);
+const char* fx_last_error(void);
+int fx_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FENIX_KNN_H_ */

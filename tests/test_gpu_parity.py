@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed
+outputs of the live reference. Bar: neighbour ids bit-exact under (distance, row) order,
+distances within 1e-5 relative (BASELINE.json north_star), tolerance written in conftest."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+import fenix_b200 as fenix
+from conftest import METRICS, assert_same_neighbours, golden_cases, golden_filter, load_golden, table_of
+from fenix_b200 import knn
+from oracle import brute_force_f64, canonical, search_rows
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = {"fp32": knn.PREC_FP32, "scan": knn.PREC_EXACT_SCAN}
+
+
+@pytest.fixture(scope="module")
+def ctx(built_library):
+    c = knn.Context(0)
+    yield c
+    c.close()
+
+
+def make_corpus(ctx, x, row_base=0, pieces=3):
+    c = knn.Corpus(ctx, len(x), x.shape[1], row_base=row_base)
+    step = max(1, -(-len(x) // pieces))
+    for lo in range(0, len(x), step):
+        c.append(x[lo: lo + step])
+    return c.finalize()
+
+
+# ---- committed reference outputs ---------------------------------------------------------
+@pytest.mark.parametrize("prec", list(PRECISIONS))
+@pytest.mark.parametrize("case", [c for c in golden_cases() if c not in ("all_rows", "k_ge_n", "filtered")])
+@pytest.mark.parametrize("metric", METRICS)
+def test_topk_matches_live_reference_outputs(ctx, case, metric, prec):
+    g = load_golden(case)
+    corpus, queries, k = g["corpus"], g["queries"], int(g["k"])
+    c = make_corpus(ctx, corpus)
+    rows, dist = c.search(queries, metric, k, PRECISIONS[prec])
+    for qi in range(len(queries)):
+        assert_same_neighbours(rows[qi], dist[qi], g[f"{metric}:{qi}:id"], g[f"{metric}:{qi}:dist"],
+                               corpus, queries[qi], metric)
+        # our own order is canonical: (distance, row) ascending
+        assert np.array_equal(canonical(rows[qi], dist[qi])[0], rows[qi])
+    c.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_distance_column_matches_reference(ctx, metric):
+    g = load_golden("all_rows")
+    c = make_corpus(ctx, g["corpus"])
+    for qi, q in enumerate(g["queries"]):
+        d = c.distances(q, metric)
+        ref = g[f"{metric}:{qi}:dist"]  # all rows, table order
+        assert np.array_equal(g[f"{metric}:{qi}:id"], np.arange(len(ref)))
+        np.testing.assert_allclose(d, ref, rtol=1e-5, atol=2e-6)
+    c.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_masked_search_matches_reference_filter(ctx, metric):
+    g = load_golden("filtered")
+    corpus, k, mod = g["corpus"], int(g["k"]), int(g["filter_mod"])
+    mask = (np.arange(len(corpus)) % mod == 0).astype(np.uint8)
+    c = make_corpus(ctx, corpus)
+    rows, dist = c.search(g["queries"], metric, k, knn.PREC_FP32, row_mask=mask)
+    for qi in range(len(g["queries"])):
+        assert (rows[qi] % mod == 0).all()
+        assert_same_neighbours(rows[qi], dist[qi], g[f"{metric}:{qi}:id"], g[f"{metric}:{qi}:dist"],
+                               corpus, g["queries"][qi], metric)
+    c.close()
+
+
+# ---- seeded inputs against the oracle ----------------------------------------------------
+@pytest.mark.parametrize("prec", list(PRECISIONS))
+@pytest.mark.parametrize("shape", [(20000, 128, 64, 10), (30000, 96, 33, 100), (5000, 768, 16, 10), (4097, 100, 5, 37)])
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_seeded_parity_with_oracle(ctx, shape, metric, prec):
+    n, d, nq, k = shape
+    rng = np.random.default_rng(n + d)
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    queries = rng.standard_normal((nq, d), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    rows, dist = c.search(queries, metric, k, PRECISIONS[prec])
+    table = table_of(corpus, 4096)
+    for qi in range(0, nq, max(1, nq // 6)):  # the oracle is O(N*D) per query
+        ref_rows, ref_dist = search_rows(table, "vector", queries[qi], metric, k)
+        assert_same_neighbours(rows[qi], dist[qi], ref_rows, ref_dist, corpus, queries[qi], metric)
+    want_rows, want_dist = brute_force_f64(corpus, queries, metric, k)
+    assert np.array_equal(rows, want_rows)
+    np.testing.assert_allclose(dist, want_dist, rtol=2e-6, atol=1e-6)
+    c.close()
+
+
+@pytest.mark.parametrize("prec", list(PRECISIONS))
+def test_duplicates_are_ordered_by_row(ctx, prec):
+    rng = np.random.default_rng(5)
+    corpus = rng.standard_normal((3000, 32), dtype=np.float32)
+    corpus[1000:1400] = corpus[17]  # 400 copies of the winner
+    c = make_corpus(ctx, corpus)
+    for metric in ("l2", "cosine", "dot"):
+        rows, dist = c.search(corpus[17], metric, 10, PRECISIONS[prec])
+        want_rows, want_dist = brute_force_f64(corpus, corpus[17], metric, 10)
+        assert np.array_equal(rows, want_rows), metric
+        np.testing.assert_allclose(dist, want_dist, rtol=2e-6, atol=1e-6)
+        if metric == "l2":
+            assert rows[0].tolist() == [17] + list(range(1000, 1009)) and (dist[0] == 0).all()
+    c.close()
+
+
+def test_clustered_data_of_reference_tests(ctx):
+    """tests/test_flight.py:17-35 data (tight clusters far from the origin) and uniform queries (:104)."""
+    rng = np.random.default_rng(11)
+    parts = []
+    for _ in range(20):
+        x = rng.standard_normal((1000, 256), dtype=np.float32)
+        parts.append(x + 10 * x[0, :])
+    corpus = np.concatenate(parts)
+    queries = rng.random((8, 256), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    table = table_of(corpus, 1000)
+    for metric in METRICS:
+        rows, dist = c.search(queries, metric, 10)
+        for qi in range(len(queries)):
+            ref_rows, ref_dist = search_rows(table, "vector", queries[qi], metric, 10)
+            assert_same_neighbours(rows[qi], dist[qi], ref_rows, ref_dist, corpus, queries[qi], metric)
+    c.close()
+
+
+def test_edge_cases(ctx):
+    rng = np.random.default_rng(3)
+    corpus = rng.standard_normal((50, 12), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    # k > N: padded with (-1, +inf)
+    rows, dist = c.search(corpus[:2], "l2", 64)
+    assert (rows[:, 50:] == -1).all() and np.isinf(dist[:, 50:]).all()
+    assert sorted(rows[0, :50].tolist()) == list(range(50))
+    # zero queries
+    r0, d0 = c.search(np.empty((0, 12), np.float32), "l2", 3)
+    assert r0.shape == (0, 3)
+    with pytest.raises(ValueError):
+        c.search(corpus[:1], "l2", 0)
+    with pytest.raises(NotImplementedError):
+        c.search(corpus[:1], "l2", 5000)
+    with pytest.raises(ValueError):
+        c.search(np.zeros((1, 5), np.float32), "l2", 3)
+    with pytest.raises(knn.FenixKnnError):
+        c.append(corpus)  # finalized
+    c.close()
+    # empty shard
+    e = knn.Corpus(ctx, 0, 12).finalize()
+    rows, dist = e.search(corpus[:2], "dot", 4)
+    assert (rows == -1).all() and np.isinf(dist).all()
+    e.close()
+    # zero vectors: cosine eps branch gives 0.5
+    z = np.zeros((4, 12), np.float32)
+    z[1] = 1
+    c = make_corpus(ctx, z)
+    rows, dist = c.search(np.zeros((1, 12), np.float32), "cosine", 4)
+    assert np.allclose(dist, 0.5) and rows[0].tolist() == [0, 1, 2, 3]
+    c.close()
+
+
+def test_row_base_and_sharded_merge_equal_single_shard(ctx):
+    """Fake 8-way row sharding on one GPU: shard-local top-k + fx_merge_topk == unsharded search."""
+    import torch
+    from fenix_b200.dist import shard_bounds
+
+    rng = np.random.default_rng(21)
+    corpus = rng.standard_normal((10007, 64), dtype=np.float32)
+    corpus[9000] = corpus[12]
+    queries = np.concatenate([rng.standard_normal((15, 64), dtype=np.float32), corpus[12:13]])
+    k, world = 10, 8
+    whole = make_corpus(ctx, corpus)
+    want_rows, want_dist = whole.search(queries, "l2", k)
+    parts_r, parts_d = [], []
+    for r in range(world):
+        lo, hi = shard_bounds(len(corpus), world, r)
+        s = make_corpus(ctx, corpus[lo:hi], row_base=lo)
+        rr, dd = s.search(queries, "l2", k)
+        assert rr.min() >= lo and rr.max() < hi
+        parts_r.append(rr)
+        parts_d.append(dd)
+        s.close()
+    dev = torch.device("cuda", 0)
+    g_rows = torch.from_numpy(np.stack(parts_r)).to(dev)
+    g_dist = torch.from_numpy(np.stack(parts_d)).to(dev)
+    out_rows = torch.empty((len(queries), k), dtype=torch.int64, device=dev)
+    out_dist = torch.empty((len(queries), k), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    ctx.merge_topk_device(g_rows.data_ptr(), g_dist.data_ptr(), world, len(queries), k, out_rows.data_ptr(), out_dist.data_ptr())
+    assert np.array_equal(out_rows.cpu().numpy(), want_rows)
+    assert np.array_equal(out_dist.cpu().numpy(), want_dist)
+    whole.close()
+
+
+def test_large_property_checks(ctx):
+    """BASELINE-sized shape (1M x 128, k = 100): size-independent properties instead of the oracle:
+    planted neighbours are found, results are sorted by (distance, row), sharding is invariant,
+    and the tensor-core path agrees with the fp64 scan on a query subset."""
+    import torch
+
+    n, d, nq, k = 1_000_000, 128, 256, 100
+    g = torch.Generator(device="cuda").manual_seed(1002)
+    x = torch.randn((n, d), generator=g, device="cuda", dtype=torch.float32)
+    q = torch.randn((nq, d), generator=g, device="cuda", dtype=torch.float32)
+    plant = torch.arange(nq, device="cuda") * 3001 + 5
+    x[plant] = q + 1e-3 * torch.randn((nq, d), generator=g, device="cuda")  # query i's nearest is row plant[i]
+    c = knn.Corpus(ctx, n, d)
+    torch.cuda.synchronize()
+    c.append_device(x.data_ptr(), n)
+    c.finalize()
+    qh = q.cpu().numpy()
+    rows, dist = c.search(qh, "l2", k)
+    assert np.array_equal(rows[:, 0], plant.cpu().numpy())
+    assert (np.diff(dist, axis=1) >= 0).all()
+    ties = np.diff(dist, axis=1) == 0
+    assert (np.diff(rows, axis=1)[ties] > 0).all()
+    sub = slice(0, 16)
+    rows_s, dist_s = c.search(qh[sub], "l2", k, knn.PREC_EXACT_SCAN)
+    assert np.array_equal(rows[sub], rows_s) and np.array_equal(dist[sub], dist_s)
+    for metric in ("cosine", "dot"):
+        r1, d1 = c.search(qh[sub], metric, 10)
+        r2, d2 = c.search(qh[sub], metric, 10, knn.PREC_EXACT_SCAN)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2)
+    c.close()
+
+
+# ---- through the reference-facing API ----------------------------------------------------
+def test_index_call_matches_oracle_table(ctx, tmp_path):
+    rng = np.random.default_rng(9)
+    corpus = rng.standard_normal((6000, 64), dtype=np.float32)
+    table = table_of(corpus, 1000)
+    root = str(tmp_path)
+    fenix.io.table.make(root, "test/table", table.to_reader())
+    from oracle import call as oracle_call
+
+    q = rng.standard_normal(64)  # float64 target is cast to the column type (index.py:110)
+    for metric in METRICS:
+        got = fenix.io.index.call(root, None, "test/table", "vector", q, metric=metric, maxval=10)
+        want = oracle_call(table, "vector", q, metric, maxval=10)
+        assert got.schema == want.schema
+        assert_same_neighbours(got.column("id").to_numpy(), got.column("__DISTANCE__").to_numpy(),
+                               want.column("id").to_numpy(), want.column("__DISTANCE__").to_numpy(),
+                               corpus, q.astype(np.float32), metric)
+        # gathered rows are the rows themselves
+        ids = got.column("id").to_numpy()
+        vec = np.stack(got.column("vector").to_numpy(zero_copy_only=False))
+        assert np.array_equal(vec, corpus[ids])
+    # maxval None -> all rows, table order; select; filter; multi-source
+    got = fenix.io.index.call(root, None, "test/table", "vector", q, metric="l2", select=["id"])
+    want = oracle_call(table, "vector", q, "l2", select=["id"])
+    assert got.schema == want.schema and got.num_rows == 6000
+    assert np.array_equal(got.column("id").to_numpy(), np.arange(6000))
+    np.testing.assert_allclose(got.column("__DISTANCE__").to_numpy(), want.column("__DISTANCE__").to_numpy(), rtol=1e-5)
+    flt = pc.field("id") >= 5990
+    got = fenix.io.index.call(root, None, "test/table", "vector", q, metric="l2", select=["id"], filter=flt, maxval=4)
+    want = oracle_call(table, "vector", q, "l2", select=["id"], filter=flt, maxval=4)
+    assert sorted(got.column("id").to_pylist()) == sorted(want.column("id").to_pylist())
+    got = fenix.io.index.call(root, None, "test/table", "vector", q, metric="l2", select=["id"], filter=flt, maxval=100)
+    assert got.column("id").to_pylist() == list(range(5990, 6000))  # <= maxval survivors: table order
+    both = fenix.io.index.call(root, None, ["test/table", "test/table"], "vector", q, metric="dot", select=["id"], maxval=6)
+    ids = both.column("id").to_pylist()
+    assert ids[0::2] == ids[1::2]  # each winner appears once per copy, ordered by (distance, row)
+    # cache invalidation: rewriting the table changes the answer
+    fenix.io.table.make(root, "test/table", table_of(-corpus, 1000).to_reader())
+    flipped = fenix.io.index.call(root, None, "test/table", "vector", q, metric="dot", select=["id"], maxval=1)
+    before = oracle_call(table_of(-corpus, 1000), "vector", q, "dot", select=["id"], maxval=1)
+    assert flipped.column("id").to_pylist() == before.column("id").to_pylist()
+
+
+class TestFlightDropIn:
+    """The reference's own acceptance test (tests/test_flight.py:42-50, 88-114, 151-154) re-run against
+    this package, plus result parity it does not check."""
+
+    VECTOR_SIZE, NUM_VECTORS, BATCH_SIZE, PORT = 256, 20_000, 1_000, 9137
+
+    @pytest.fixture(scope="class")
+    def served(self, tmp_path_factory, built_library):
+        root = str(tmp_path_factory.mktemp("fenix"))
+        server = fenix.Server(root, "127.0.0.1", self.PORT)
+        rng = np.random.default_rng(42)
+        parts = []
+        for _ in range(self.NUM_VECTORS // self.BATCH_SIZE):
+            x = rng.standard_normal((self.BATCH_SIZE, self.VECTOR_SIZE), dtype=np.float32)
+            parts.append(x + 10 * x[0, :])
+        corpus = np.concatenate(parts)
+        source = table_of(corpus, self.BATCH_SIZE)
+        client = fenix.Flight("127.0.0.1", self.PORT)
+        client.make_table("test/table", source.to_reader())
+        yield client, source, corpus
+        client.remove()
+        server.shutdown()
+
+    def test_make_table_roundtrip(self, served):
+        client, source, _ = served
+        assert client.read_table("test/table").read_all() == source
+
+    @pytest.mark.parametrize("metric", METRICS)
+    def test_search_without_index(self, served, metric):
+        client, source, corpus = served
+        target = pc.random(self.VECTOR_SIZE).cast(pa.float32())
+        result = client.search(target=target, source="test/table", column="vector", metric=metric, maxval=10)
+        assert result.num_rows == 10
+        assert result.schema == pa.schema([*source.schema, pa.field("__DISTANCE__", pa.float32())])
+        q = target.to_numpy()
+        ref_rows, ref_dist = search_rows(source, "vector", q, metric, 10)
+        assert_same_neighbours(result.column("id").to_numpy(), result.column("__DISTANCE__").to_numpy(),
+                               ref_rows, ref_dist, corpus, q, metric)
+
+    def test_batched_wire_extension(self, served):
+        client, source, corpus = served
+        rng = np.random.default_rng(1)
+        qs = rng.random((5, self.VECTOR_SIZE), dtype=np.float32)
+        out = client.search(qs, "test/table", "vector", "l2", select=["id"], maxval=3)
+        assert out.column_names == ["id", "__DISTANCE__", "__QUERY__"] and out.num_rows == 15
+        for qi in range(5):
+            one = client.search(qs[qi], "test/table", "vector", "l2", select=["id"], maxval=3)
+            sel = out.filter(pc.field("__QUERY__") == qi)
+            assert sel.column("id").to_pylist() == one.column("id").to_pylist()
+
+    def test_errors_surface_as_flight_errors(self, served):
+        import pyarrow.flight as fl
+
+        client, _, _ = served
+        with pytest.raises(fl.FlightServerError):
+            client.search(np.zeros(self.VECTOR_SIZE, np.float32), "nope", "vector", "l2", maxval=3)
+        with pytest.raises(AssertionError):
+            client.search(np.zeros(self.VECTOR_SIZE, np.float32), "test/table", "vector", "manhattan")

@@ -1,0 +1,140 @@
+"""CPU tests of the host-side mirror of the reference interface (no device work)."""
+import os
+import pickle
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+import fenix_b200 as fenix
+from conftest import table_of
+from fenix_b200.io import index as ix
+from fenix_b200.io import shards
+
+
+def test_public_surface_matches_reference():
+    # src/fenix/__init__.py:1-2 and the Flight client methods (flight.py:137-292)
+    for name in ("Flight", "Server", "io"):
+        assert hasattr(fenix, name)
+    for name in ("make_table", "read_table", "drop_table", "make_index", "sync_index", "drop_index", "search", "remove"):
+        assert callable(getattr(fenix.Flight, name))
+    import inspect
+
+    sig = inspect.signature(fenix.Flight.search)
+    assert list(sig.parameters) == ["self", "target", "source", "column", "metric", "coding", "select", "filter", "maxval", "probes"]
+    sig = inspect.signature(fenix.io.index.call)
+    assert list(sig.parameters)[:10] == ["root", "coding", "source", "column", "target", "metric", "select", "filter", "maxval", "probes"]
+    assert ix.DIST_COL == "__DISTANCE__" and ix.CODE_COL == "__CODED_ID__"
+
+
+def test_table_roundtrip_and_chunking(tmp_path):
+    corpus = np.random.default_rng(0).standard_normal((2500, 12), dtype=np.float32)
+    src = table_of(corpus, 1000)
+    out = fenix.io.table.make(str(tmp_path), "test/table", src.to_reader())
+    assert out == src
+    assert os.path.exists(tmp_path / "sources" / "test" / "table.arrow")
+    loaded = fenix.io.table.load(str(tmp_path), "test/table")
+    assert loaded.column("vector").num_chunks == 3  # writer's batch boundaries survive
+    both = fenix.io.table.load(str(tmp_path), ["test/table", "test/table"])
+    assert both.num_rows == 5000
+    assert sorted(fenix.io.table.list(str(tmp_path))) == ["test/table"]
+    fenix.io.table.drop(str(tmp_path), "test/table")
+    assert list(fenix.io.table.list(str(tmp_path))) == []
+
+
+def test_chunk_rows_is_zero_copy_and_honours_offset():
+    corpus = np.arange(40, dtype=np.float32).reshape(10, 4)
+    arr = table_of(corpus, 10).column("vector").chunk(0)
+    view = shards.chunk_rows(arr)
+    assert view.shape == (10, 4) and np.array_equal(view, corpus)
+    assert not view.flags.owndata
+    sl = arr.slice(3, 4)
+    assert np.array_equal(shards.chunk_rows(sl), corpus[3:7])
+    with pytest.raises(NotImplementedError):
+        shards.chunk_rows(pa.FixedSizeListArray.from_arrays(pa.array(np.zeros(8)), 4))  # float64 column
+
+
+def test_coerce_target_forms():
+    q = np.arange(6, dtype=np.float64)
+    typ = pa.list_(pa.float32(), 6)
+    forms = [q, q.astype(np.float32), pa.array(q), pa.chunked_array([pa.array(q[:2]), pa.array(q[2:])]),
+             pa.scalar(q.astype(np.float32), type=typ)]
+    import torch
+
+    forms.append(torch.from_numpy(q))
+    for f in forms:
+        out = ix.coerce_target(f, 6)
+        assert out.dtype == np.float32 and out.shape == (1, 6) and np.array_equal(out[0], q.astype(np.float32))
+    batch = ix.coerce_target(np.ones((3, 6)), 6)
+    assert batch.shape == (3, 6)
+    with pytest.raises(pa.ArrowInvalid):
+        ix.coerce_target(np.ones(5), 6)
+
+
+def test_row_mask_follows_expression():
+    corpus = np.zeros((10, 4), dtype=np.float32)
+    t = table_of(corpus, 4)
+    mask = ix._row_mask(t, "vector", pc.field("id") >= 6)
+    assert mask.tolist() == [0] * 6 + [1] * 4
+
+
+def test_ivf_branch_is_out_of_scope(tmp_path):
+    with pytest.raises(NotImplementedError):
+        fenix.io.index.call(str(tmp_path), "some-coding", "t", "vector", np.zeros(4), metric="l2", probes=4)
+
+
+def test_unknown_metric_is_value_error(tmp_path):
+    with pytest.raises(ValueError):
+        fenix.io.index.call(str(tmp_path), None, "t", "vector", np.zeros(4), metric="manhattan")
+
+
+def test_search_command_wire_format(monkeypatch):
+    """The descriptor is the reference's pickled dict (flight.py:258-271) and the request stream a
+    one-column table named `target` (flight.py:279)."""
+    import pyarrow.flight as fl
+
+    seen = {}
+
+    class FakeWriter:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def begin(self, schema):
+            seen["schema"] = schema
+
+        def write_table(self, t):
+            seen["table"] = t
+
+        def done_writing(self):
+            pass
+
+    class FakeReader:
+        def read_all(self):
+            return pa.table({"ok": [1]})
+
+    class FakeConn:
+        def do_exchange(self, descriptor):
+            seen["descriptor"] = descriptor
+            return FakeWriter(), FakeReader()
+
+        def close(self):
+            pass
+
+    client = fenix.Flight()
+    client.__dict__["conn"] = FakeConn()
+    flt = pc.field("id") > 3
+    client.search(np.arange(4, dtype=np.float32), "s", "vector", "l2", select=["id"], filter=flt, maxval=7)
+    cmd = pickle.loads(seen["descriptor"].command)
+    assert set(cmd) == {"coding", "source", "column", "metric", "select", "filter", "maxval", "probes"}
+    assert cmd["source"] == "s" and cmd["maxval"] == 7 and cmd["coding"] is None
+    assert pickle.loads(cmd["filter"]).equals(flt)
+    assert seen["table"].column_names == ["target"] and seen["table"].num_rows == 4
+    with pytest.raises(AssertionError):
+        client.search(np.zeros(4), "s", "vector", "manhattan")
+    # wire extension: 2-D target -> FixedSizeList column with Q rows
+    client.search(np.zeros((3, 4), dtype=np.float32), "s", "vector", "l2", maxval=2)
+    assert pa.types.is_fixed_size_list(seen["table"].schema.field("target").type) and seen["table"].num_rows == 3
