@@ -206,8 +206,10 @@ extern "C" int fx_corpus_create(fx_ctx* ctx, int64_t capacity_rows, int32_t dim,
   size_t rows_alloc = size_t(std::max<int64_t>(capacity_rows, 1));
   // the tensor-core tiles read whole 256-row boxes; TMA clips to the tensor bounds, no padding needed
   cudaError_t e = cudaMalloc(&c->X, rows_alloc * c->pitch * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&c->hx, rows_alloc * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&c->rx, rows_alloc * sizeof(float));
+  // norm terms are fetched in whole 256-entry tiles (1 KB bulk copies) by the tensor-core kernel
+  const size_t norm_alloc = ((rows_alloc + 255) / 256) * 256;
+  if (e == cudaSuccess) e = cudaMalloc(&c->hx, norm_alloc * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->rx, norm_alloc * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&c->max_n2_bits, sizeof(unsigned int));
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -219,6 +221,8 @@ extern "C" int fx_corpus_create(fx_ctx* ctx, int64_t capacity_rows, int32_t dim,
                 rows_alloc, c ? ((dim + 3) & ~3) : 0, ctx->device, cudaGetErrorString(e));
   }
   if (c->pitch != c->dim) FX_CUDA(cudaMemsetAsync(c->X, 0, rows_alloc * c->pitch * sizeof(float), ctx->upload));
+  FX_CUDA(cudaMemsetAsync(c->hx, 0, norm_alloc * sizeof(float), ctx->upload));
+  FX_CUDA(cudaMemsetAsync(c->rx, 0, norm_alloc * sizeof(float), ctx->upload));
   c->stats.dim = dim; c->stats.pitch = c->pitch;
   c->stats.device_bytes = int64_t(rows_alloc * (c->pitch + 2) * sizeof(float));
   *out = c;
@@ -434,7 +438,7 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
     s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
     s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = d_q; s.n_q = int(n_q); s.metric = metric; s.k = k;
     s.certify = precision == FX_PREC_FP32; s.out_rows = d_out_rows; s.out_dist = d_out_dist;
-    s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1;
+    s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.dbg = nullptr;
     std::string err;
     size_t need = fx::tc_scratch_bytes(&ctx->tc, s);
     FX_TRY(ctx->d_tc.ensure(need));
@@ -564,6 +568,36 @@ extern "C" int fx_distances(fx_corpus* c, const float* query, int32_t metric, fl
   FX_CUDA(cudaMemcpyAsync(ctx->h_dist.p, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   FX_CUDA(cudaStreamSynchronize(ctx->stream));
   std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
+  return FX_OK;
+}
+
+extern "C" int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, float* out_scores) {
+  if (!c || !queries || !out_scores) return fail(FX_EINVAL, "fx_debug_scores: NULL argument");
+  if (!c->finalized) return fail(FX_ESTATE, "fx_debug_scores: corpus is not finalized");
+  if (n_q < 1 || metric < 0 || metric > 2) return fail(FX_EINVAL, "fx_debug_scores: bad arguments");
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  if (!fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, 10, int(n_q)))
+    return fail(FX_EUNSUP, "fx_debug_scores: the tensor-core path does not cover this shard");
+  const size_t q_bytes = size_t(n_q) * c->dim * sizeof(float);
+  FX_TRY(ctx->d_q.ensure(q_bytes));
+  FX_TRY(ctx->d_rows.ensure(size_t(n_q) * 10 * sizeof(int64_t)));
+  FX_TRY(ctx->d_dist.ensure(size_t(n_q) * 10 * sizeof(float) + 128 * 256 * sizeof(float) + 256));
+  FX_CUDA(cudaMemcpyAsync(ctx->d_q.p, queries, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  float* d_dbg = reinterpret_cast<float*>(static_cast<char*>(ctx->d_dist.p) + ((size_t(n_q) * 10 * sizeof(float) + 255) & ~size_t(255)));
+  FX_CUDA(cudaMemsetAsync(d_dbg, 0, 128 * 256 * sizeof(float), ctx->stream));
+  fx::TcSearch s{};
+  s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
+  s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = static_cast<const float*>(ctx->d_q.p); s.n_q = int(n_q);
+  s.metric = metric; s.k = 10; s.certify = false; s.out_rows = static_cast<int64_t*>(ctx->d_rows.p);
+  s.out_dist = static_cast<float*>(ctx->d_dist.p); s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1;
+  s.dbg = d_dbg;
+  FX_TRY(ctx->d_tc.ensure(fx::tc_scratch_bytes(&ctx->tc, s)));
+  std::string err; int launched = 0;
+  if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err)) return fail(FX_ECUDA, "fx_debug_scores: %s", err.c_str());
+  FX_CUDA(cudaMemcpyAsync(out_scores, d_dbg, 128 * 256 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
   return FX_OK;
 }
 

@@ -1,25 +1,824 @@
-// tc_filter.cuh — tcgen05/TMEM TF32 filter + fp64 rerank path (host glue + kernels).
-// STUB for the first milestone: the tensor-core path reports "unsupported" so every search
-// runs the exact scan kernel. Replaced by the real kernels next.
+// tc_filter.cuh — the tensor-core path: tcgen05/TMEM TF32 GEMM with a fused threshold-filter
+// epilogue (no distance matrix ever reaches HBM), followed by an fp64 rerank + certificate.
+//
+//   knn_prep_kernel      pads queries to the TMA pitch, resets per-query state
+//   knn_tc_filter_kernel warp-specialised persistent kernel, one CTA per SM:
+//                          warp 0   TMA producer  (cp.async.bulk.tensor, 128B swizzle, 4 stages)
+//                          warp 1   MMA issuer    (tcgen05.mma kind::tf32, M=128 N=256 K=8, fp32 in TMEM)
+//                          warp 2   TMEM allocator
+//                          warps 4-11 epilogue    (tcgen05.ld 32x32b -> score -> compare with a
+//                                                  per-query running threshold in a register;
+//                                                  rare survivors are appended to an L2-resident
+//                                                  candidate buffer, warp-cooperative radix select
+//                                                  tightens the threshold)
+//   knn_tc_finish_kernel one CTA per query: top-K' of the surviving candidates by approximate score,
+//                        exact (fp64-accumulated) rerank, (distance,row) sort, certificate.
+//
+// Exactness argument (FX_PREC_FP32): every corpus row that is NOT a candidate has approximate
+// score s^ <= T; |s^ - s| <= E (rigorous TF32 rounding bound from |q|, max|x|, D); so its exact
+// distance is >= f(T + E). If the k-th reranked distance is strictly below that bound the top-k is
+// proven exact; otherwise the query is flagged and recomputed by the fp64 scan (exact_scan.cuh).
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
 #include <string>
+
 #include "common.cuh"
 
 namespace fx {
 
-struct TcState { int sm_count = 0; };
-struct TcCorpus { int dummy = 0; };
+// ---------------------------------------------------------------------------------------------
+// tile configuration
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;                 // queries per CTA tile (UMMA M, TMEM lanes)
+constexpr int TC_BN = 256;                 // corpus rows per accumulator (UMMA N)
+constexpr int TC_BK = 32;                  // fp32 elements per k-block = 128 B = one swizzle row
+constexpr int TC_UMMA_K = 8;               // kind::tf32: 32 bytes of K per instruction
+constexpr int TC_STAGES = 4;
+constexpr int TC_ACC_STAGES = 2;           // 2 x 256 TMEM columns = all 512
+constexpr int TC_THREADS = 384;            // 12 warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_FIRST_WARP = 4;
+constexpr int TC_HALF_COLS = TC_BN / 2;    // columns per epilogue warp-group
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr uint32_t TC_NORM_BYTES = TC_BN * 4;        // per accumulator stage
+constexpr uint32_t TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES +
+                                   TC_ACC_STAGES * TC_NORM_BYTES + 256 /*barriers*/;
+constexpr int TC_MAX_WAVES = 4;            // units per CTA at most (bounds the candidate-buffer scratch)
+constexpr uint32_t ORD_NEG_INF = 0x007fffffu;  // f2ord(-inf)
+
+struct TcState {
+  int sm_count = 0;
+  void* encode = nullptr;  // cuTensorMapEncodeTiled
+};
+struct TcCorpus {
+  CUtensorMap map_x;       // [n_rows][pitch] fp32, box 32 x 256, 128B swizzle
+  bool ok = false;
+};
 struct TcSearch {
   const float* X; const float* hx; const float* rx; int64_t n_rows; int dim; int pitch; int64_t row_base;
   float max_norm; const float* Q; int n_q; int metric; int k; bool certify;
   int64_t* out_rows; float* out_dist; cudaStream_t stream; cudaEvent_t ev_k0, ev_k1;
+  float* dbg;              // optional [128][256] raw score dump (diagnostics)
 };
 
-inline bool tc_init(TcState* st, int sm_count, std::string*) { st->sm_count = sm_count; return true; }
-inline bool tc_bind_corpus(TcState*, TcCorpus*, const float*, int64_t, int, int, std::string*) { return true; }
-inline bool tc_supported(const TcState*, const TcCorpus*, int64_t, int, int, int) { return false; }
-inline size_t tc_scratch_bytes(const TcState*, const TcSearch&) { return 0; }
-inline bool tc_search(TcState*, TcCorpus*, const TcSearch&, void*, int*, std::string* err) { *err = "tc path not built"; return false; }
-inline const int* tc_flags(const TcState*, const TcSearch&, void*) { return nullptr; }
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by one thread.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3ffffu) >> 4);        // start address        bits [0,14)
+  d |= uint64_t(1) << 16;                            // leading byte offset  (ignored for swizzled K-major)
+  d |= uint64_t(1024 >> 4) << 32;                    // stride byte offset   bits [32,46): 8 rows * 128 B
+  d |= uint64_t(1) << 46;                            // descriptor version 1 (sm_100)
+  d |= uint64_t(2) << 61;                            // layout: SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+  int n_q;                // queries
+  int n_qt;               // query tiles of 128
+  int64_t n_rows;         // corpus rows in the shard
+  int n_tiles;            // corpus tiles of 256 rows
+  int n_slices;           // corpus slices (units = n_slices * n_qt)
+  int tiles_per_slice;
+  int n_kblocks;          // ceil(pitch / 32)
+  int kp;                 // K': candidates kept per (query, unit-half) selection
+  int cap;                // candidate buffer capacity per epilogue thread (512 or 1024)
+  const float* hx;        // [n_rows padded to 256] -0.5|x|^2
+  const float* rx;        // [n_rows padded to 256] 1/max(|x|,eps)
+  uint2* wbuf;            // [units][256][cap] candidate buffers (score bits, row), one per (unit, epilogue thread)
+  int* wcnt;              // [units][256] entries left in each buffer when its unit finished
+  uint32_t* tau_g;        // [n_q] shared per-query threshold, ordered-uint encoding
+  float* dbg;             // diagnostics: raw scores of (query tile 0) x (corpus tile 0), [128][256], or null
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp-cooperative selection on one thread's candidate buffer
+// ---------------------------------------------------------------------------------------------
+// Keeps the kp best (largest score) of buf[0..cnt), compacted to the front; returns the kp-th best
+// score in ordered-uint form (the new admission threshold: everything dropped is <= it).
+template <int PER>
+__device__ __forceinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp, int& new_cnt) {
+  const uint32_t lane = lane_id();
+  uint32_t s[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int idx = i * 32 + int(lane);
+    s[i] = (idx < cnt) ? f2ord(__uint_as_float(buf[idx].x)) : 0u;
+  }
+  // radix descent: largest v with count(s >= v) >= kp
+  uint32_t v = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    uint32_t cand = v | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) c += (s[i] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= kp) v = cand;
+  }
+  int n_gt = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) n_gt += (s[i] > v) ? 1 : 0;
+  n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+  int ties_left = kp - n_gt;   // >= 1
+  int out = 0;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    if (i * 32 < cnt) {   // warp-uniform
+      int idx = i * 32 + int(lane);
+      uint2 e = (idx < cnt) ? buf[idx] : make_uint2(0u, 0u);
+      __syncwarp();
+      bool gt = s[i] > v;
+      bool tie = (idx < cnt) && (s[i] == v);
+      uint32_t tie_ballot = __ballot_sync(0xffffffffu, tie);
+      int tie_rank = __popc(tie_ballot & lt_mask);
+      bool keep = gt || (tie && tie_rank < ties_left);
+      ties_left -= min(ties_left, __popc(tie_ballot));
+      uint32_t keep_ballot = __ballot_sync(0xffffffffu, keep);
+      if (keep) buf[out + __popc(keep_ballot & lt_mask)] = e;
+      out += __popc(keep_ballot);
+      __syncwarp();
+    }
+  }
+  new_cnt = out;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the filter kernel
+// ---------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled operand tiles
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* tiles = smem;
+  float* norm_smem = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_ACC_STAGES * TC_NORM_BYTES);
+  uint64_t* full_bar = bars;                         // [TC_STAGES]   TMA -> MMA
+  uint64_t* empty_bar = bars + TC_STAGES;            // [TC_STAGES]   MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;        // [2]           MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + TC_ACC_STAGES;  // [2]           epilogue -> MMA / TMA(norms)
+  uint64_t* norm_full = tmem_empty + TC_ACC_STAGES;  // [2]           TMA(norms) -> epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + TC_ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_x);
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < TC_ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], TC_EPI_WARPS);
+      mbar_init(&norm_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_units = p.n_slices * p.n_qt;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int slice = u / p.n_qt, qt = u - slice * p.n_qt;
+        const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
+        for (int t = t0; t < t1; ++t) {
+          if (METRIC != 2) {
+            // per-column norm terms of this tile ride along, one buffer per accumulator stage
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            mbar_expect_tx(&norm_full[acc], TC_NORM_BYTES);
+            const float* src = (METRIC == 0 ? p.hx : p.rx) + size_t(t) * TC_BN;
+            bulk_load_1d(norm_smem + acc * TC_BN, src, TC_NORM_BYTES, &norm_full[acc]);
+          }
+          for (int kb = 0; kb < p.n_kblocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+            unsigned char* a_dst = tiles + stage * TC_STAGE_BYTES;
+            tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * TC_BK, qt * TC_BM);
+            tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * TC_BK, t * TC_BN);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int slice = u / p.n_qt;
+        const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * TC_BN);
+          for (int kb = 0; kb < p.n_kblocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(tiles + stage * TC_STAGE_BYTES);
+            const uint64_t a_desc = make_smem_desc(a_addr);
+            const uint64_t b_desc = make_smem_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              // advance 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+              umma_tf32(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[acc]);       // accumulator ready for the epilogue
+          if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= TC_EPI_FIRST_WARP) {
+    // ===================== epilogue: score, threshold filter, candidate buffers =====================
+    const int e = warp - TC_EPI_FIRST_WARP;
+    const int lane_grp = warp & 3;               // TMEM lanes this warp may touch: 32*lane_grp ..
+    const int half = e >> 2;                     // which 128 columns of the accumulator
+    const int row_in_tile = lane_grp * 32 + int(lane);
+    const int slot = half * TC_BM + row_in_tile; // candidate buffer of this thread
+    const uint32_t t_lane = tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(half * TC_HALF_COLS);
+    int acc = 0; uint32_t acc_phase = 0;
+
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int slice = u / p.n_qt, qt = u - slice * p.n_qt;
+      const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
+      const int q = qt * TC_BM + row_in_tile;
+      const bool active = q < p.n_q;
+      uint2* buf = p.wbuf + (size_t(u) * (2 * TC_BM) + slot) * p.cap;
+      int cnt = 0;
+      float tau = -INFINITY;
+
+      for (int t = t0; t < t1; ++t) {
+        if (active) tau = fmaxf(tau, ord2f(ld_relaxed_u32(p.tau_g + q)));
+        mbar_wait(&tmem_full[acc], acc_phase);
+        if (METRIC != 2) mbar_wait(&norm_full[acc], acc_phase);
+        tc_fence_after();
+        const int col0 = t * TC_BN + half * TC_HALF_COLS;                  // global row of column 0 of this half
+        const int ncols = int(min(int64_t(TC_HALF_COLS), p.n_rows - int64_t(col0)));  // valid columns (<=0: none)
+        const float* nrm = norm_smem + acc * TC_BN + half * TC_HALF_COLS;
+        if (__any_sync(0xffffffffu, active) && ncols > 0) {
+#pragma unroll 1
+          for (int c = 0; c < TC_HALF_COLS; c += 32) {
+            if (c >= ncols) break;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_lane + uint32_t(acc * TC_BN + c), v);
+            tmem_ld_wait();
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (METRIC != 2) n4 = *reinterpret_cast<const float4*>(nrm + c + j);
+              float s0 = __uint_as_float(v[j + 0]), s1 = __uint_as_float(v[j + 1]);
+              float s2 = __uint_as_float(v[j + 2]), s3 = __uint_as_float(v[j + 3]);
+              if (METRIC == 0) { s0 += n4.x; s1 += n4.y; s2 += n4.z; s3 += n4.w; }
+              if (METRIC == 1) { s0 *= n4.x; s1 *= n4.y; s2 *= n4.z; s3 *= n4.w; }
+              v[j + 0] = __float_as_uint(s0); v[j + 1] = __float_as_uint(s1);
+              v[j + 2] = __float_as_uint(s2); v[j + 3] = __float_as_uint(s3);
+              any |= (s0 > tau) | (s1 > tau) | (s2 > tau) | (s3 > tau);
+            }
+            if (p.dbg != nullptr && u == 0 && t == t0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) p.dbg[row_in_tile * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
+            }
+            if (any && active) {
+              const int lim = min(32, ncols - c);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float s = __uint_as_float(v[j]);
+                if (j < lim && s > tau) { buf[cnt] = make_uint2(v[j], uint32_t(col0 + c + j)); ++cnt; }
+              }
+            }
+          }
+        }
+        // release the accumulator stage (and its norm buffer) back to the MMA / TMA warps
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+
+        __syncwarp();
+        // tighten thresholds: a lane whose buffer could overflow next tile, or that holds >= K'
+        // candidates but no threshold yet, gets a warp-cooperative selection
+        bool need = active && ((cnt > p.cap - TC_HALF_COLS) || (tau == -INFINITY && cnt >= p.kp));
+        uint32_t need_mask = __ballot_sync(0xffffffffu, need);
+        while (need_mask) {
+          const int src = __ffs(need_mask) - 1;
+          need_mask &= need_mask - 1;
+          uint2* b = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
+          const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+          int new_cnt;
+          uint32_t v_ord = (p.cap == 1024) ? warp_select_compact<32>(b, c_src, p.kp, new_cnt)
+                                           : warp_select_compact<16>(b, c_src, p.kp, new_cnt);
+          if (int(lane) == src) {
+            cnt = new_cnt;
+            tau = fmaxf(tau, ord2f(v_ord));
+            atomicMax(p.tau_g + q, v_ord);
+          }
+        }
+      }
+
+      // end of unit: the finish kernel reads the buffer in place
+      p.wcnt[size_t(u) * (2 * TC_BM) + slot] = active ? cnt : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// query preparation: pad to the TMA pitch, reset per-query state
+// ---------------------------------------------------------------------------------------------
+__global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, int pitch, float* __restrict__ Qp,
+                                uint32_t* __restrict__ tau_g, int* __restrict__ flags) {
+  const int64_t total = int64_t(n_q) * pitch;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    int q = int(i / pitch), d = int(i - int64_t(q) * pitch);
+    Qp[i] = d < dim ? Q[size_t(q) * dim + d] : 0.f;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += gridDim.x * blockDim.x) {
+    tau_g[i] = ORD_NEG_INF; flags[i] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finish: select K' by approximate score, exact rerank, sort, certificate
+// ---------------------------------------------------------------------------------------------
+struct FinishParams {
+  const float* X; int pitch; int dim; int64_t row_base;
+  const float* Qp; int n_q; int n_qt; int n_slices; int cap; int metric; int k; int kp; int sort2;  // sort2: pow2 >= kp
+  const uint32_t* tau_g; const uint2* wbuf; const int* wcnt;
+  int* flags; int certify; float max_norm; double c_err;
+  int64_t* out_rows; float* out_dist;
+};
+
+// One CTA per query. The query's candidates live in 2 * n_slices buffers (one per unit-half).
+//  1. block-wide radix select (4 passes of 8 bits over the ordered score bits) finds the K'-th best
+//     approximate score among the entries above the final shared threshold;
+//  2. the <= K' winners are re-ranked exactly (fp64 accumulation, one warp per candidate);
+//  3. bitonic sort by (distance, row), write top-k, evaluate the certificate.
+__global__ void __launch_bounds__(256)
+knn_tc_finish_kernel(FinishParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys2 = reinterpret_cast<uint64_t*>(smem_raw);                 // [sort2] (distance,row) keys
+  uint32_t* cand = reinterpret_cast<uint32_t*>(keys2 + p.sort2);           // [sort2] candidate rows
+  float* qs = reinterpret_cast<float*>(cand + p.sort2);                    // [pitch]
+  __shared__ int hist[256];
+  __shared__ int s_n_gt, s_n_tie, s_total;
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  __shared__ double s_qq;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_warps = blockDim.x >> 5;
+  const int qt = q / TC_BM, r = q - qt * TC_BM;
+  const int n_lists = 2 * p.n_slices;
+
+  for (int d = tid; d < p.pitch; d += blockDim.x) qs[d] = p.Qp[size_t(q) * p.pitch + d];
+  if (tid == 0) { s_n_gt = 0; s_n_tie = 0; s_prefix = 0; s_remaining = p.kp; }
+  __syncthreads();
+  if (warp == 0) {
+    double s = 0.0;
+    for (int d = lane; d < p.pitch; d += 32) s = fma(double(qs[d]), double(qs[d]), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_qq = s;
+  }
+  const uint32_t tg = p.tau_g[q];
+
+  // list l = (slice, half): buffer of thread slot half*128 + r of unit slice*n_qt + qt
+  auto list_ptr = [&](int l, int& count) -> const uint2* {
+    const int slice = l >> 1, half = l & 1;
+    const size_t unit_slot = (size_t(slice) * p.n_qt + qt) * (2 * TC_BM) + half * TC_BM + r;
+    count = p.wcnt[unit_slot];
+    return p.wbuf + unit_slot * p.cap;
+  };
+
+  // ---- 1. radix select of the kp-th largest ordered score among entries > tg ----
+  uint32_t prefix = 0, mask = 0;
+  bool keep_all = false;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int l = warp; l < n_lists; l += n_warps) {
+      int count; const uint2* b = list_ptr(l, count);
+      for (int i = lane; i < count; i += 32) {
+        uint32_t o = f2ord(__uint_as_float(b[i].x));
+        if (o > tg && (o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 0xffu], 1);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int remaining = s_remaining;
+      if (pass == 0) {
+        int total = 0;
+        for (int b = 0; b < 256; ++b) total += hist[b];
+        s_total = total;
+      }
+      if (pass == 0 && s_total <= p.kp) {
+        s_remaining = -1;  // keep everything above tg
+      } else {
+        int cum = 0, b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= remaining) break;
+          cum += hist[b];
+        }
+        s_prefix = prefix | (uint32_t(b) << shift);
+        s_remaining = remaining - cum;
+      }
+    }
+    __syncthreads();
+    if (s_remaining < 0) { keep_all = true; break; }
+    prefix = s_prefix;
+    mask |= 0xffu << shift;
+  }
+  const uint32_t pivot = keep_all ? tg : prefix;          // kp-th best ordered score (or the threshold)
+  const int ties_wanted = keep_all ? 0 : s_remaining;      // entries == pivot still admitted
+
+  // ---- collect winners: score > pivot, plus `ties_wanted` entries equal to the pivot ----
+  for (int l = warp; l < n_lists; l += n_warps) {
+    int count; const uint2* b = list_ptr(l, count);
+    for (int i = lane; i < count; i += 32) {
+      uint2 ent = b[i];
+      uint32_t o = f2ord(__uint_as_float(ent.x));
+      if (o > pivot) {
+        int pos = atomicAdd(&s_n_gt, 1);
+        if (pos < p.sort2) cand[pos] = ent.y;
+      } else if (!keep_all && o == pivot) {
+        int t = atomicAdd(&s_n_tie, 1);
+        if (t < ties_wanted) cand[p.kp - 1 - t] = ent.y;    // ties fill the tail of the kp slots
+      }
+    }
+  }
+  __syncthreads();
+  // winners occupy cand[0, n_gt) and (when a pivot exists) cand[kp - n_tie_kept, kp)
+  const int n_gt = min(s_n_gt, p.sort2);
+  const int n_tie_kept = keep_all ? 0 : min(s_n_tie, ties_wanted);
+  const int n_cand = n_gt + n_tie_kept;
+
+  // ---- 2. exact rerank: one warp per candidate, fp64 accumulation of exact fp32 products ----
+  const double qq = s_qq;
+  for (int c = warp; c < p.sort2; c += n_warps) {
+    uint64_t out_key = KEY_PAD;
+    const bool is_gt = c < n_gt;
+    const bool is_tie = !keep_all && c >= p.kp - n_tie_kept && c < p.kp;
+    if (is_gt || is_tie) {
+      const uint32_t row = cand[c];
+      const float4* xp = reinterpret_cast<const float4*>(p.X + size_t(row) * p.pitch);
+      double xx = 0.0, qx = 0.0;
+      for (int j = lane; j < (p.pitch >> 2); j += 32) {
+        float4 xv = __ldg(xp + j);
+        float4 qv = *reinterpret_cast<const float4*>(qs + 4 * j);
+        xx = fma(double(xv.x), double(xv.x), xx); qx = fma(double(xv.x), double(qv.x), qx);
+        xx = fma(double(xv.y), double(xv.y), xx); qx = fma(double(xv.y), double(qv.y), qx);
+        xx = fma(double(xv.z), double(xv.z), xx); qx = fma(double(xv.z), double(qv.z), qx);
+        xx = fma(double(xv.w), double(xv.w), xx); qx = fma(double(xv.w), double(qv.w), qx);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+        qx += __shfl_xor_sync(0xffffffffu, qx, o);
+      }
+      out_key = make_key(finish_distance(p.metric, qq, xx, qx), row);
+    }
+    if (lane == 0) keys2[c] = out_key;
+  }
+  __syncthreads();
+  // ---- 3. sort by (distance, row), output, certificate ----
+  for (int size = 2; size <= p.sort2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (p.sort2 >> 1); i += blockDim.x) {
+        int pos = 2 * i - (i & (stride - 1));
+        int j = pos + stride;
+        bool up = (pos & size) == 0;
+        uint64_t a = keys2[pos], b = keys2[j];
+        if ((a > b) == up) { keys2[pos] = b; keys2[j] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < p.k; i += blockDim.x) {
+    uint64_t key = (i < p.sort2) ? keys2[i] : KEY_PAD;
+    bool pad = key == KEY_PAD;
+    p.out_rows[size_t(q) * p.k + i] = pad ? int64_t(-1) : p.row_base + int64_t(key & 0xffffffffull);
+    p.out_dist[size_t(q) * p.k + i] = pad ? __int_as_float(0x7f800000) : ord2f(uint32_t(key >> 32));
+  }
+  if (tid == 0) {
+    int flag = 0;
+    if (p.certify) {
+      // every row that is not a candidate has approximate score <= T
+      const float t_score = ord2f(pivot);
+      const double nq = sqrt(qq);
+      const double xm = double(p.max_norm);
+      double e_abs, lb;
+      if (p.metric == 0) {
+        e_abs = p.c_err * nq * xm + 4.8e-7 * (0.5 * xm * xm + nq * xm);
+        double d2 = qq - 2.0 * (double(t_score) + e_abs);
+        lb = sqrt(d2 > 0.0 ? d2 : 0.0);
+      } else if (p.metric == 1) {
+        e_abs = nq * (p.c_err + 1e-6);
+        lb = 0.5 - 0.5 * (double(t_score) + e_abs) / (nq > 1e-12 ? nq : 1e-12);
+      } else {
+        e_abs = p.c_err * nq * xm;
+        lb = -(double(t_score) + e_abs);
+      }
+      lb = lb - 1e-6 * fabs(lb) - 1e-37;
+      bool ok = false;
+      if (n_cand >= p.k && s_n_gt <= p.sort2) {
+        float dk = ord2f(uint32_t(keys2[p.k - 1] >> 32));
+        ok = double(dk) < lb;   // NaN compares false -> flagged
+      }
+      flag = ok ? 0 : 1;
+    }
+    p.flags[q] = flag;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host glue
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline bool tc_encode_2d(const TcState* st, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                         uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer, std::string* err) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(st->encode)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r));
+    return false;
+  }
+  return true;
+}
+
+inline bool tc_init(TcState* st, int sm_count, std::string* err) {
+  st->sm_count = sm_count;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    *err = std::string("cuTensorMapEncodeTiled entry point unavailable: ") + cudaGetErrorString(e);
+    return false;
+  }
+  st->encode = fn;
+  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (a != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(tc kernels) failed: ") + cudaGetErrorString(a); return false; }
+  return true;
+}
+
+inline bool tc_bind_corpus(TcState* st, TcCorpus* tc, const float* X, int64_t n_rows, int dim, int pitch, std::string* err) {
+  (void)dim;
+  tc->ok = false;
+  if (n_rows < 1) return true;
+  if (!tc_encode_2d(st, &tc->map_x, X, uint64_t(pitch), uint64_t(n_rows), uint64_t(pitch), TC_BK, TC_BN, err)) return false;
+  tc->ok = true;
+  return true;
+}
+
+// K' (candidates kept by each selection) and the buffer capacity that goes with it
+inline int tc_kp(int k, bool certify) {
+  int kp = certify ? k + std::max(16, k / 2) : k;
+  return (kp + 31) & ~31;
+}
+inline int tc_cap(int kp) { return kp <= 128 ? 512 : 1024; }
+
+inline bool tc_supported(const TcState* st, const TcCorpus* tc, int64_t n_rows, int dim, int k, int n_q) {
+  (void)n_q;
+  if (!st->encode || !tc->ok) return false;
+  if (dim > 8192) return false;                   // finish kernel stages the query in shared memory
+  if (k > 320) return false;                      // K' <= 512 so that a 1024-entry buffer keeps room to append
+  if (n_rows < 4096 || n_rows < 8 * int64_t(k)) return false;  // tiny shards: the scan is already instant
+  if (n_rows > int64_t(0x7fffff00)) return false; // 32-bit tile arithmetic
+  return true;
+}
+
+struct TcPlan {
+  int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks;
+  size_t off_qp, off_tau, off_flags, off_wcnt, off_wbuf, total;
+};
+
+inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
+  TcPlan pl{};
+  pl.n_qt = (s.n_q + TC_BM - 1) / TC_BM;
+  pl.n_tiles = int((s.n_rows + TC_BN - 1) / TC_BN);
+  pl.kp = tc_kp(s.k, s.certify);
+  pl.cap = tc_cap(pl.kp);
+  pl.n_kblocks = (s.pitch + TC_BK - 1) / TC_BK;
+  // Slices: units = n_slices * n_qt are dealt round-robin to min(units, #SM) persistent CTAs.
+  // Maximise SM utilisation units / (G * ceil(units / G)); few slices are preferred (longer units give
+  // tighter thresholds and fewer candidate lists), and every unit should span enough tiles for its
+  // threshold to become selective.
+  const int sms = st->sm_count;
+  const int min_tiles = std::max(4, (8 * pl.kp + TC_BN - 1) / TC_BN);
+  const int s_cap = std::max(1, (TC_MAX_WAVES * sms) / pl.n_qt);
+  const int s_max = std::max(1, std::min(pl.n_tiles / min_tiles, s_cap));
+  double best = -1.0; int best_s = 1;
+  for (int sl = 1; sl <= s_max; ++sl) {
+    int tps = (pl.n_tiles + sl - 1) / sl;
+    int eff_s = (pl.n_tiles + tps - 1) / tps;
+    if (eff_s != sl) continue;
+    long units = long(sl) * pl.n_qt;
+    long g = std::min<long>(units, sms);
+    double eff = double(units) / double(sms * ((units + g - 1) / g));
+    if (eff > best + 0.02) { best = eff; best_s = sl; }
+  }
+  pl.n_slices = best_s;
+  pl.tiles_per_slice = (pl.n_tiles + best_s - 1) / best_s;
+  pl.units = pl.n_slices * pl.n_qt;
+  pl.grid = int(std::min<long>(pl.units, sms));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  pl.off_qp = take(size_t(s.n_q) * s.pitch * 4);
+  pl.off_tau = take(size_t(s.n_q) * 4);
+  pl.off_flags = take(size_t(s.n_q) * 4);
+  pl.off_wcnt = take(size_t(pl.units) * 2 * TC_BM * 4);
+  pl.off_wbuf = take(size_t(pl.units) * 2 * TC_BM * pl.cap * 8);
+  pl.total = off;
+  return pl;
+}
+
+inline size_t tc_scratch_bytes(const TcState* st, const TcSearch& s) { return tc_plan(st, s).total; }
+inline const int* tc_flags(const TcState* st, const TcSearch& s, void* scratch) {
+  return reinterpret_cast<const int*>(static_cast<char*>(scratch) + tc_plan(st, s).off_flags);
+}
+// rigorous bound constant of the TF32 dot product: |acc - <q,x>| <= c * |q| * |x|
+// (operands truncated to 10 mantissa bits: 2^-10 each -> 2^-9 on the product, 25% margin;
+//  fp32 accumulation of D terms: D * 2^-21)
+inline double tc_c_err(int dim) { return 1.25 * std::ldexp(1.0, -9) + double(dim) * std::ldexp(1.0, -21); }
+
+inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratch, int* launched, std::string* err) {
+  const TcPlan pl = tc_plan(st, s);
+  char* base = static_cast<char*>(scratch);
+  float* qp = reinterpret_cast<float*>(base + pl.off_qp);
+  uint32_t* tau_g = reinterpret_cast<uint32_t*>(base + pl.off_tau);
+  int* flags = reinterpret_cast<int*>(base + pl.off_flags);
+  int* wcnt = reinterpret_cast<int*>(base + pl.off_wcnt);
+  uint2* wbuf = reinterpret_cast<uint2*>(base + pl.off_wbuf);
+
+  CUtensorMap map_q;
+  if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(s.n_q), uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
+
+  const int prep_blocks = int(std::min<int64_t>((int64_t(s.n_q) * s.pitch + 255) / 256, 4 * 148));
+  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags);
+
+  TcParams p{};
+  p.n_q = s.n_q; p.n_qt = pl.n_qt; p.n_rows = s.n_rows; p.n_tiles = pl.n_tiles; p.n_slices = pl.n_slices;
+  p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.kp = pl.kp; p.cap = pl.cap;
+  p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
+  cudaEventRecord(s.ev_k0, s.stream);
+  if (s.metric == 0) knn_tc_filter_kernel<0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+  else if (s.metric == 1) knn_tc_filter_kernel<1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+  else knn_tc_filter_kernel<2><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+  cudaEventRecord(s.ev_k1, s.stream);
+
+  FinishParams f{};
+  f.X = s.X; f.pitch = s.pitch; f.dim = s.dim; f.row_base = s.row_base; f.Qp = qp; f.n_q = s.n_q; f.n_qt = pl.n_qt;
+  f.n_slices = pl.n_slices; f.cap = pl.cap; f.metric = s.metric; f.k = s.k; f.kp = pl.kp;
+  int sort2 = 2; while (sort2 < pl.kp) sort2 <<= 1;
+  f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.flags = flags; f.certify = s.certify ? 1 : 0;
+  f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
+  const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + 16;
+  knn_tc_finish_kernel<<<s.n_q, 256, fin_smem, s.stream>>>(f);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("tensor-core path launch failed: ") + cudaGetErrorString(e); return false; }
+  *launched = 3;
+  return true;
+}
 
 }  // namespace fx

@@ -36,7 +36,7 @@ METRICS = {"l2": 0, "euclidean": 0, "cosine": 1, "dot": 2, "inner_product": 2}
 ABI_SYMBOLS = (
     "fx_init", "fx_shutdown", "fx_corpus_create", "fx_corpus_append", "fx_corpus_append_device",
     "fx_corpus_finalize", "fx_corpus_destroy", "fx_search", "fx_search_device", "fx_distances",
-    "fx_merge_topk", "fx_get_stats", "fx_last_error", "fx_abi_version",
+    "fx_merge_topk", "fx_get_stats", "fx_debug_scores", "fx_last_error", "fx_abi_version",
 )
 
 
@@ -118,6 +118,7 @@ def load_library() -> ctypes.CDLL:
         lib.fx_distances.argtypes = [vp, vp, i32, vp]
         lib.fx_merge_topk.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp]
         lib.fx_get_stats.argtypes = [vp, ctypes.POINTER(_FxStats)]
+        lib.fx_debug_scores.argtypes = [vp, vp, i64, i32, vp]
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
             if name not in ("fx_last_error",):
@@ -248,6 +249,14 @@ class Corpus:
             raise ValueError(f"expected a query of {self.dim} values, got {q.size}")
         out = np.empty(self.n_rows, dtype=np.float32)
         _check(self._lib, self._lib.fx_distances(self._h, q.ctypes.data, m, out.ctypes.data))
+        return out
+
+    def debug_scores(self, queries: np.ndarray, metric: str | int) -> np.ndarray:
+        """Raw tensor-core filter scores, first 128 queries x first 256 rows (diagnostics)."""
+        m = metric if isinstance(metric, int) else metric_code(metric)
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        out = np.zeros((128, 256), dtype=np.float32)
+        _check(self._lib, self._lib.fx_debug_scores(self._h, q.ctypes.data, q.shape[0], m, out.ctypes.data))
         return out
 
     # ---- introspection ----

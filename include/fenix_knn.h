@@ -141,6 +141,12 @@ int fx_merge_topk(fx_ctx* ctx, const int64_t* d_rows, const float* d_dist, int32
 /* ---- introspection --------------------------------------------------------------------- */
 
 int fx_get_stats(fx_corpus* c, fx_stats* out);
+
+/* Diagnostics: raw tensor-core filter scores of the first min(n_q,128) queries (HOST) against the
+ * first 256 shard rows, out_scores[128*256] row-major (query, row). Scores are the filter's ranking
+ * quantity: l2  <q,x> - 0.5|x|^2, cosine  <q,x>/max(|x|,eps), ip  <q,x>. Used by the tests to check the
+ * TF32 error bound the exactness certificate relies on. */
+int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, float* out_scores);
 const char* fx_last_error(void);
 int fx_abi_version(void);
 

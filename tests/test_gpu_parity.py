@@ -229,6 +229,48 @@ def test_large_property_checks(ctx):
     c.close()
 
 
+def test_tensor_core_path_runs_and_certifies(ctx):
+    """fp32 mode must take the tcgen05 path on ordinary data (no silent fallback to the scan) and the
+    certificate must hold for (nearly) every query; tf32 mode reports its recall."""
+    rng = np.random.default_rng(77)
+    corpus = rng.standard_normal((60000, 128), dtype=np.float32)
+    queries = rng.standard_normal((300, 128), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    for metric in ("l2", "cosine", "dot"):
+        before = c.stats()
+        rows, dist = c.search(queries, metric, 10, knn.PREC_FP32)
+        after = c.stats()
+        assert after.last_path == 1, "tensor-core path not taken"
+        assert after.fallback_queries - before.fallback_queries <= 3, "certificate fails on gaussian data"
+        rows_s, dist_s = c.search(queries, metric, 10, knn.PREC_EXACT_SCAN)
+        assert c.stats().last_path == 0
+        assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
+        rows_t, dist_t = c.search(queries, metric, 10, knn.PREC_TF32)
+        recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(rows, rows_t)])
+        assert recall >= 0.99, recall
+    c.close()
+
+
+@pytest.mark.parametrize("dim", [32, 100, 128, 768])
+def test_tf32_error_bound_of_the_certificate(ctx, dim):
+    """|filter score - exact score| <= c * |q| * |x| with c = 1.25 * 2^-9 + D * 2^-21 (tc_filter.cuh)."""
+    rng = np.random.default_rng(dim)
+    corpus = rng.standard_normal((8192, dim), dtype=np.float32) * rng.uniform(0.1, 10, (8192, 1)).astype(np.float32)
+    queries = rng.standard_normal((128, dim), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    x = corpus[:256].astype(np.float64)
+    q = queries.astype(np.float64)
+    qn, xn = np.linalg.norm(q, axis=1)[:, None], np.linalg.norm(x, axis=1)[None, :]
+    cerr = 1.25 * 2.0 ** -9 + dim * 2.0 ** -21
+    exact = {"dot": q @ x.T, "l2": q @ x.T - 0.5 * xn ** 2, "cosine": (q @ x.T) / np.maximum(xn, 1e-12)}
+    scale = {"dot": qn * xn, "l2": qn * xn + 2.0 ** -22 * (0.5 * xn ** 2 + qn * xn), "cosine": qn * np.ones_like(xn)}
+    for metric in ("dot", "l2", "cosine"):
+        s = c.debug_scores(queries, metric).astype(np.float64)
+        ratio = np.abs(s - exact[metric]) / (cerr * scale[metric])
+        assert ratio.max() < 0.5, (metric, ratio.max())  # observed ~0.2: the bound has 2x+ headroom
+    c.close()
+
+
 # ---- through the reference-facing API ----------------------------------------------------
 def test_index_call_matches_oracle_table(ctx, tmp_path):
     rng = np.random.default_rng(9)
