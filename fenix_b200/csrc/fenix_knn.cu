@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -92,7 +93,7 @@ struct fx_ctx {
   cudaStream_t upload = nullptr;   // H2D of corpus chunks
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   std::mutex mu;                   // one search at a time per device context
-  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc;
+  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref;
   HostBuf h_q, h_rows, h_dist, h_flags;
   int64_t launches = 0;
   fx::TcState tc;                  // driver entry points / kernel attributes of the TC path
@@ -105,6 +106,8 @@ struct fx_corpus {
   int64_t cap = 0, n = 0, row_base = 0;
   int dim = 0, pitch = 0;
   float* X = nullptr;
+  void* Xb = nullptr;              // optional bf16 shadow of X for the bf16 filter ([n][pitch_b])
+  int pitch_b = 0;
   float* hx = nullptr;
   float* rx = nullptr;
   unsigned int* max_n2_bits = nullptr;
@@ -180,7 +183,7 @@ extern "C" int fx_shutdown(fx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->upload);
   ctx->d_q.release(); ctx->d_rows.release(); ctx->d_dist.release(); ctx->d_mask.release();
-  ctx->d_partial.release(); ctx->d_qlist.release(); ctx->d_tc.release();
+  ctx->d_partial.release(); ctx->d_qlist.release(); ctx->d_tc.release(); ctx->d_ref.release();
   ctx->h_q.release(); ctx->h_rows.release(); ctx->h_dist.release(); ctx->h_flags.release();
   cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_stop);
   cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
@@ -306,9 +309,30 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
   for (int i = 0; i < 2; ++i) {
     if (c->ring[i]) { cudaFreeHost(c->ring[i]); c->ring[i] = nullptr; cudaEventDestroy(c->ring_ev[i]); c->ring_ev[i] = nullptr; }
   }
+  // bf16 shadow: the exact (fp32) mode then filters with 2x-rate bf16 MMAs. Built when the tensor pipe is the
+  // limiter (D >= 256) or when FENIX_BF16_SHADOW=1; FENIX_BF16_SHADOW=0 disables it.
+  {
+    const char* e = std::getenv("FENIX_BF16_SHADOW");
+    bool want = e ? std::atoi(e) != 0 : c->dim >= 256;
+    if (want && c->n >= 4096) {
+      c->pitch_b = (c->dim + 7) & ~7;
+      cudaError_t me = cudaMalloc(&c->Xb, size_t(c->n) * c->pitch_b * 2);
+      if (me != cudaSuccess) { cudaGetLastError(); c->Xb = nullptr; }   // not fatal: the TF32 filter needs no shadow
+      if (c->Xb) {
+        const int64_t total = c->n * int64_t(c->pitch_b / 2);
+        int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
+        fx::to_bf16_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim,
+                                                                 static_cast<__nv_bfloat16*>(c->Xb), c->pitch_b);
+        FX_CUDA(cudaGetLastError());
+        FX_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->launches++; c->stats.kernel_launches++;
+        c->stats.device_bytes += int64_t(size_t(c->n) * c->pitch_b * 2);
+      }
+    }
+  }
   {
     std::string err;
-    if (!fx::tc_bind_corpus(&ctx->tc, &c->tc, c->X, c->n, c->dim, c->pitch, &err))
+    if (!fx::tc_bind_corpus(&ctx->tc, &c->tc, c->X, c->n, c->dim, c->pitch, c->Xb, c->pitch_b, &err))
       return fail(FX_ECUDA, "fx_corpus_finalize: %s", err.c_str());
   }
   c->stats.n_rows = c->n;
@@ -327,6 +351,7 @@ extern "C" int fx_corpus_destroy(fx_corpus* c) {
     if (c->ring[i]) { cudaFreeHost(c->ring[i]); cudaEventDestroy(c->ring_ev[i]); }
   }
   if (c->X) cudaFree(c->X);
+  if (c->Xb) cudaFree(c->Xb);
   if (c->hx) cudaFree(c->hx);
   if (c->rx) cudaFree(c->rx);
   if (c->max_n2_bits) cudaFree(c->max_n2_bits);
@@ -415,7 +440,7 @@ static int check_search_args(fx_corpus* c, const void* q, int64_t n_q, int metri
   if (metric < 0 || metric > 2) return fail(FX_EINVAL, "fx_search: unknown metric %d", metric);
   if (k < 1) return fail(FX_EINVAL, "fx_search: k must be >= 1 (got %d)", k);
   if (k > 2048) return fail(FX_EUNSUP, "fx_search: k = %d exceeds the supported maximum of 2048", k);
-  if (precision != FX_PREC_FP32 && precision != FX_PREC_TF32 && precision != FX_PREC_EXACT_SCAN)
+  if (precision != FX_PREC_FP32 && precision != FX_PREC_TF32 && precision != FX_PREC_BF16 && precision != FX_PREC_EXACT_SCAN)
     return fail(FX_EINVAL, "fx_search: unknown precision mode %d", precision);
   return FX_OK;
 }
@@ -438,7 +463,11 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
     s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
     s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = d_q; s.n_q = int(n_q); s.metric = metric; s.k = k;
     s.certify = precision == FX_PREC_FP32; s.out_rows = d_out_rows; s.out_dist = d_out_dist;
-    s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.dbg = nullptr;
+    s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.dbg = nullptr; s.tau_fixed = nullptr;
+    // operand kind of the filter: exact mode takes the bf16 shadow when the shard has one
+    s.pitch_b = c->pitch_b;
+    s.kind = (precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && c->tc.ok_b && !std::getenv("FENIX_FP32_FILTER_TF32"))) ? 1 : 0;
+    if (s.kind == 1 && !c->tc.ok_b) return fail(FX_ESTATE, "fx_search: FX_PREC_BF16 needs the bf16 shadow (FENIX_BF16_SHADOW=1 at finalize)");
     std::string err;
     size_t need = fx::tc_scratch_bytes(&ctx->tc, s);
     FX_TRY(ctx->d_tc.ensure(need));
@@ -454,7 +483,55 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
       FX_CUDA(cudaStreamSynchronize(ctx->stream));
       std::vector<int> bad;
       for (int64_t i = 0; i < n_q; ++i) if (h_flags[i]) bad.push_back(int(i));
+      if (!bad.empty() && !std::getenv("FENIX_NO_REFINE")) {
+        // tier 1: second filter pass for the flagged queries only, with the admission threshold preset from
+        // their k-th distance minus the error bound; every survivor is reranked, so the result is exact
+        const int n_f = int(bad.size());
+        FX_TRY(ctx->d_qlist.ensure(size_t(n_f) * sizeof(int)));
+        FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), size_t(n_f) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+        const size_t o_q = take(size_t(n_f) * c->dim * 4), o_tau = take(size_t(n_f) * 4);
+        const size_t o_rows = take(size_t(n_f) * k * 8), o_dist = take(size_t(n_f) * k * 4);
+        FX_TRY(ctx->d_ref.ensure(off));
+        char* rb = static_cast<char*>(ctx->d_ref.p);
+        float* q_r = reinterpret_cast<float*>(rb + o_q);
+        uint32_t* tau_fixed = reinterpret_cast<uint32_t*>(rb + o_tau);
+        int64_t* rows2 = reinterpret_cast<int64_t*>(rb + o_rows);
+        float* dist2 = reinterpret_cast<float*>(rb + o_dist);
+        fx::refine_prep_kernel<<<n_f, 128, 0, ctx->stream>>>(d_q, static_cast<const int*>(ctx->d_qlist.p), c->dim, metric, k,
+                                                            d_out_dist, c->max_norm, fx::tc_c_err(c->dim, s.kind), q_r, tau_fixed);
+        FX_CUDA(cudaGetLastError());
+        fx::TcSearch s2 = s;
+        s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.tau_fixed = tau_fixed; s2.certify = true;
+        s2.ev_k0 = nullptr; s2.ev_k1 = nullptr;   // keep the timing of the main pass
+        FX_TRY(ctx->d_tc.ensure(fx::tc_scratch_bytes(&ctx->tc, s2)));
+        int launched2 = 0;
+        if (!fx::tc_search(&ctx->tc, &c->tc, s2, ctx->d_tc.p, &launched2, &err)) return fail(FX_ECUDA, "fx_search (refine): %s", err.c_str());
+        const int* d_flags2 = fx::tc_flags(&ctx->tc, s2, ctx->d_tc.p);
+        fx::refine_scatter_kernel<<<std::min((n_f * k + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+            static_cast<const int*>(ctx->d_qlist.p), d_flags2, n_f, k, rows2, dist2, d_out_rows, d_out_dist);
+        FX_CUDA(cudaGetLastError());
+        ctx->launches += launched2 + 2; c->stats.kernel_launches += launched2 + 2;
+        FX_CUDA(cudaMemcpyAsync(h_flags, d_flags2, size_t(n_f) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FX_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (std::getenv("FENIX_DEBUG_REFINE")) {
+          std::vector<uint32_t> tf(n_f); std::vector<float> d2(size_t(n_f) * k); std::vector<int64_t> r2(size_t(n_f) * k);
+          cudaMemcpy(tf.data(), tau_fixed, size_t(n_f) * 4, cudaMemcpyDeviceToHost);
+          cudaMemcpy(d2.data(), dist2, size_t(n_f) * k * 4, cudaMemcpyDeviceToHost);
+          cudaMemcpy(r2.data(), rows2, size_t(n_f) * k * 8, cudaMemcpyDeviceToHost);
+          for (int i = 0; i < std::min(n_f, 4); ++i)
+            fprintf(stderr, "[refine] q=%d tau=%g flag=%d rows %lld %lld .. %lld dist %g .. %g\n", bad[i], fx::ord2f(tf[i]), h_flags[i],
+                    (long long)r2[size_t(i) * k], (long long)r2[size_t(i) * k + 1], (long long)r2[size_t(i) * k + k - 1],
+                    d2[size_t(i) * k], d2[size_t(i) * k + k - 1]);
+        }
+        std::vector<int> still;
+        for (int i = 0; i < n_f; ++i) if (h_flags[i]) still.push_back(bad[i]);
+        c->stats.refined_queries += int64_t(n_f - int(still.size()));
+        bad.swap(still);
+      }
       if (!bad.empty()) {
+        // tier 2: the certificate-free fp64 scan
         FX_TRY(ctx->d_qlist.ensure(bad.size() * sizeof(int)));
         FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), bad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         FX_TRY(run_exact_scan(c, d_q, int(n_q), static_cast<int*>(ctx->d_qlist.p), int(bad.size()), metric, k,
@@ -592,7 +669,8 @@ extern "C" int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, 
   s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = static_cast<const float*>(ctx->d_q.p); s.n_q = int(n_q);
   s.metric = metric; s.k = 10; s.certify = false; s.out_rows = static_cast<int64_t*>(ctx->d_rows.p);
   s.out_dist = static_cast<float*>(ctx->d_dist.p); s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1;
-  s.dbg = d_dbg;
+  s.dbg = d_dbg; s.kind = 0; s.pitch_b = c->pitch_b; s.tau_fixed = nullptr;
+  if (std::getenv("FENIX_DEBUG_BF16") && c->tc.ok_b) s.kind = 1;
   FX_TRY(ctx->d_tc.ensure(fx::tc_scratch_bytes(&ctx->tc, s)));
   std::string err; int launched = 0;
   if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err)) return fail(FX_ECUDA, "fx_debug_scores: %s", err.c_str());

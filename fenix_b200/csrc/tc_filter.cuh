@@ -20,8 +20,10 @@
 // proven exact; otherwise the query is flagged and recomputed by the fp64 scan (exact_scan.cuh).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -41,6 +43,7 @@ constexpr int TC_THREADS = 384;            // 12 warps
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_FIRST_WARP = 4;
 constexpr int TC_HALF_COLS = TC_BN / 2;    // columns per epilogue warp-group
+constexpr int TC_CW = 16;                  // accumulator columns per tcgen05.ld in the epilogue
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -56,13 +59,18 @@ struct TcState {
 };
 struct TcCorpus {
   CUtensorMap map_x;       // [n_rows][pitch] fp32, box 32 x 256, 128B swizzle
+  CUtensorMap map_xb;      // [n_rows][pitch_b] bf16 shadow, box 64 x 256, 128B swizzle
   bool ok = false;
+  bool ok_b = false;
 };
 struct TcSearch {
   const float* X; const float* hx; const float* rx; int64_t n_rows; int dim; int pitch; int64_t row_base;
   float max_norm; const float* Q; int n_q; int metric; int k; bool certify;
   int64_t* out_rows; float* out_dist; cudaStream_t stream; cudaEvent_t ev_k0, ev_k1;
   float* dbg;              // optional [128][256] raw score dump (diagnostics)
+  int kind;                // 0: TF32 filter over the fp32 rows, 1: bf16 filter over the bf16 shadow
+  int pitch_b;             // elements per row of the bf16 shadow (multiple of 8)
+  const uint32_t* tau_fixed; // refinement pass: preset per-query admission thresholds (ordered encoding) or null
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -136,6 +144,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -155,6 +171,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
+// kind::f16 with bf16 operands, fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
 
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -167,12 +187,55 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Branch-free candidate append: if (s > tau) { buf[cnt] = (s, col_base + J); ++cnt; } as predicated SASS.
+template <int J>
+__device__ __forceinline__ void append_if_above(uint32_t s_bits, float tau, uint2* buf, int& cnt, uint32_t col_base) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u64 a;\n\t"
+      ".reg .u32 c;\n\t"
+      "setp.gt.f32 p, %1, %2;\n\t"
+      "@p mad.wide.s32 a, %0, 8, %3;\n\t"
+      "@p add.u32 c, %5, %6;\n\t"
+      "@p st.global.v2.u32 [a], {%4, c};\n\t"
+      "@p add.s32 %0, %0, 1;\n\t"
+      "}"
+      : "+r"(cnt)
+      : "f"(__uint_as_float(s_bits)), "f"(tau), "l"(buf), "r"(s_bits), "r"(col_base), "n"(J)
+      : "memory");
+}
+template <int G>
+__device__ __forceinline__ void append_group8(const uint32_t (&v)[TC_CW], float tau, uint2* buf, int& cnt, uint32_t col_base) {
+  append_if_above<8 * G + 0>(v[8 * G + 0], tau, buf, cnt, col_base);
+  append_if_above<8 * G + 1>(v[8 * G + 1], tau, buf, cnt, col_base);
+  append_if_above<8 * G + 2>(v[8 * G + 2], tau, buf, cnt, col_base);
+  append_if_above<8 * G + 3>(v[8 * G + 3], tau, buf, cnt, col_base);
+  append_if_above<8 * G + 4>(v[8 * G + 4], tau, buf, cnt, col_base);
+  append_if_above<8 * G + 5>(v[8 * G + 5], tau, buf, cnt, col_base);
+  append_if_above<8 * G + 6>(v[8 * G + 6], tau, buf, cnt, col_base);
+  append_if_above<8 * G + 7>(v[8 * G + 7], tau, buf, cnt, col_base);
+}
+__device__ __forceinline__ float max8(const uint32_t (&v)[TC_CW], int g) {
+  float a = fmaxf(fmaxf(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), fmaxf(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])));
+  float b = fmaxf(fmaxf(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+  return fmaxf(a, b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,6 +256,13 @@ struct TcParams {
   uint2* wbuf;            // [units][256][cap] candidate buffers (score bits, row), one per (unit, epilogue thread)
   int* wcnt;              // [units][256] entries left in each buffer when its unit finished
   uint32_t* tau_g;        // [n_q] shared per-query threshold, ordered-uint encoding
+  uint32_t* tau_u;        // [n_q][n_pub] rank-r score of each candidate list (0 = not published yet)
+  int n_pub;              // lists that publish (min(2 * n_slices, 512))
+  int rank_r;             // each list publishes its r-th best score, r = ceil(K' / n_pub)
+  int rank_m;             // ceil(K' / r): the m-th largest published value has >= K' rows at or above it
+  int qt_major;           // unit order: 1 = all slices of a query tile adjacent, 0 = all query tiles of a slice adjacent
+  int fixed;              // refinement pass: thresholds are preset in tau_g, no selection; buffer overflow sets flags[q]
+  int* flags;             // [n_q]
   float* dbg;             // diagnostics: raw scores of (query tile 0) x (corpus tile 0), [128][256], or null
 };
 
@@ -202,7 +272,7 @@ struct TcParams {
 // Keeps the kp best (largest score) of buf[0..cnt), compacted to the front; returns the kp-th best
 // score in ordered-uint form (the new admission threshold: everything dropped is <= it).
 template <int PER>
-__device__ __forceinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp, int& new_cnt) {
+__device__ __noinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp, int& new_cnt) {
   const uint32_t lane = lane_id();
   uint32_t s[PER];
 #pragma unroll
@@ -249,15 +319,44 @@ __device__ __forceinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int
   return v;
 }
 
+// kth largest of n (<= 512) values read with a word stride (2: .x of candidate entries, converted to the
+// ordered encoding; 1: already-ordered u32). Returns 0 when fewer than kth non-zero values exist.
+__device__ __noinline__ uint32_t warp_kth_largest(const uint32_t* base, int n, int stride, int kth) {
+  const uint32_t lane = lane_id();
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int idx = i * 32 + int(lane);
+    uint32_t w = 0u;
+    if (idx < n) {
+      w = base[size_t(idx) * stride];
+      if (stride == 2) w = f2ord(__uint_as_float(w));
+    }
+    s[i] = w;
+  }
+  uint32_t v = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    uint32_t cand = v | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c += (s[i] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= kth) v = cand;
+  }
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the filter kernel
 // ---------------------------------------------------------------------------------------------
-template <int METRIC>
+// KIND 0: fp32 operands read as TF32 (k-block = 32 elements, UMMA K = 8)
+// KIND 1: bf16 operands          (k-block = 64 elements, UMMA K = 16); both are 128 B rows / 32 B per MMA
+template <int METRIC, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B-swizzled operand tiles
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* tiles = smem;
   float* norm_smem = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_ACC_STAGES * TC_NORM_BYTES);
@@ -296,7 +395,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int slice = u / p.n_qt, qt = u - slice * p.n_qt;
+        const int qt = p.qt_major ? u / p.n_slices : u % p.n_qt, slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
         const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
         for (int t = t0; t < t1; ++t) {
           if (METRIC != 2) {
@@ -310,8 +409,9 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
             unsigned char* a_dst = tiles + stage * TC_STAGE_BYTES;
-            tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * TC_BK, qt * TC_BM);
-            tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * TC_BK, t * TC_BN);
+            constexpr int kElemsPerBlock = KIND == 0 ? TC_BK : 2 * TC_BK;
+            tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * kElemsPerBlock, qt * TC_BM);
+            tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * kElemsPerBlock, t * TC_BN);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -321,11 +421,11 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+      constexpr uint32_t idesc = KIND == 0 ? make_idesc_tf32(TC_BM, TC_BN) : make_idesc_bf16(TC_BM, TC_BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int slice = u / p.n_qt;
+        const int slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
         const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -340,7 +440,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
               // advance 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-              umma_tf32(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              if (KIND == 0) umma_tf32(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -361,16 +462,17 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     int acc = 0; uint32_t acc_phase = 0;
 
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int slice = u / p.n_qt, qt = u - slice * p.n_qt;
+      const int qt = p.qt_major ? u / p.n_slices : u % p.n_qt, slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
       const int q = qt * TC_BM + row_in_tile;
       const bool active = q < p.n_q;
       uint2* buf = p.wbuf + (size_t(u) * (2 * TC_BM) + slot) * p.cap;
       int cnt = 0;
-      float tau = -INFINITY;
+      float tau = active ? -INFINITY : INFINITY;   // lanes past the last query never admit anything
+      if (p.fixed && active) tau = ord2f(p.tau_g[q]);
 
       for (int t = t0; t < t1; ++t) {
-        if (active) tau = fmaxf(tau, ord2f(ld_relaxed_u32(p.tau_g + q)));
+        if (active && !p.fixed) tau = fmaxf(tau, ord2f(ld_relaxed_u32(p.tau_g + q)));
         mbar_wait(&tmem_full[acc], acc_phase);
         if (METRIC != 2) mbar_wait(&norm_full[acc], acc_phase);
         tc_fence_after();
@@ -379,14 +481,14 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const float* nrm = norm_smem + acc * TC_BN + half * TC_HALF_COLS;
         if (__any_sync(0xffffffffu, active) && ncols > 0) {
 #pragma unroll 1
-          for (int c = 0; c < TC_HALF_COLS; c += 32) {
+          for (int c = 0; c < TC_HALF_COLS; c += TC_CW) {
             if (c >= ncols) break;
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_lane + uint32_t(acc * TC_BN + c), v);
+            uint32_t v[TC_CW];
+            tmem_ld_32x32b_x16(t_lane + uint32_t(acc * TC_BN + c), v);
             tmem_ld_wait();
             bool any = false;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < TC_CW; j += 4) {
               float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
               if (METRIC != 2) n4 = *reinterpret_cast<const float4*>(nrm + c + j);
               float s0 = __uint_as_float(v[j + 0]), s1 = __uint_as_float(v[j + 1]);
@@ -399,14 +501,22 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
             if (p.dbg != nullptr && u == 0 && t == t0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) p.dbg[row_in_tile * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
+              for (int j = 0; j < TC_CW; ++j) p.dbg[row_in_tile * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
             }
-            if (any && active) {
-              const int lim = min(32, ncols - c);
+            if (__any_sync(0xffffffffu, any)) {
+              const uint32_t col_base = uint32_t(col0 + c);
+              if (ncols - c >= TC_CW) {
+                // full chunk: per group of 8 columns, a warp-uniform test, then predicated appends
+                if (__any_sync(0xffffffffu, max8(v, 0) > tau)) append_group8<0>(v, tau, buf, cnt, col_base);
+                if (__any_sync(0xffffffffu, max8(v, 1) > tau)) append_group8<1>(v, tau, buf, cnt, col_base);
+              } else {
+                // the ragged last tile of the corpus
+                const int lim = ncols - c;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float s = __uint_as_float(v[j]);
-                if (j < lim && s > tau) { buf[cnt] = make_uint2(v[j], uint32_t(col0 + c + j)); ++cnt; }
+                for (int j = 0; j < TC_CW; ++j) {
+                  float sj = __uint_as_float(v[j]);
+                  if (j < lim && sj > tau) { buf[cnt] = make_uint2(v[j], col_base + uint32_t(j)); ++cnt; }
+                }
               }
             }
           }
@@ -420,7 +530,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         __syncwarp();
         // tighten thresholds: a lane whose buffer could overflow next tile, or that holds >= K'
         // candidates but no threshold yet, gets a warp-cooperative selection
-        bool need = active && ((cnt > p.cap - TC_HALF_COLS) || (tau == -INFINITY && cnt >= p.kp));
+        if (p.fixed && active && cnt > p.cap - TC_HALF_COLS) { p.flags[q] = 1; tau = INFINITY; }   // more survivors than the buffer holds
+        bool need = active && !p.fixed && ((cnt > p.cap - TC_HALF_COLS) || (tau == -INFINITY && cnt >= p.kp));
         uint32_t need_mask = __ballot_sync(0xffffffffu, need);
         while (need_mask) {
           const int src = __ffs(need_mask) - 1;
@@ -430,10 +541,27 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           int new_cnt;
           uint32_t v_ord = (p.cap == 1024) ? warp_select_compact<32>(b, c_src, p.kp, new_cnt)
                                            : warp_select_compact<16>(b, c_src, p.kp, new_cnt);
+          // cross-list threshold: this list publishes its r-th best score; the m-th largest of the
+          // published values has >= m * r >= K' rows at or above it, so it is a valid (and far tighter)
+          // admission threshold for every list of the query
+          uint32_t w_ord = 0u;
+          const int list_id = slice * 2 + half;
+          if (list_id < p.n_pub) {
+            const int q_src = __shfl_sync(0xffffffffu, q, src);
+            uint32_t* tu = p.tau_u + size_t(q_src) * p.n_pub;
+            __syncwarp();
+            const uint32_t u_ord = warp_kth_largest(reinterpret_cast<const uint32_t*>(b), new_cnt, 2, p.rank_r);
+            if (u_ord != 0u) {
+              if (lane == 0) atomicMax(tu + list_id, u_ord);
+              __syncwarp();
+              w_ord = warp_kth_largest(tu, p.n_pub, 1, p.rank_m);
+            }
+          }
           if (int(lane) == src) {
             cnt = new_cnt;
-            tau = fmaxf(tau, ord2f(v_ord));
-            atomicMax(p.tau_g + q, v_ord);
+            const uint32_t best = v_ord > w_ord ? v_ord : w_ord;
+            tau = fmaxf(tau, ord2f(best));
+            atomicMax(p.tau_g + q, best);
           }
         }
       }
@@ -455,15 +583,26 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // query preparation: pad to the TMA pitch, reset per-query state
 // ---------------------------------------------------------------------------------------------
 __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, int pitch, float* __restrict__ Qp,
-                                uint32_t* __restrict__ tau_g, int* __restrict__ flags) {
+                                uint32_t* __restrict__ tau_g, int* __restrict__ flags,
+                                uint32_t* __restrict__ tau_u, int n_pub, __nv_bfloat16* __restrict__ Qb, int pitch_b,
+                                const uint32_t* __restrict__ tau_fixed) {
   const int64_t total = int64_t(n_q) * pitch;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     int q = int(i / pitch), d = int(i - int64_t(q) * pitch);
     Qp[i] = d < dim ? Q[size_t(q) * dim + d] : 0.f;
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += gridDim.x * blockDim.x) {
-    tau_g[i] = ORD_NEG_INF; flags[i] = 0;
+  if (Qb != nullptr) {
+    const int64_t total_b = int64_t(n_q) * pitch_b;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total_b; i += int64_t(gridDim.x) * blockDim.x) {
+      int q = int(i / pitch_b), d = int(i - int64_t(q) * pitch_b);
+      Qb[i] = __float2bfloat16_rn(d < dim ? Q[size_t(q) * dim + d] : 0.f);
+    }
   }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += gridDim.x * blockDim.x) {
+    tau_g[i] = tau_fixed ? tau_fixed[i] : ORD_NEG_INF; flags[i] = 0;
+  }
+  const int64_t n_u = int64_t(n_q) * n_pub;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_u; i += int64_t(gridDim.x) * blockDim.x) tau_u[i] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -472,7 +611,7 @@ __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, i
 struct FinishParams {
   const float* X; int pitch; int dim; int64_t row_base;
   const float* Qp; int n_q; int n_qt; int n_slices; int cap; int metric; int k; int kp; int sort2;  // sort2: pow2 >= kp
-  const uint32_t* tau_g; const uint2* wbuf; const int* wcnt;
+  const uint32_t* tau_g; const uint2* wbuf; const int* wcnt; int qt_major;
   int* flags; int certify; float max_norm; double c_err;
   int64_t* out_rows; float* out_dist;
 };
@@ -510,11 +649,13 @@ knn_tc_finish_kernel(FinishParams p) {
     if (lane == 0) s_qq = s;
   }
   const uint32_t tg = p.tau_g[q];
+  const bool overflowed = p.flags[q] != 0;   // set by the filter kernel in refinement mode
 
   // list l = (slice, half): buffer of thread slot half*128 + r of unit slice*n_qt + qt
   auto list_ptr = [&](int l, int& count) -> const uint2* {
     const int slice = l >> 1, half = l & 1;
-    const size_t unit_slot = (size_t(slice) * p.n_qt + qt) * (2 * TC_BM) + half * TC_BM + r;
+    const size_t unit = p.qt_major ? size_t(qt) * p.n_slices + slice : size_t(slice) * p.n_qt + qt;
+    const size_t unit_slot = unit * (2 * TC_BM) + half * TC_BM + r;
     count = p.wcnt[unit_slot];
     return p.wbuf + unit_slot * p.cap;
   };
@@ -530,7 +671,7 @@ knn_tc_finish_kernel(FinishParams p) {
       int count; const uint2* b = list_ptr(l, count);
       for (int i = lane; i < count; i += 32) {
         uint32_t o = f2ord(__uint_as_float(b[i].x));
-        if (o > tg && (o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 0xffu], 1);
+        if (o >= tg && (o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 0xffu], 1);
       }
     }
     __syncthreads();
@@ -567,7 +708,7 @@ knn_tc_finish_kernel(FinishParams p) {
     for (int i = lane; i < count; i += 32) {
       uint2 ent = b[i];
       uint32_t o = f2ord(__uint_as_float(ent.x));
-      if (o > pivot) {
+      if (o > pivot || (keep_all && o == pivot)) {
         int pos = atomicAdd(&s_n_gt, 1);
         if (pos < p.sort2) cand[pos] = ent.y;
       } else if (!keep_all && o == pivot) {
@@ -650,13 +791,83 @@ knn_tc_finish_kernel(FinishParams p) {
       }
       lb = lb - 1e-6 * fabs(lb) - 1e-37;
       bool ok = false;
-      if (n_cand >= p.k && s_n_gt <= p.sort2) {
+      if (n_cand >= p.k && s_n_gt <= p.sort2 && !overflowed) {
         float dk = ord2f(uint32_t(keys2[p.k - 1] >> 32));
         ok = double(dk) < lb;   // NaN compares false -> flagged
       }
       flag = ok ? 0 : 1;
     }
     p.flags[q] = flag;
+  }
+}
+
+// Refinement of flagged queries. One block per flagged query i (original index qlist[i]): gathers the query
+// into Qr[i] and derives the preset admission threshold from the k-th distance d_k of the first pass:
+// every row that can still beat d_k has exact score > s(d_k), hence filter score > s(d_k) - E.
+__global__ void __launch_bounds__(128)
+refine_prep_kernel(const float* __restrict__ Q, const int* __restrict__ qlist, int dim, int metric, int k,
+                   const float* __restrict__ dist, float max_norm, double c_err,
+                   float* __restrict__ Qr, uint32_t* __restrict__ tau_fixed) {
+  __shared__ double part[4];
+  const int i = blockIdx.x, q = qlist[i];
+  double s = 0.0;
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    float v = Q[size_t(q) * dim + d];
+    Qr[size_t(i) * dim + d] = v;
+    s = fma(double(v), double(v), s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double qq = part[0] + part[1] + part[2] + part[3];
+    const double nq = sqrt(qq), xm = double(max_norm);
+    double dk = double(dist[size_t(q) * k + (k - 1)]);
+    dk = dk + 1e-6 * fabs(dk) + 1e-37;            // a row at distance <= dk (after fp32 rounding) must survive
+    double score, e_abs;
+    if (metric == 0) {
+      e_abs = c_err * nq * xm + 4.8e-7 * (0.5 * xm * xm + nq * xm);
+      score = 0.5 * (qq - dk * dk);
+    } else if (metric == 1) {
+      e_abs = nq * (c_err + 1e-6);
+      score = (1.0 - 2.0 * dk) * (nq > 1e-12 ? nq : 1e-12);
+    } else {
+      e_abs = c_err * nq * xm;
+      score = -dk;
+    }
+    double t = score - e_abs;
+    t = t - 1e-6 * fabs(t) - 1e-30;
+    float tf = __double2float_rd(t);
+    // fewer than k candidates in the first pass (dk = inf) or non-finite input: admit everything
+    tau_fixed[i] = (t == t && dk < 1e300) ? f2ord(tf) : ORD_NEG_INF;
+  }
+}
+
+// Copy refined results of the queries whose certificate now holds back to their slots.
+__global__ void refine_scatter_kernel(const int* __restrict__ qlist, const int* __restrict__ flags2, int n_f, int k,
+                                      const int64_t* __restrict__ rows2, const float* __restrict__ dist2,
+                                      int64_t* __restrict__ out_rows, float* __restrict__ out_dist) {
+  const int64_t total = int64_t(n_f) * k;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int i = int(t / k), j = int(t - int64_t(i) * k);
+    if (flags2[i] == 0) {
+      out_rows[size_t(qlist[i]) * k + j] = rows2[t];
+      out_dist[size_t(qlist[i]) * k + j] = dist2[t];
+    }
+  }
+}
+
+// fp32 rows -> bf16 shadow rows (round to nearest even), pad columns zero.
+__global__ void to_bf16_rows_kernel(const float* __restrict__ X, int64_t n_rows, int pitch, int dim,
+                                    __nv_bfloat16* __restrict__ Xb, int pitch_b) {
+  const int64_t total = n_rows * int64_t(pitch_b >> 1);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / (pitch_b >> 1);
+    const int d = int(i - r * (pitch_b >> 1)) * 2;
+    const float a = d < dim ? X[size_t(r) * pitch + d] : 0.f;
+    const float b = d + 1 < dim ? X[size_t(r) * pitch + d + 1] : 0.f;
+    reinterpret_cast<__nv_bfloat162*>(Xb)[i] = __floats2bfloat162_rn(a, b);
   }
 }
 
@@ -668,13 +879,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline bool tc_encode_2d(const TcState* st, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
-                         uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer, std::string* err) {
+                         uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer, std::string* err, bool bf16 = false) {
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+  cuuint64_t strides[1] = {pitch_elems * (bf16 ? 2 : sizeof(float))};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(st->encode)(
-      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+      map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -694,20 +905,28 @@ inline bool tc_init(TcState* st, int sm_count, std::string* err) {
     return false;
   }
   st->encode = fn;
-  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (a != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(tc kernels) failed: ") + cudaGetErrorString(a); return false; }
   return true;
 }
 
-inline bool tc_bind_corpus(TcState* st, TcCorpus* tc, const float* X, int64_t n_rows, int dim, int pitch, std::string* err) {
+inline bool tc_bind_corpus(TcState* st, TcCorpus* tc, const float* X, int64_t n_rows, int dim, int pitch,
+                           const void* Xb, int pitch_b, std::string* err) {
   (void)dim;
-  tc->ok = false;
+  tc->ok = false; tc->ok_b = false;
   if (n_rows < 1) return true;
   if (!tc_encode_2d(st, &tc->map_x, X, uint64_t(pitch), uint64_t(n_rows), uint64_t(pitch), TC_BK, TC_BN, err)) return false;
   tc->ok = true;
+  if (Xb != nullptr) {
+    if (!tc_encode_2d(st, &tc->map_xb, Xb, uint64_t(pitch_b), uint64_t(n_rows), uint64_t(pitch_b), 2 * TC_BK, TC_BN, err, true)) return false;
+    tc->ok_b = true;
+  }
   return true;
 }
 
@@ -730,17 +949,19 @@ inline bool tc_supported(const TcState* st, const TcCorpus* tc, int64_t n_rows, 
 
 struct TcPlan {
   int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks;
-  size_t off_qp, off_tau, off_flags, off_wcnt, off_wbuf, total;
+  int n_pub, rank_r, rank_m, qt_major;
+  size_t off_qp, off_qb, off_tau, off_flags, off_tau_u, off_wcnt, off_wbuf, total;
 };
 
 inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   TcPlan pl{};
   pl.n_qt = (s.n_q + TC_BM - 1) / TC_BM;
   pl.n_tiles = int((s.n_rows + TC_BN - 1) / TC_BN);
-  pl.kp = tc_kp(s.k, s.certify);
+  pl.kp = s.tau_fixed ? 1024 : tc_kp(s.k, s.certify);   // refinement reranks every survivor (up to 1024)
   pl.cap = tc_cap(pl.kp);
-  pl.n_kblocks = (s.pitch + TC_BK - 1) / TC_BK;
-  // Slices: units = n_slices * n_qt are dealt round-robin to min(units, #SM) persistent CTAs.
+  pl.n_kblocks = s.kind == 0 ? (s.pitch + TC_BK - 1) / TC_BK : (s.pitch_b + 2 * TC_BK - 1) / (2 * TC_BK);
+  // Slices: units = n_qt * n_slices (query-tile major, so all slices of a query tile run at the same time and
+  // share thresholds) are dealt round-robin to min(units, #SM) persistent CTAs.
   // Maximise SM utilisation units / (G * ceil(units / G)); few slices are preferred (longer units give
   // tighter thresholds and fewer candidate lists), and every unit should span enough tiles for its
   // threshold to become selective.
@@ -758,6 +979,15 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     double eff = double(units) / double(sms * ((units + g - 1) / g));
     if (eff > best + 0.02) { best = eff; best_s = sl; }
   }
+  if (const char* e = std::getenv("FENIX_TC_SLICES")) {   // tuning knob: force the slice count
+    int forced = std::atoi(e);
+    if (forced >= 1 && forced <= s_max) {
+      int tps = (pl.n_tiles + forced - 1) / forced;
+      best_s = (pl.n_tiles + tps - 1) / tps;
+    }
+  }
+  pl.qt_major = 0;   // measured on C3: slice-major 94 ms vs query-tile-major 112 ms (profiles/r01_c3_sweep.txt)
+  if (const char* e = std::getenv("FENIX_TC_ORDER")) pl.qt_major = std::atoi(e) != 0;
   pl.n_slices = best_s;
   pl.tiles_per_slice = (pl.n_tiles + best_s - 1) / best_s;
   pl.units = pl.n_slices * pl.n_qt;
@@ -765,8 +995,15 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   pl.off_qp = take(size_t(s.n_q) * s.pitch * 4);
+  pl.off_qb = take(s.kind == 1 ? size_t(s.n_q) * s.pitch_b * 2 : 0);
   pl.off_tau = take(size_t(s.n_q) * 4);
   pl.off_flags = take(size_t(s.n_q) * 4);
+  // cross-list threshold publication is off by default: on C3 it costs more than it saves (120 vs 94 ms)
+  pl.n_pub = 0;
+  if (const char* e = std::getenv("FENIX_TC_PUBLISH")) { if (std::atoi(e) != 0) pl.n_pub = std::min(2 * pl.n_slices, 512); }
+  pl.rank_r = pl.n_pub ? (pl.kp + pl.n_pub - 1) / pl.n_pub : 1;
+  pl.rank_m = (pl.kp + pl.rank_r - 1) / pl.rank_r;
+  pl.off_tau_u = take(size_t(s.n_q) * std::max(pl.n_pub, 1) * 4);
   pl.off_wcnt = take(size_t(pl.units) * 2 * TC_BM * 4);
   pl.off_wbuf = take(size_t(pl.units) * 2 * TC_BM * pl.cap * 8);
   pl.total = off;
@@ -780,7 +1017,11 @@ inline const int* tc_flags(const TcState* st, const TcSearch& s, void* scratch) 
 // rigorous bound constant of the TF32 dot product: |acc - <q,x>| <= c * |q| * |x|
 // (operands truncated to 10 mantissa bits: 2^-10 each -> 2^-9 on the product, 25% margin;
 //  fp32 accumulation of D terms: D * 2^-21)
-inline double tc_c_err(int dim) { return 1.25 * std::ldexp(1.0, -9) + double(dim) * std::ldexp(1.0, -21); }
+// bf16 operands are rounded to nearest (2^-9 each -> 2^-8 on the product, 10% margin).
+inline double tc_c_err(int dim, int kind = 0) {
+  const double prod = kind == 0 ? 1.25 * std::ldexp(1.0, -9) : 1.10 * std::ldexp(1.0, -8);
+  return prod + double(dim) * std::ldexp(1.0, -21);
+}
 
 inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratch, int* launched, std::string* err) {
   const TcPlan pl = tc_plan(st, s);
@@ -788,31 +1029,45 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   float* qp = reinterpret_cast<float*>(base + pl.off_qp);
   uint32_t* tau_g = reinterpret_cast<uint32_t*>(base + pl.off_tau);
   int* flags = reinterpret_cast<int*>(base + pl.off_flags);
+  uint32_t* tau_u = reinterpret_cast<uint32_t*>(base + pl.off_tau_u);
   int* wcnt = reinterpret_cast<int*>(base + pl.off_wcnt);
   uint2* wbuf = reinterpret_cast<uint2*>(base + pl.off_wbuf);
 
+  __nv_bfloat16* qb = s.kind == 1 ? reinterpret_cast<__nv_bfloat16*>(base + pl.off_qb) : nullptr;
   CUtensorMap map_q;
-  if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(s.n_q), uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
+  if (s.kind == 0) {
+    if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(s.n_q), uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
+  } else {
+    if (!tc->ok_b) { *err = "bf16 filter requested but the shard has no bf16 shadow"; return false; }
+    if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(s.n_q), uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
+  }
 
   const int prep_blocks = int(std::min<int64_t>((int64_t(s.n_q) * s.pitch + 255) / 256, 4 * 148));
-  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags);
+  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags, tau_u, pl.n_pub, qb, s.pitch_b, s.tau_fixed);
 
   TcParams p{};
   p.n_q = s.n_q; p.n_qt = pl.n_qt; p.n_rows = s.n_rows; p.n_tiles = pl.n_tiles; p.n_slices = pl.n_slices;
   p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.kp = pl.kp; p.cap = pl.cap;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
-  cudaEventRecord(s.ev_k0, s.stream);
-  if (s.metric == 0) knn_tc_filter_kernel<0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
-  else if (s.metric == 1) knn_tc_filter_kernel<1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
-  else knn_tc_filter_kernel<2><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
-  cudaEventRecord(s.ev_k1, s.stream);
+  p.tau_u = tau_u; p.n_pub = pl.n_pub; p.rank_r = pl.rank_r; p.rank_m = pl.rank_m; p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
+  if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);
+  if (s.kind == 0) {
+    if (s.metric == 0) knn_tc_filter_kernel<0, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+    else if (s.metric == 1) knn_tc_filter_kernel<1, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+    else knn_tc_filter_kernel<2, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+  } else {
+    if (s.metric == 0) knn_tc_filter_kernel<0, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
+    else if (s.metric == 1) knn_tc_filter_kernel<1, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
+    else knn_tc_filter_kernel<2, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
+  }
+  if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
 
   FinishParams f{};
   f.X = s.X; f.pitch = s.pitch; f.dim = s.dim; f.row_base = s.row_base; f.Qp = qp; f.n_q = s.n_q; f.n_qt = pl.n_qt;
   f.n_slices = pl.n_slices; f.cap = pl.cap; f.metric = s.metric; f.k = s.k; f.kp = pl.kp;
   int sort2 = 2; while (sort2 < pl.kp) sort2 <<= 1;
-  f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.flags = flags; f.certify = s.certify ? 1 : 0;
-  f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
+  f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.qt_major = pl.qt_major; f.flags = flags; f.certify = s.certify ? 1 : 0;
+  f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim, s.kind); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
   const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + 16;
   knn_tc_finish_kernel<<<s.n_q, 256, fin_smem, s.stream>>>(f);
   cudaError_t e = cudaGetLastError();

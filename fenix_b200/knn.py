@@ -18,7 +18,7 @@ import numpy as np
 
 __all__ = [
     "FenixKnnError", "Context", "Corpus", "Stats", "METRICS", "metric_code",
-    "PREC_FP32", "PREC_TF32", "PREC_EXACT_SCAN", "load_library", "library_path", "K_MAX",
+    "PREC_FP32", "PREC_TF32", "PREC_BF16", "PREC_EXACT_SCAN", "load_library", "library_path", "K_MAX",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -27,7 +27,7 @@ K_MAX = 2048
 
 FX_OK = 0
 FX_EINVAL, FX_ECUDA, FX_ENOMEM, FX_ESTATE, FX_EUNSUP = -1, -2, -3, -4, -5
-PREC_FP32, PREC_TF32, PREC_EXACT_SCAN = 0, 1, 3
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_EXACT_SCAN = 0, 1, 2, 3
 
 # the five names accepted by the reference (flight.py:254, coder.py:39,42,47) -> 3 forms
 METRICS = {"l2": 0, "euclidean": 0, "cosine": 1, "dot": 2, "inner_product": 2}
@@ -60,7 +60,7 @@ class _FxStats(ctypes.Structure):
     _fields_ = [
         ("n_rows", ctypes.c_int64), ("dim", ctypes.c_int32), ("pitch", ctypes.c_int32),
         ("device_bytes", ctypes.c_int64), ("searches", ctypes.c_int64), ("queries", ctypes.c_int64),
-        ("fallback_queries", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
+        ("fallback_queries", ctypes.c_int64), ("refined_queries", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
         ("last_search_ms", ctypes.c_double), ("last_main_kernel_ms", ctypes.c_double),
         ("last_path", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
@@ -75,6 +75,7 @@ class Stats:
     searches: int
     queries: int
     fallback_queries: int
+    refined_queries: int
     kernel_launches: int
     last_search_ms: float
     last_main_kernel_ms: float

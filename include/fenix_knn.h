@@ -52,12 +52,16 @@ extern "C" {
  *   FP32: exact. A TF32 tensor-core pass filters candidates under a rigorous error bound,
  *         survivors are re-ranked with fp64-accumulated arithmetic, the result is certified
  *         (or recomputed by the exact scan kernel when the certificate fails).
- *   TF32: the same tensor-core pass without slack/certificate; distances of the returned
- *         rows are still exact, membership is approximate (recall reported by bench.py).
+ *         The filter runs on a bf16 shadow copy of the shard (2x MMA rate, built at finalize when
+ *         D >= 256 or FENIX_BF16_SHADOW=1) or, without one, on the fp32 rows read as TF32.
+ *   TF32 / BF16: the same tensor-core pass (TF32 over the fp32 rows / bf16 over the shadow) without
+ *         slack or certificate; distances of the returned rows are still exact, membership is
+ *         approximate (recall reported by bench.py). BF16 needs the shadow (FX_ESTATE otherwise).
  *   EXACT_SCAN: forces the fp64-accumulating CUDA-core scan kernel (checker / fallback path).
  */
 #define FX_PREC_FP32 0
 #define FX_PREC_TF32 1
+#define FX_PREC_BF16 2
 #define FX_PREC_EXACT_SCAN 3
 
 /* dtype of corpus rows */
@@ -73,7 +77,8 @@ typedef struct fx_stats {
   int64_t device_bytes;      /* HBM held by this shard (rows + norms) */
   int64_t searches;          /* fx_search* calls completed */
   int64_t queries;           /* queries answered */
-  int64_t fallback_queries;  /* queries whose certificate failed -> exact scan recompute */
+  int64_t fallback_queries;  /* queries recomputed by the exact scan (certificate failed twice) */
+  int64_t refined_queries;   /* queries whose certificate failed once and were settled by the refinement pass */
   int64_t kernel_launches;   /* kernels of this library launched so far */
   double last_search_ms;     /* device time of the last search (CUDA events) */
   double last_main_kernel_ms;/* device time of the dominant kernel of the last search */

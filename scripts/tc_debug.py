@@ -3,6 +3,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fenix_b200 import knn
 ctx = knn.Context(0)
+kind = "bf16" if os.environ.get("FENIX_DEBUG_BF16") else "tf32"
 for (n, d) in [(8192, 128), (8192, 32), (8192, 64), (8192, 768), (8192, 100)]:
     rng = np.random.default_rng(d)
     x = rng.standard_normal((n, d), dtype=np.float32)
@@ -12,13 +13,5 @@ for (n, d) in [(8192, 128), (8192, 32), (8192, 64), (8192, 768), (8192, 100)]:
     ref = q.astype(np.float64) @ x[:256].astype(np.float64).T
     err = np.abs(s - ref)
     bound = np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x[:256], axis=1)[None, :]
-    print(f"d={d}: max abs err {err.max():.4g}  max err/(|q||x|) {np.max(err/bound):.3g}  frac bad(>1e-2*bound) {(err > 1e-2*bound).mean():.3f}")
-    badmap = (err > 1e-2 * bound)
-    if badmap.any():
-        print("  bad rows (queries):", np.nonzero(badmap.any(1))[0][:20], " count", badmap.any(1).sum())
-        print("  bad cols (corpus):", np.nonzero(badmap.any(0))[0][:20], " count", badmap.any(0).sum())
-        # try to explain: partial K sums
-        for kk in range(32, d + 1, 32):
-            part = q[:, :kk].astype(np.float64) @ x[:256, :kk].astype(np.float64).T
-            print(f"   vs K<{kk}: max err {np.abs(s-part).max():.4g}")
+    print(f"{kind} d={d}: max abs err {err.max():.4g}  max err/(|q||x|) {np.max(err/bound):.3g}  frac bad(>2e-2*bound) {(err > 2e-2*bound).mean():.3f}")
     c.close()

@@ -251,6 +251,29 @@ def test_tensor_core_path_runs_and_certifies(ctx):
     c.close()
 
 
+def test_refinement_pass_settles_ties_and_near_ties(ctx):
+    """Duplicates defeat the first-pass certificate (K' equal scores); the preset-threshold refinement pass must
+    then produce the exact (distance, row) answer without the full fp64 scan."""
+    rng = np.random.default_rng(91)
+    corpus = rng.standard_normal((30000, 96), dtype=np.float32)
+    corpus[5000:5400] = corpus[17]                    # 400 copies of row 17
+    corpus[20000:20050] = corpus[17] + 1e-4           # 50 near-duplicates
+    queries = np.concatenate([corpus[17:18], rng.standard_normal((40, 96), dtype=np.float32)])
+    c = make_corpus(ctx, corpus)
+    for metric in ("l2", "cosine", "dot"):
+        before = c.stats()
+        rows, dist = c.search(queries, metric, 10, knn.PREC_FP32)
+        after = c.stats()
+        want_rows, want_dist = c.search(queries, metric, 10, knn.PREC_EXACT_SCAN)
+        assert np.array_equal(rows, want_rows) and np.array_equal(dist, want_dist), metric
+        assert after.refined_queries - before.refined_queries >= 1, "the duplicate query should need the refinement pass"
+        assert after.fallback_queries == before.fallback_queries, "refinement should make the full scan unnecessary here"
+    truth_rows, _ = brute_force_f64(corpus, queries[:1], "l2", 10)
+    rows, _ = c.search(queries[:1], "l2", 10)
+    assert np.array_equal(rows, truth_rows)
+    c.close()
+
+
 @pytest.mark.parametrize("dim", [32, 100, 128, 768])
 def test_tf32_error_bound_of_the_certificate(ctx, dim):
     """|filter score - exact score| <= c * |q| * |x| with c = 1.25 * 2^-9 + D * 2^-21 (tc_filter.cuh)."""
@@ -268,6 +291,30 @@ def test_tf32_error_bound_of_the_certificate(ctx, dim):
         s = c.debug_scores(queries, metric).astype(np.float64)
         ratio = np.abs(s - exact[metric]) / (cerr * scale[metric])
         assert ratio.max() < 0.5, (metric, ratio.max())  # observed ~0.2: the bound has 2x+ headroom
+    c.close()
+
+
+@pytest.mark.parametrize("dim", [64, 768])
+def test_bf16_shadow_filter_is_exact_in_fp32_mode(ctx, dim, monkeypatch):
+    """With a bf16 shadow the exact mode filters with kind::f16 MMAs; results must not change, and the bf16
+    error bound c = 1.1 * 2^-8 + D * 2^-21 must hold for the raw scores."""
+    monkeypatch.setenv("FENIX_BF16_SHADOW", "1")
+    rng = np.random.default_rng(dim + 5)
+    corpus = rng.standard_normal((20000, dim), dtype=np.float32)
+    queries = rng.standard_normal((130, dim), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    monkeypatch.setenv("FENIX_DEBUG_BF16", "1")
+    s = c.debug_scores(queries, "dot").astype(np.float64)
+    q, x = queries[:128].astype(np.float64), corpus[:256].astype(np.float64)
+    bound = (1.1 * 2.0 ** -8 + dim * 2.0 ** -21) * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :]
+    assert (np.abs(s - q @ x.T) / bound).max() < 0.6
+    for metric in ("l2", "cosine", "dot"):
+        rows, dist = c.search(queries, metric, 10, knn.PREC_FP32)
+        assert c.stats().last_path == 1
+        want_rows, want_dist = c.search(queries, metric, 10, knn.PREC_EXACT_SCAN)
+        assert np.array_equal(rows, want_rows) and np.array_equal(dist, want_dist), metric
+        rows_b, _ = c.search(queries, metric, 10, knn.PREC_BF16)
+        assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(rows, rows_b)]) >= 0.97
     c.close()
 
 
