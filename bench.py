@@ -253,6 +253,7 @@ def run_ours(args, cfg: dict) -> dict:
     clocks = sampler.stop() if rank == 0 else None
     launches = st1.kernel_launches - st0.kernel_launches + (args.steps if world > 1 else 0)
     fallback = st1.fallback_queries - st0.fallback_queries
+    refined = st1.refined_queries - st0.refined_queries
 
     # ---- end to end through the host API: pinned queries in, pinned results out ----
     for _ in range(max(1, min(args.warmup, 2))):
@@ -278,8 +279,10 @@ def run_ours(args, cfg: dict) -> dict:
 
     # ---- optional recall of the tf32 mode against the exact result ----
     recall = None
-    if args.precision == "fp32" and corpus.stats().last_path == 1:
-        r_t, _ = searcher.search_device(d_q, metric, k, knn.PREC_TF32)
+    path = st1.last_path            # 0 scan, 1 TF32 filter, 2 bf16 filter
+    if args.precision == "fp32" and path >= 1:
+        approx = knn.PREC_BF16 if path == 2 else knn.PREC_TF32
+        r_t, _ = searcher.search_device(d_q, metric, k, approx)
         a, b = rows.cpu().numpy(), r_t.cpu().numpy()
         recall = float(np.mean([len(set(x) & set(y)) / k for x, y in zip(a, b)]))
 
@@ -288,21 +291,24 @@ def run_ours(args, cfg: dict) -> dict:
         pk = peaks()
         n_shard = hi - lo
         flops = 2.0 * n_q * n_shard * d
-        bytes_alg = 4.0 * n_shard * d + 4.0 * n_q * d + 12.0 * n_q * k
-        tensor_bound = n_q >= 210 and st1.last_path == 1
+        elem = 2.0 if path == 2 else 4.0     # the bf16 filter streams the bf16 shadow, otherwise the fp32 rows
+        bytes_alg = elem * n_shard * d + 4.0 * n_q * d + 12.0 * n_q * k
+        tensor_bound = path >= 1 and n_q >= (420 if path == 2 else 210)
         if tensor_bound:
             achieved = flops / (k_ms * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
             roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
-                        peak_source=f"{pk['_source']} bf16 dense sustained; the kernel issues kind::tf32 MMAs whose "
-                                    f"nominal rate is half of bf16, so frac <= ~0.5 by construction",
-                        frac_of_tf32_nominal_half=achieved / (peak / 2))
+                        peak_source=f"{pk['_source']} bf16 dense sustained (cuBLAS 8192^3 loop)" +
+                                    ("" if path == 2 else "; this launch issues kind::tf32 MMAs whose nominal rate is half of "
+                                     "bf16, so frac <= ~0.5 by construction"))
+            if path == 1:
+                roof["frac_of_tf32_nominal_half"] = achieved / (peak / 2)
         else:
             achieved = bytes_alg / (k_ms * 1e-3) / 1e9
             peak = pk["hbm_gbs"]
             roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                         peak_source=f"{pk['_source']} copy bandwidth")
-        roof.update(kernel="knn_tc_filter_kernel" if st1.last_path == 1 else "exact_scan_kernel",
+        roof.update(kernel={0: "exact_scan_kernel", 1: "knn_tc_filter_kernel<metric, tf32>", 2: "knn_tc_filter_kernel<metric, bf16>"}[path],
                     kernel_ms=k_ms, search_device_ms=s_ms,
                     algorithmic=dict(flops=flops, bytes=bytes_alg, per="launch (one query batch against this rank's shard)"))
         out = {
@@ -315,8 +321,9 @@ def run_ours(args, cfg: dict) -> dict:
                 "queries_per_step": n_q, "precision_mode": args.precision, "parallelism": f"row-shard x{world}",
                 "l2_policy": "corpus shard is larger than L2 (126 MB), no flush needed" if 4.0 * n_shard * d > 2.5e8
                 else "corpus shard fits in L2: steady-state (warm L2) timing",
-                "path": "tcgen05 TF32 filter + fp64 rerank + certificate" if st1.last_path == 1 else "fp64 exact scan (CUDA cores)",
-                "fallback_queries": int(fallback), "corpus_build_s": t_build,
+                "path": {0: "fp64 exact scan (CUDA cores)", 1: "tcgen05 TF32 filter + fp64 rerank + certificate",
+                         2: "tcgen05 bf16-shadow filter + fp64 rerank + certificate"}[path],
+                "refined_queries": int(refined), "fallback_queries": int(fallback), "corpus_build_s": t_build,
             },
             "clocks": clocks,
             "e2e": {"value": n_q / (e2e_elapsed / args.steps), "unit": "queries/s",
@@ -326,7 +333,7 @@ def run_ours(args, cfg: dict) -> dict:
             "roofline": roof,
         }
         if recall is not None:
-            out["tf32_mode_recall_at_k"] = recall
+            out["approx_mode_recall_at_k"] = {"mode": "bf16" if path == 2 else "tf32", "recall": recall}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = time_reference(cfg, steps=3, warmup=1, budget_s=20.0)
     corpus.close()

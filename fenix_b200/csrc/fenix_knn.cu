@@ -449,7 +449,7 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
                                 const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist) {
   fx_ctx* ctx = c->ctx;
   FX_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
-  int path = 0;
+  int path = 0;   // 0 exact scan, 1 tensor-core TF32 filter, 2 tensor-core bf16 filter
   const bool want_tc = precision != FX_PREC_EXACT_SCAN && d_mask == nullptr &&
                        fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q));
   if (c->n == 0) {
@@ -467,6 +467,7 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
     // operand kind of the filter: exact mode takes the bf16 shadow when the shard has one
     s.pitch_b = c->pitch_b;
     s.kind = (precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && c->tc.ok_b && !std::getenv("FENIX_FP32_FILTER_TF32"))) ? 1 : 0;
+    path = 1 + s.kind;
     if (s.kind == 1 && !c->tc.ok_b) return fail(FX_ESTATE, "fx_search: FX_PREC_BF16 needs the bf16 shadow (FENIX_BF16_SHADOW=1 at finalize)");
     std::string err;
     size_t need = fx::tc_scratch_bytes(&ctx->tc, s);

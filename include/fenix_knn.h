@@ -82,7 +82,7 @@ typedef struct fx_stats {
   int64_t kernel_launches;   /* kernels of this library launched so far */
   double last_search_ms;     /* device time of the last search (CUDA events) */
   double last_main_kernel_ms;/* device time of the dominant kernel of the last search */
-  int32_t last_path;         /* 0 = exact scan, 1 = tcgen05 filter + rerank */
+  int32_t last_path;         /* 0 = exact scan, 1 = tcgen05 TF32 filter + rerank, 2 = tcgen05 bf16 filter + rerank */
   int32_t reserved;
 } fx_stats;
 

@@ -310,7 +310,7 @@ def test_bf16_shadow_filter_is_exact_in_fp32_mode(ctx, dim, monkeypatch):
     assert (np.abs(s - q @ x.T) / bound).max() < 0.6
     for metric in ("l2", "cosine", "dot"):
         rows, dist = c.search(queries, metric, 10, knn.PREC_FP32)
-        assert c.stats().last_path == 1
+        assert c.stats().last_path == 2   # bf16 filter
         want_rows, want_dist = c.search(queries, metric, 10, knn.PREC_EXACT_SCAN)
         assert np.array_equal(rows, want_rows) and np.array_equal(dist, want_dist), metric
         rows_b, _ = c.search(queries, metric, 10, knn.PREC_BF16)
