@@ -119,48 +119,66 @@ def time_reference(cfg: dict, steps: int, warmup: int, budget_s: float = 25.0) -
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread, ~4 ms period, so
+    even a 40 ms region gets samples; falls back to one nvidia-smi query when NVML is unavailable)."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu: int) -> None:
         self.gpu = gpu
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        self.proc = None
+        self.sm, self.bits, self.max_mhz = [], 0, None
+        self._stop = None
+        self._thread = None
+        self._nvml = None
+
+    def _loop(self, handle) -> None:
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+            except Exception:
+                break
+            self._stop.wait(0.004)
 
     def start(self) -> None:
+        import threading
+
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML device through its UUID
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            try:
+                handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self._nvml = nv
+            self._stop = threading.Event()
+            self._thread = threading.Thread(target=self._loop, args=(handle,), daemon=True)
+            self._thread.start()
+        except Exception:
+            self._nvml = None
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
-                continue
+        if self._nvml is None:
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(t) for t in out.strip().split(",")[:2]]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": ["sampled once after the region (NVML unavailable)"], "samples": 1}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        reasons = sorted(name for name, bit in self.REASONS.items() if self.bits & bit)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------------------

@@ -93,7 +93,7 @@ struct fx_ctx {
   cudaStream_t upload = nullptr;   // H2D of corpus chunks
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   std::mutex mu;                   // one search at a time per device context
-  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref;
+  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref, d_maskn;
   HostBuf h_q, h_rows, h_dist, h_flags;
   int64_t launches = 0;
   fx::TcState tc;                  // driver entry points / kernel attributes of the TC path
@@ -183,7 +183,7 @@ extern "C" int fx_shutdown(fx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->upload);
   ctx->d_q.release(); ctx->d_rows.release(); ctx->d_dist.release(); ctx->d_mask.release();
-  ctx->d_partial.release(); ctx->d_qlist.release(); ctx->d_tc.release(); ctx->d_ref.release();
+  ctx->d_partial.release(); ctx->d_qlist.release(); ctx->d_tc.release(); ctx->d_ref.release(); ctx->d_maskn.release();
   ctx->h_q.release(); ctx->h_rows.release(); ctx->h_dist.release(); ctx->h_flags.release();
   cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_stop);
   cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
@@ -316,17 +316,20 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
     bool want = e ? std::atoi(e) != 0 : c->dim >= 256;
     if (want && c->n >= 4096) {
       c->pitch_b = (c->dim + 7) & ~7;
-      cudaError_t me = cudaMalloc(&c->Xb, size_t(c->n) * c->pitch_b * 2);
+      const int n_kb = (c->pitch_b + 63) / 64;
+      const int64_t n_tiles = (c->n + fx::TC_BN - 1) / fx::TC_BN;
+      const size_t shadow_bytes = size_t(n_tiles) * n_kb * fx::TC_BN * 64 * 2;
+      cudaError_t me = cudaMalloc(&c->Xb, shadow_bytes);
       if (me != cudaSuccess) { cudaGetLastError(); c->Xb = nullptr; }   // not fatal: the TF32 filter needs no shadow
       if (c->Xb) {
-        const int64_t total = c->n * int64_t(c->pitch_b / 2);
+        const int64_t total = int64_t(shadow_bytes / 4);
         int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
-        fx::to_bf16_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim,
-                                                                 static_cast<__nv_bfloat16*>(c->Xb), c->pitch_b);
+        fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim,
+                                                                  static_cast<__nv_bfloat16*>(c->Xb), n_kb, n_tiles);
         FX_CUDA(cudaGetLastError());
         FX_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->launches++; c->stats.kernel_launches++;
-        c->stats.device_bytes += int64_t(size_t(c->n) * c->pitch_b * 2);
+        c->stats.device_bytes += int64_t(shadow_bytes);
       }
     }
   }
@@ -450,7 +453,7 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
   fx_ctx* ctx = c->ctx;
   FX_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
   int path = 0;   // 0 exact scan, 1 tensor-core TF32 filter, 2 tensor-core bf16 filter
-  const bool want_tc = precision != FX_PREC_EXACT_SCAN && d_mask == nullptr &&
+  const bool want_tc = precision != FX_PREC_EXACT_SCAN &&
                        fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q));
   if (c->n == 0) {
     // empty shard: all pads
@@ -462,6 +465,18 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
     fx::TcSearch s{};
     s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
     s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = d_q; s.n_q = int(n_q); s.metric = metric; s.k = k;
+    if (d_mask) {
+      // predicate filter: masked rows get an epilogue term that can never pass (-inf / NaN)
+      const int64_t n_alloc = ((c->n + 255) / 256) * 256;
+      FX_TRY(ctx->d_maskn.ensure(size_t(n_alloc) * sizeof(float)));
+      float* mn = static_cast<float*>(ctx->d_maskn.p);
+      const int mode = metric == 0 ? 0 : (metric == 1 ? 1 : 2);
+      fx::masked_norms_kernel<<<int(std::min<int64_t>((n_alloc + 255) / 256, int64_t(ctx->sm_count) * 8)), 256, 0, ctx->stream>>>(
+          d_mask, metric == 1 ? c->rx : c->hx, c->n, n_alloc, mode, mn);
+      FX_CUDA(cudaGetLastError());
+      ctx->launches++; c->stats.kernel_launches++;
+      s.hx = mn; s.rx = mn; s.epi_add = 1;
+    }
     s.certify = precision == FX_PREC_FP32; s.out_rows = d_out_rows; s.out_dist = d_out_dist;
     s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.dbg = nullptr; s.tau_fixed = nullptr;
     // operand kind of the filter: exact mode takes the bf16 shadow when the shard has one
@@ -536,7 +551,7 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
         FX_TRY(ctx->d_qlist.ensure(bad.size() * sizeof(int)));
         FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), bad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         FX_TRY(run_exact_scan(c, d_q, int(n_q), static_cast<int*>(ctx->d_qlist.p), int(bad.size()), metric, k,
-                              nullptr, d_out_rows, d_out_dist));
+                              d_mask, d_out_rows, d_out_dist));
         FX_CUDA(cudaStreamSynchronize(ctx->stream));  // `bad` must outlive the H2D copy
         c->stats.fallback_queries += int64_t(bad.size());
       }

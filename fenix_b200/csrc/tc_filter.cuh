@@ -59,7 +59,7 @@ struct TcState {
 };
 struct TcCorpus {
   CUtensorMap map_x;       // [n_rows][pitch] fp32, box 32 x 256, 128B swizzle
-  CUtensorMap map_xb;      // [n_rows][pitch_b] bf16 shadow, box 64 x 256, 128B swizzle
+  CUtensorMap map_xb;      // bf16 shadow, tiled [tile][k-block][256 rows][64], box 64 x 256 = one contiguous 32 KB block
   bool ok = false;
   bool ok_b = false;
 };
@@ -71,6 +71,7 @@ struct TcSearch {
   int kind;                // 0: TF32 filter over the fp32 rows, 1: bf16 filter over the bf16 shadow
   int pitch_b;             // elements per row of the bf16 shadow (multiple of 8)
   const uint32_t* tau_fixed; // refinement pass: preset per-query admission thresholds (ordered encoding) or null
+  int epi_add;               // 1: inner-product search with a row mask -> epilogue adds hx (0 / -inf) like L2
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -280,21 +281,37 @@ __device__ __noinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp
     int idx = i * 32 + int(lane);
     s[i] = (idx < cnt) ? f2ord(__uint_as_float(buf[idx].x)) : 0u;
   }
-  // radix descent: largest v with count(s >= v) >= kp
-  uint32_t v = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    uint32_t cand = v | (1u << bit);
-    int c = 0;
+  // Radix descent for a value v with count(s >= v) >= kp. Bits above the highest bit in which the buffer's
+  // minimum and maximum differ are common to all entries and skipped; the descent stops as soon as at most
+  // kp + 16 entries remain at or above v (any such v is a valid threshold: everything dropped is <= v), and
+  // only runs to bit 0 when many entries are (nearly) equal.
+  uint32_t mx = 0u, mn = 0xffffffffu;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) c += (s[i] >= cand) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= kp) v = cand;
+  for (int i = 0; i < PER; ++i) {
+    mx = max(mx, s[i]);
+    if (i * 32 + int(lane) < cnt) mn = min(mn, s[i]);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  uint32_t v = mn;
+  if (mx != mn && cnt > kp) {
+    const int top = 31 - __clz(mx ^ mn);
+    v = (top == 31) ? 0u : (mx & ~((2u << top) - 1u));
+    int c_v = cnt;
+    for (int bit = top; bit >= 0 && c_v > kp + 16; --bit) {
+      uint32_t cand = v | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) c += (s[i] >= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= kp) { v = cand; c_v = c; }
+    }
   }
   int n_gt = 0;
 #pragma unroll
   for (int i = 0; i < PER; ++i) n_gt += (s[i] > v) ? 1 : 0;
   n_gt = __reduce_add_sync(0xffffffffu, n_gt);
-  int ties_left = kp - n_gt;   // >= 1
+  int ties_left = max(kp - n_gt, 0);
   int out = 0;
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -411,7 +428,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             unsigned char* a_dst = tiles + stage * TC_STAGE_BYTES;
             constexpr int kElemsPerBlock = KIND == 0 ? TC_BK : 2 * TC_BK;
             tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * kElemsPerBlock, qt * TC_BM);
-            tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * kElemsPerBlock, t * TC_BN);
+            if (KIND == 0) tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * kElemsPerBlock, t * TC_BN);
+            else tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0, (t * p.n_kblocks + kb) * TC_BN);  // tiled shadow: one contiguous 32 KB block
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -858,15 +876,41 @@ __global__ void refine_scatter_kernel(const int* __restrict__ qlist, const int* 
   }
 }
 
-// fp32 rows -> bf16 shadow rows (round to nearest even), pad columns zero.
-__global__ void to_bf16_rows_kernel(const float* __restrict__ X, int64_t n_rows, int pitch, int dim,
-                                    __nv_bfloat16* __restrict__ Xb, int pitch_b) {
-  const int64_t total = n_rows * int64_t(pitch_b >> 1);
+// Masked search (reference: `data.filter(expr)` before the distance column, index.py:161): fold the row mask
+// into the per-row epilogue term so masked rows can never pass the threshold test:
+//   additive term (L2: -0.5|x|^2, IP: 0) -> -inf;  multiplicative term (cosine 1/|x|) -> NaN (NaN > tau is false)
+__global__ void masked_norms_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ base, int64_t n_rows,
+                                    int64_t n_alloc, int mode /*0 add-from-base, 1 mul-from-base, 2 add-zero*/,
+                                    float* __restrict__ out) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_alloc; i += int64_t(gridDim.x) * blockDim.x) {
+    float v;
+    if (i >= n_rows) v = 0.f;
+    else if (mask[i]) v = mode == 2 ? 0.f : base[i];
+    else v = mode == 1 ? __int_as_float(0x7fc00000) : -INFINITY;
+    out[i] = v;
+  }
+}
+
+// fp32 rows -> bf16 shadow (round to nearest even) in the filter's streaming layout: for every corpus tile of
+// 256 rows and every k-block of 64 elements, the 256 x 64 sub-block is stored contiguously (32 KB), i.e.
+//   element (r, d) lives at ((tile * KB + kb) * 256 + r % 256) * 64 + d % 64,  tile = r / 256, kb = d / 64.
+// One TMA box of the filter kernel is then a single contiguous 32 KB read. Pad rows / columns are zero.
+__global__ void to_bf16_tiled_kernel(const float* __restrict__ X, int64_t n_rows, int pitch, int dim,
+                                     __nv_bfloat16* __restrict__ Xb, int n_kb, int64_t n_tiles) {
+  const int64_t total = n_tiles * n_kb * int64_t(TC_BN) * 32;   // bf16 pairs
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t r = i / (pitch_b >> 1);
-    const int d = int(i - r * (pitch_b >> 1)) * 2;
-    const float a = d < dim ? X[size_t(r) * pitch + d] : 0.f;
-    const float b = d + 1 < dim ? X[size_t(r) * pitch + d + 1] : 0.f;
+    const int dd = int(i & 31) * 2;
+    const int64_t line = i >> 5;                      // (tile * KB + kb) * 256 + rr
+    const int rr = int(line % TC_BN);
+    const int64_t blk = line / TC_BN;
+    const int kb = int(blk % n_kb);
+    const int64_t r = (blk / n_kb) * TC_BN + rr;
+    const int d = kb * 64 + dd;
+    float a = 0.f, b = 0.f;
+    if (r < n_rows) {
+      if (d < dim) a = X[size_t(r) * pitch + d];
+      if (d + 1 < dim) b = X[size_t(r) * pitch + d + 1];
+    }
     reinterpret_cast<__nv_bfloat162*>(Xb)[i] = __floats2bfloat162_rn(a, b);
   }
 }
@@ -924,7 +968,10 @@ inline bool tc_bind_corpus(TcState* st, TcCorpus* tc, const float* X, int64_t n_
   if (!tc_encode_2d(st, &tc->map_x, X, uint64_t(pitch), uint64_t(n_rows), uint64_t(pitch), TC_BK, TC_BN, err)) return false;
   tc->ok = true;
   if (Xb != nullptr) {
-    if (!tc_encode_2d(st, &tc->map_xb, Xb, uint64_t(pitch_b), uint64_t(n_rows), uint64_t(pitch_b), 2 * TC_BK, TC_BN, err, true)) return false;
+    // tiled shadow: a flat list of 128-byte lines, 256 lines per (tile, k-block)
+    const uint64_t n_kb = uint64_t((pitch_b + 2 * TC_BK - 1) / (2 * TC_BK));
+    const uint64_t lines = uint64_t((n_rows + TC_BN - 1) / TC_BN) * n_kb * TC_BN;
+    if (!tc_encode_2d(st, &tc->map_xb, Xb, uint64_t(2 * TC_BK), lines, uint64_t(2 * TC_BK), 2 * TC_BK, TC_BN, err, true)) return false;
     tc->ok_b = true;
   }
   return true;
@@ -1051,13 +1098,14 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
   p.tau_u = tau_u; p.n_pub = pl.n_pub; p.rank_r = pl.rank_r; p.rank_m = pl.rank_m; p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
   if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);
+  const int epi = (s.metric == 2 && s.epi_add) ? 0 : s.metric;   // epilogue form: 0 add, 1 multiply, 2 none
   if (s.kind == 0) {
-    if (s.metric == 0) knn_tc_filter_kernel<0, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
-    else if (s.metric == 1) knn_tc_filter_kernel<1, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+    if (epi == 0) knn_tc_filter_kernel<0, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
+    else if (epi == 1) knn_tc_filter_kernel<1, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
     else knn_tc_filter_kernel<2, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
   } else {
-    if (s.metric == 0) knn_tc_filter_kernel<0, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
-    else if (s.metric == 1) knn_tc_filter_kernel<1, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
+    if (epi == 0) knn_tc_filter_kernel<0, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
+    else if (epi == 1) knn_tc_filter_kernel<1, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
     else knn_tc_filter_kernel<2, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
   }
   if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);

@@ -251,6 +251,32 @@ def test_tensor_core_path_runs_and_certifies(ctx):
     c.close()
 
 
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_masked_search_on_tensor_core_path(ctx, metric):
+    """Row mask (the device form of index.py:161 filter) folded into the filter epilogue: same answer as the
+    masked fp64 scan and as the oracle run on the surviving rows."""
+    rng = np.random.default_rng(123)
+    corpus = rng.standard_normal((20000, 64), dtype=np.float32)
+    queries = rng.standard_normal((70, 64), dtype=np.float32)
+    mask = (rng.random(20000) < 0.3).astype(np.uint8)
+    mask[:300] = 0
+    c = make_corpus(ctx, corpus)
+    rows, dist = c.search(queries, metric, 10, knn.PREC_FP32, row_mask=mask)
+    assert c.stats().last_path >= 1
+    assert mask[rows].all()
+    rows_s, dist_s = c.search(queries, metric, 10, knn.PREC_EXACT_SCAN, row_mask=mask)
+    assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
+    live = np.nonzero(mask)[0]
+    want_rows, want_dist = brute_force_f64(corpus[live], queries, metric, 10)
+    assert np.array_equal(rows, live[want_rows])
+    # a mask that leaves fewer than k rows: pads, through the fallback tiers
+    few = np.zeros(20000, np.uint8)
+    few[[5, 77, 19000]] = 1
+    rows, dist = c.search(queries[:3], metric, 10, knn.PREC_FP32, row_mask=few)
+    assert (np.sort(rows[:, :3], axis=1) == np.array([5, 77, 19000])).all() and (rows[:, 3:] == -1).all()
+    c.close()
+
+
 def test_refinement_pass_settles_ties_and_near_ties(ctx):
     """Duplicates defeat the first-pass certificate (K' equal scores); the preset-threshold refinement pass must
     then produce the exact (distance, row) answer without the full fp64 scan."""
