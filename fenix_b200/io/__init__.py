@@ -1,6 +1,6 @@
 """Host-side mirror of the reference's `fenix.io` namespace for the exact-search path
 (src/fenix/io/__init__.py:1-2): `io.index.call` is the seam the Flight handler dispatches to."""
-from . import arrow, coder, index, shards, table
+from . import arrow, batcher, coder, index, shards, table
 from .index import call
 
-__all__ = ["arrow", "coder", "index", "shards", "table", "call"]
+__all__ = ["arrow", "batcher", "coder", "index", "shards", "table", "call"]

@@ -23,6 +23,9 @@ import pyarrow.compute as pc
 from .. import knn
 from . import shards as _shards
 from . import table as _table
+from .batcher import MicroBatcher
+
+_batcher = MicroBatcher()
 
 CODE_COL: str = "__CODED_ID__"
 DIST_COL: str = "__DISTANCE__"
@@ -99,7 +102,7 @@ def call(
         shard = _shards.from_chunks(data.column(column))
         owned = True
     else:
-        data = _table.load(root, source)
+        data = _shards.load_table(root, source)   # raises like table.load when the file is missing
         shard = _shards.get(root, source, column, data)
         owned = False
 
@@ -126,7 +129,13 @@ def call(
             if batched:
                 empty = empty.append_column(QUERY_COL, pa.array([], type=pa.int32()))
             return empty.combine_chunks()
-        rows, dist = shard.search(queries, metric, k, precision, mask)
+        if not batched and mask is None and not owned and _batcher.enabled:
+            # concurrent single-query RPCs against the same table/metric/k share one pass over the corpus
+            key = (id(shard), metric, k, precision)
+            r1, d1 = _batcher.submit(key, queries[0], lambda qs: shard.search(qs, metric, k, precision, None))
+            rows, dist = r1[None, :], d1[None, :]
+        else:
+            rows, dist = shard.search(queries, metric, k, precision, mask)
 
         keep = rows.reshape(-1) >= 0
         flat_rows = rows.reshape(-1)[keep]

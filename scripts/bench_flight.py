@@ -1,0 +1,91 @@
+"""BASELINE.json configs[0]: exact L2 k=10 over 100k x 128 fp32, 1k queries through the Flight server.
+
+Runs the fenix_b200 server + client over loopback (sequential single-query RPCs, as the reference serves
+them, then the batched wire extension), and the same server class with io.index.call swapped for the oracle
+port of the reference's CPU path (so both arms pay the same RPC cost). Prints one JSON line per arm."""
+import json, os, sys, time, tempfile, shutil
+import numpy as np
+import pyarrow as pa
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fenix_b200 as fenix
+from fenix_b200 import io as fio
+
+N, D, K, NQ, CHUNK = 100_000, 128, 10, 1000, 1000
+rng = np.random.default_rng(1001)
+corpus = rng.standard_normal((N, D), dtype=np.float32)
+queries = np.random.default_rng(2001).standard_normal((NQ, D), dtype=np.float32)
+batches = []
+for lo in range(0, N, CHUNK):
+    x = corpus[lo:lo + CHUNK]
+    batches.append(pa.record_batch([pa.array(np.arange(lo, lo + CHUNK, dtype=np.int64)),
+                                    pa.FixedSizeListArray.from_arrays(pa.array(x.reshape(-1)), D)], names=["id", "vector"]))
+table = pa.Table.from_batches(batches)
+root = tempfile.mkdtemp(prefix="fenix_c1_")
+port = 9311
+server = fenix.Server(root, "127.0.0.1", port)
+client = fenix.Flight("127.0.0.1", port)
+client.make_table("c1", table.to_reader())
+
+def run(label, n_q, fn):
+    fn(0)
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(n_q):
+        t1 = time.perf_counter(); fn(i); lat.append(time.perf_counter() - t1)
+    dt = time.perf_counter() - t0
+    lat = np.array(lat) * 1e3
+    print(json.dumps({"arm": label, "queries": n_q, "qps": n_q / dt, "p50_ms": float(np.median(lat)), "p99_ms": float(np.percentile(lat, 99))}), flush=True)
+
+ours = {}
+def ours_single(i):
+    ours[i] = client.search(queries[i], "c1", "vector", "l2", select=["id"], maxval=K)
+run("fenix_b200 Flight, 1 query per RPC (GPU)", NQ, ours_single)
+client.search(queries, "c1", "vector", "l2", select=["id"], maxval=K)   # warm-up (scratch growth for a 1000-query batch)
+t0 = time.perf_counter()
+for _ in range(5):
+    out = client.search(queries, "c1", "vector", "l2", select=["id"], maxval=K)
+dt = (time.perf_counter() - t0) / 5
+print(json.dumps({"arm": "fenix_b200 Flight, batched wire extension: 1000 queries in one RPC (GPU)", "queries": NQ, "qps": NQ / dt, "ms_per_rpc": dt * 1e3}), flush=True)
+
+# concurrent clients: 16 threads, each with its own connection, sequential single-query RPCs
+import threading
+def concurrent(label, n_threads=16, per_thread=125):
+    clients = [fenix.Flight("127.0.0.1", port) for _ in range(n_threads)]
+    for c in clients:
+        c.search(queries[0], "c1", "vector", "l2", select=["id"], maxval=K)
+    res = {}
+    def work(t):
+        for j in range(per_thread):
+            i = t * per_thread + j
+            res[i] = clients[t].search(queries[i % NQ], "c1", "vector", "l2", select=["id"], maxval=K)
+    b0, r0 = fio.index._batcher.batches, fio.index._batcher.requests
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    t0 = time.perf_counter()
+    for t in ths: t.start()
+    for t in ths: t.join()
+    dt = time.perf_counter() - t0
+    nb, nr = fio.index._batcher.batches - b0, fio.index._batcher.requests - r0
+    ok = all(sorted(res[i].column("id").to_pylist()) == sorted(ours[i % NQ].column("id").to_pylist()) for i in range(0, n_threads * per_thread, 37))
+    print(json.dumps({"arm": label, "queries": n_threads * per_thread, "qps": n_threads * per_thread / dt,
+                      "gpu_batches": nb, "mean_batch": (nr / nb if nb else None), "same_as_sequential": ok}), flush=True)
+wait = fio.index._batcher.max_wait
+fio.index._batcher.max_wait = 0.0
+concurrent("fenix_b200 Flight, 16 concurrent clients, micro-batching OFF")
+fio.index._batcher.max_wait = wait
+concurrent("fenix_b200 Flight, 16 concurrent clients, micro-batching ON (300 us window)")
+
+# reference arm: same server, CPU path of the reference (oracle port) behind io.index.call
+from oracle import call as oracle_call
+real_call = fio.index.call
+def cpu_call(root_, coding, source, column, target, metric=None, select=None, filter=None, maxval=None, probes=None):
+    data = fio.table.load(root_, source)
+    return oracle_call(data, column, target, metric, select=select, filter=filter, maxval=maxval)
+fio.index.call = cpu_call
+ref = {}
+def ref_single(i):
+    ref[i] = client.search(queries[i], "c1", "vector", "l2", select=["id"], maxval=K)
+run("reference CPU path (oracle port) behind the same Flight server", 100, ref_single)
+fio.index.call = real_call
+same = sum(sorted(ours[i].column("id").to_pylist()) == sorted(ref[i].column("id").to_pylist()) for i in range(100))
+print(json.dumps({"parity": f"{same}/100 queries return identical id sets"}), flush=True)
+client.remove(); server.shutdown(); shutil.rmtree(root, ignore_errors=True)

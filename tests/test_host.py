@@ -138,3 +138,40 @@ def test_search_command_wire_format(monkeypatch):
     # wire extension: 2-D target -> FixedSizeList column with Q rows
     client.search(np.zeros((3, 4), dtype=np.float32), "s", "vector", "l2", maxval=2)
     assert pa.types.is_fixed_size_list(seen["table"].schema.field("target").type) and seen["table"].num_rows == 3
+
+
+def test_micro_batcher_coalesces_concurrent_requests():
+    """Concurrent submissions under one key run as ONE batched call; a lone request runs at once."""
+    import threading
+    import time
+
+    from fenix_b200.io.batcher import MicroBatcher
+
+    calls = []
+
+    def runner(qs):
+        calls.append(len(qs))
+        time.sleep(0.02)  # a slow "search" so that peers pile up behind the first leader
+        return qs.sum(axis=1, keepdims=True).astype(np.int64), qs[:, :1].astype(np.float32)
+
+    mb = MicroBatcher(max_wait_us=20000, max_batch=64)
+    t0 = time.perf_counter()
+    r, d = mb.submit("k", np.full(4, 7.0, np.float32), runner)
+    assert time.perf_counter() - t0 < 0.035 and r[0] == 28 and calls == [1]   # lonely => no waiting
+    out = {}
+
+    def client(i):
+        out[i] = mb.submit("k", np.full(4, float(i), np.float32), runner)
+
+    threads = [threading.Thread(target=client, args=(i,)) for i in range(24)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert all(out[i][0][0] == 4 * i and out[i][1][0] == float(i) for i in range(24))
+    assert sum(calls) == 25 and len(calls) < 12, calls     # far fewer calls than requests
+    # failures propagate to every member of the batch
+    def boom(qs):
+        raise RuntimeError("device lost")
+    with pytest.raises(RuntimeError):
+        mb.submit("x", np.zeros(4, np.float32), boom)
