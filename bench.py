@@ -34,6 +34,8 @@ CONFIGS = {
     "c4": dict(n=100_000_000, d=96, metric="inner_product", k=100, q=10_000, num=4,
                label="100M x 96 inner product (Deep-100M shape), k=100, 10k-query batch"),
 }
+CONFIGS["c4s"] = dict(n=12_500_000, d=96, metric="inner_product", k=100, q=10_000, num=4,
+                      label="one 8-GPU shard of C4: 12.5M x 96 inner product, k=100, 10k-query batch")
 for _b in (1, 2, 4, 8, 16, 32, 64):
     CONFIGS[f"c5_{_b}"] = dict(n=10_000_000, d=768, metric="cosine", k=10, q=_b, num=5,
                                label=f"latency sweep batch {_b}, k=10 over 10M x 768")

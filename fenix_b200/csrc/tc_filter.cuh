@@ -39,10 +39,15 @@ constexpr int TC_BK = 32;                  // fp32 elements per k-block = 128 B 
 constexpr int TC_UMMA_K = 8;               // kind::tf32: 32 bytes of K per instruction
 constexpr int TC_STAGES = 4;
 constexpr int TC_ACC_STAGES = 2;           // 2 x 256 TMEM columns = all 512
-constexpr int TC_THREADS = 384;            // 12 warps
-constexpr int TC_EPI_WARPS = 8;
+#ifndef FENIX_TC_SPLIT
+#define FENIX_TC_SPLIT 2                   // column split of an accumulator among epilogue warp groups (2 or 4)
+#endif
+constexpr int TC_SPLIT = FENIX_TC_SPLIT;
+constexpr int TC_EPI_WARPS = 4 * TC_SPLIT; // 4 warps cover the 128 TMEM lanes; TC_SPLIT groups split the columns
+constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
 constexpr int TC_EPI_FIRST_WARP = 4;
-constexpr int TC_HALF_COLS = TC_BN / 2;    // columns per epilogue warp-group
+constexpr int TC_HALF_COLS = TC_BN / TC_SPLIT;   // columns per epilogue warp group ("part")
+constexpr int TC_SLOTS = TC_SPLIT * TC_BM;       // candidate buffers per unit
 constexpr int TC_CW = 16;                  // accumulator columns per tcgen05.ld in the epilogue
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
@@ -484,13 +489,20 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
       const int q = qt * TC_BM + row_in_tile;
       const bool active = q < p.n_q;
-      uint2* buf = p.wbuf + (size_t(u) * (2 * TC_BM) + slot) * p.cap;
+      uint2* buf = p.wbuf + (size_t(u) * TC_SLOTS + slot) * p.cap;
       int cnt = 0;
       float tau = active ? -INFINITY : INFINITY;   // lanes past the last query never admit anything
       if (p.fixed && active) tau = ord2f(p.tau_g[q]);
+      // the shared threshold is re-read once per tile; the load is issued a tile ahead so its L2 latency
+      // (hundreds of cycles) never sits on the critical path of the first compare
+      const bool poll = active && !p.fixed;
+      uint32_t tg_next = poll ? ld_relaxed_u32(p.tau_g + q) : ORD_NEG_INF;
 
       for (int t = t0; t < t1; ++t) {
-        if (active && !p.fixed) tau = fmaxf(tau, ord2f(ld_relaxed_u32(p.tau_g + q)));
+        if (poll) {
+          tau = fmaxf(tau, ord2f(tg_next));
+          tg_next = ld_relaxed_u32(p.tau_g + q);
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         if (METRIC != 2) mbar_wait(&norm_full[acc], acc_phase);
         tc_fence_after();
@@ -563,7 +575,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           // published values has >= m * r >= K' rows at or above it, so it is a valid (and far tighter)
           // admission threshold for every list of the query
           uint32_t w_ord = 0u;
-          const int list_id = slice * 2 + half;
+          const int list_id = slice * TC_SPLIT + half;
           if (list_id < p.n_pub) {
             const int q_src = __shfl_sync(0xffffffffu, q, src);
             uint32_t* tu = p.tau_u + size_t(q_src) * p.n_pub;
@@ -585,7 +597,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
 
       // end of unit: the finish kernel reads the buffer in place
-      p.wcnt[size_t(u) * (2 * TC_BM) + slot] = active ? cnt : 0;
+      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? cnt : 0;
     }
   }
 
@@ -654,7 +666,7 @@ knn_tc_finish_kernel(FinishParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_warps = blockDim.x >> 5;
   const int qt = q / TC_BM, r = q - qt * TC_BM;
-  const int n_lists = 2 * p.n_slices;
+  const int n_lists = TC_SPLIT * p.n_slices;
 
   for (int d = tid; d < p.pitch; d += blockDim.x) qs[d] = p.Qp[size_t(q) * p.pitch + d];
   if (tid == 0) { s_n_gt = 0; s_n_tie = 0; s_prefix = 0; s_remaining = p.kp; }
@@ -671,9 +683,9 @@ knn_tc_finish_kernel(FinishParams p) {
 
   // list l = (slice, half): buffer of thread slot half*128 + r of unit slice*n_qt + qt
   auto list_ptr = [&](int l, int& count) -> const uint2* {
-    const int slice = l >> 1, half = l & 1;
+    const int slice = l / TC_SPLIT, half = l % TC_SPLIT;
     const size_t unit = p.qt_major ? size_t(qt) * p.n_slices + slice : size_t(slice) * p.n_qt + qt;
-    const size_t unit_slot = unit * (2 * TC_BM) + half * TC_BM + r;
+    const size_t unit_slot = unit * TC_SLOTS + half * TC_BM + r;
     count = p.wcnt[unit_slot];
     return p.wbuf + unit_slot * p.cap;
   };
@@ -997,6 +1009,7 @@ inline bool tc_supported(const TcState* st, const TcCorpus* tc, int64_t n_rows, 
 struct TcPlan {
   int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks;
   int n_pub, rank_r, rank_m, qt_major;
+  int kp_list;   // candidates each (query, list) keeps at a selection (<= kp)
   size_t off_qp, off_qb, off_tau, off_flags, off_tau_u, off_wcnt, off_wbuf, total;
 };
 
@@ -1038,6 +1051,18 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.n_slices = best_s;
   pl.tiles_per_slice = (pl.n_tiles + best_s - 1) / best_s;
   pl.units = pl.n_slices * pl.n_qt;
+  // Each query's candidates are spread over L = TC_SPLIT * n_slices lists. A list does not need to keep K'
+  // entries: the global top-k lands ~k/L per list, so keeping 2k/L + 16 (>= 32) per list gives much tighter
+  // local thresholds (fewer appends and selections). If a query's neighbours are concentrated in few lists
+  // the certificate fails and the refinement pass settles it.
+  {
+    const int lists = TC_SPLIT * pl.n_slices;
+    int m = std::max(32, (2 * s.k + lists - 1) / lists + 16);
+    m = (m + 31) & ~31;
+    pl.kp_list = s.tau_fixed ? pl.kp : std::min(pl.kp, m);
+    if (const char* e = std::getenv("FENIX_TC_KP_LIST")) { int f = std::atoi(e); if (f >= 32) pl.kp_list = std::min(pl.kp, (f + 31) & ~31); }
+    pl.cap = s.tau_fixed ? pl.cap : tc_cap(pl.kp_list);
+  }
   pl.grid = int(std::min<long>(pl.units, sms));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
@@ -1047,12 +1072,12 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.off_flags = take(size_t(s.n_q) * 4);
   // cross-list threshold publication is off by default: on C3 it costs more than it saves (120 vs 94 ms)
   pl.n_pub = 0;
-  if (const char* e = std::getenv("FENIX_TC_PUBLISH")) { if (std::atoi(e) != 0) pl.n_pub = std::min(2 * pl.n_slices, 512); }
+  if (const char* e = std::getenv("FENIX_TC_PUBLISH")) { if (std::atoi(e) != 0) pl.n_pub = std::min(TC_SPLIT * pl.n_slices, 512); }
   pl.rank_r = pl.n_pub ? (pl.kp + pl.n_pub - 1) / pl.n_pub : 1;
   pl.rank_m = (pl.kp + pl.rank_r - 1) / pl.rank_r;
   pl.off_tau_u = take(size_t(s.n_q) * std::max(pl.n_pub, 1) * 4);
-  pl.off_wcnt = take(size_t(pl.units) * 2 * TC_BM * 4);
-  pl.off_wbuf = take(size_t(pl.units) * 2 * TC_BM * pl.cap * 8);
+  pl.off_wcnt = take(size_t(pl.units) * TC_SLOTS * 4);
+  pl.off_wbuf = take(size_t(pl.units) * TC_SLOTS * pl.cap * 8);
   pl.total = off;
   return pl;
 }
@@ -1094,7 +1119,7 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
 
   TcParams p{};
   p.n_q = s.n_q; p.n_qt = pl.n_qt; p.n_rows = s.n_rows; p.n_tiles = pl.n_tiles; p.n_slices = pl.n_slices;
-  p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.kp = pl.kp; p.cap = pl.cap;
+  p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.kp = pl.kp_list; p.cap = pl.cap;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
   p.tau_u = tau_u; p.n_pub = pl.n_pub; p.rank_r = pl.rank_r; p.rank_m = pl.rank_m; p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
   if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);

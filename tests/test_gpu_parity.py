@@ -240,14 +240,15 @@ def test_tensor_core_path_runs_and_certifies(ctx):
         before = c.stats()
         rows, dist = c.search(queries, metric, 10, knn.PREC_FP32)
         after = c.stats()
-        assert after.last_path == 1, "tensor-core path not taken"
+        assert after.last_path in (1, 2), "tensor-core path not taken"   # 2: bf16-shadow filter (default)
         assert after.fallback_queries - before.fallback_queries <= 3, "certificate fails on gaussian data"
         rows_s, dist_s = c.search(queries, metric, 10, knn.PREC_EXACT_SCAN)
         assert c.stats().last_path == 0
         assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
-        rows_t, dist_t = c.search(queries, metric, 10, knn.PREC_TF32)
-        recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(rows, rows_t)])
-        assert recall >= 0.99, recall
+        for approx in (knn.PREC_TF32, knn.PREC_BF16):
+            rows_t, dist_t = c.search(queries, metric, 10, approx)
+            recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(rows, rows_t)])
+            assert recall >= 0.98, (approx, recall)
     c.close()
 
 
