@@ -487,7 +487,9 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int qt = p.qt_major ? u / p.n_slices : u % p.n_qt, slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
-      const int q = qt * TC_BM + row_in_tile;
+      // tile row j = lane_grp*32 + lane holds query qt*128 + lane*4 + lane_grp (see knn_prep_kernel): a small
+      // batch is spread over all four lane groups, i.e. over all epilogue warps and SM sub-partitions
+      const int q = qt * TC_BM + int(lane) * 4 + lane_grp;
       const bool active = q < p.n_q;
       uint2* buf = p.wbuf + (size_t(u) * TC_SLOTS + slot) * p.cap;
       int cnt = 0;
@@ -531,7 +533,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
             if (p.dbg != nullptr && u == 0 && t == t0) {
 #pragma unroll
-              for (int j = 0; j < TC_CW; ++j) p.dbg[row_in_tile * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
+              for (int j = 0; j < TC_CW; ++j) p.dbg[(int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
             }
             if (__any_sync(0xffffffffu, any)) {
               const uint32_t col_base = uint32_t(col0 + c);
@@ -616,16 +618,23 @@ __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, i
                                 uint32_t* __restrict__ tau_g, int* __restrict__ flags,
                                 uint32_t* __restrict__ tau_u, int n_pub, __nv_bfloat16* __restrict__ Qb, int pitch_b,
                                 const uint32_t* __restrict__ tau_fixed) {
-  const int64_t total = int64_t(n_q) * pitch;
+  // Rows are written in TILE order: row qt*128 + j holds query qt*128 + (j % 32) * 4 + j / 32 (zeros past the last
+  // query), so that consecutive queries land in different TMEM lane groups.
+  const int n_rows_p = ((n_q + TC_BM - 1) / TC_BM) * TC_BM;
+  const int64_t total = int64_t(n_rows_p) * pitch;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    int q = int(i / pitch), d = int(i - int64_t(q) * pitch);
-    Qp[i] = d < dim ? Q[size_t(q) * dim + d] : 0.f;
+    int row = int(i / pitch), d = int(i - int64_t(row) * pitch);
+    int j = row % TC_BM;
+    int q = row - j + (j % 32) * 4 + j / 32;
+    Qp[i] = (d < dim && q < n_q) ? Q[size_t(q) * dim + d] : 0.f;
   }
   if (Qb != nullptr) {
-    const int64_t total_b = int64_t(n_q) * pitch_b;
+    const int64_t total_b = int64_t(n_rows_p) * pitch_b;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total_b; i += int64_t(gridDim.x) * blockDim.x) {
-      int q = int(i / pitch_b), d = int(i - int64_t(q) * pitch_b);
-      Qb[i] = __float2bfloat16_rn(d < dim ? Q[size_t(q) * dim + d] : 0.f);
+      int row = int(i / pitch_b), d = int(i - int64_t(row) * pitch_b);
+      int j = row % TC_BM;
+      int q = row - j + (j % 32) * 4 + j / 32;
+      Qb[i] = __float2bfloat16_rn((d < dim && q < n_q) ? Q[size_t(q) * dim + d] : 0.f);
     }
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += gridDim.x * blockDim.x) {
@@ -665,10 +674,12 @@ knn_tc_finish_kernel(FinishParams p) {
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_warps = blockDim.x >> 5;
-  const int qt = q / TC_BM, r = q - qt * TC_BM;
+  const int qt = q / TC_BM, w = q - qt * TC_BM;
+  const int r = (w % 4) * 32 + w / 4;               // tile row / candidate-buffer slot of this query
+  const size_t q_row = size_t(qt) * TC_BM + r;      // its row in the (tile-ordered) padded query matrix
   const int n_lists = TC_SPLIT * p.n_slices;
 
-  for (int d = tid; d < p.pitch; d += blockDim.x) qs[d] = p.Qp[size_t(q) * p.pitch + d];
+  for (int d = tid; d < p.pitch; d += blockDim.x) qs[d] = p.Qp[q_row * p.pitch + d];
   if (tid == 0) { s_n_gt = 0; s_n_tie = 0; s_prefix = 0; s_remaining = p.kp; }
   __syncthreads();
   if (warp == 0) {
@@ -1066,8 +1077,9 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.grid = int(std::min<long>(pl.units, sms));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-  pl.off_qp = take(size_t(s.n_q) * s.pitch * 4);
-  pl.off_qb = take(s.kind == 1 ? size_t(s.n_q) * s.pitch_b * 2 : 0);
+  const size_t q_rows_p = size_t(pl.n_qt) * TC_BM;   // queries are stored in whole tiles
+  pl.off_qp = take(q_rows_p * s.pitch * 4);
+  pl.off_qb = take(s.kind == 1 ? q_rows_p * s.pitch_b * 2 : 0);
   pl.off_tau = take(size_t(s.n_q) * 4);
   pl.off_flags = take(size_t(s.n_q) * 4);
   // cross-list threshold publication is off by default: on C3 it costs more than it saves (120 vs 94 ms)
@@ -1108,13 +1120,13 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   __nv_bfloat16* qb = s.kind == 1 ? reinterpret_cast<__nv_bfloat16*>(base + pl.off_qb) : nullptr;
   CUtensorMap map_q;
   if (s.kind == 0) {
-    if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(s.n_q), uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
+    if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(pl.n_qt) * TC_BM, uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
   } else {
     if (!tc->ok_b) { *err = "bf16 filter requested but the shard has no bf16 shadow"; return false; }
-    if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(s.n_q), uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
+    if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(pl.n_qt) * TC_BM, uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
   }
 
-  const int prep_blocks = int(std::min<int64_t>((int64_t(s.n_q) * s.pitch + 255) / 256, 4 * 148));
+  const int prep_blocks = int(std::min<int64_t>((int64_t(pl.n_qt) * TC_BM * s.pitch + 255) / 256, 4 * 148));
   knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags, tau_u, pl.n_pub, qb, s.pitch_b, s.tau_fixed);
 
   TcParams p{};
