@@ -262,10 +262,6 @@ struct TcParams {
   uint2* wbuf;            // [units][256][cap] candidate buffers (score bits, row), one per (unit, epilogue thread)
   int* wcnt;              // [units][256] entries left in each buffer when its unit finished
   uint32_t* tau_g;        // [n_q] shared per-query threshold, ordered-uint encoding
-  uint32_t* tau_u;        // [n_q][n_pub] rank-r score of each candidate list (0 = not published yet)
-  int n_pub;              // lists that publish (min(2 * n_slices, 512))
-  int rank_r;             // each list publishes its r-th best score, r = ceil(K' / n_pub)
-  int rank_m;             // ceil(K' / r): the m-th largest published value has >= K' rows at or above it
   int qt_major;           // unit order: 1 = all slices of a query tile adjacent, 0 = all query tiles of a slice adjacent
   int fixed;              // refinement pass: thresholds are preset in tau_g, no selection; buffer overflow sets flags[q]
   int* flags;             // [n_q]
@@ -341,39 +337,12 @@ __device__ __noinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp
   return v;
 }
 
-// kth largest of n (<= 512) values read with a word stride (2: .x of candidate entries, converted to the
-// ordered encoding; 1: already-ordered u32). Returns 0 when fewer than kth non-zero values exist.
-__device__ __noinline__ uint32_t warp_kth_largest(const uint32_t* base, int n, int stride, int kth) {
-  const uint32_t lane = lane_id();
-  uint32_t s[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    int idx = i * 32 + int(lane);
-    uint32_t w = 0u;
-    if (idx < n) {
-      w = base[size_t(idx) * stride];
-      if (stride == 2) w = f2ord(__uint_as_float(w));
-    }
-    s[i] = w;
-  }
-  uint32_t v = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    uint32_t cand = v | (1u << bit);
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) c += (s[i] >= cand) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= kth) v = cand;
-  }
-  return v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // the filter kernel
 // ---------------------------------------------------------------------------------------------
 // KIND 0: fp32 operands read as TF32 (k-block = 32 elements, UMMA K = 8)
 // KIND 1: bf16 operands          (k-block = 64 elements, UMMA K = 16); both are 128 B rows / 32 B per MMA
-template <int METRIC, int KIND>
+template <int METRIC, int KIND, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -512,13 +481,10 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int ncols = int(min(int64_t(TC_HALF_COLS), p.n_rows - int64_t(col0)));  // valid columns (<=0: none)
         const float* nrm = norm_smem + acc * TC_BN + half * TC_HALF_COLS;
         if (__any_sync(0xffffffffu, active) && ncols > 0) {
-#pragma unroll 1
-          for (int c = 0; c < TC_HALF_COLS; c += TC_CW) {
-            if (c >= ncols) break;
-            uint32_t v[TC_CW];
-            tmem_ld_32x32b_x16(t_lane + uint32_t(acc * TC_BN + c), v);
-            tmem_ld_wait();
-            bool any = false;
+          // One chunk = 16 accumulator columns of this thread's query. Scores are formed in place, the two
+          // 8-column group maxima (independent 3-level trees) give the fast-path test and are reused by the
+          // slow path. The TMEM load of the next chunk is issued before the current one is processed.
+          auto process = [&](uint32_t (&v)[TC_CW], int c) {
 #pragma unroll
             for (int j = 0; j < TC_CW; j += 4) {
               float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -529,28 +495,34 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
               if (METRIC == 1) { s0 *= n4.x; s1 *= n4.y; s2 *= n4.z; s3 *= n4.w; }
               v[j + 0] = __float_as_uint(s0); v[j + 1] = __float_as_uint(s1);
               v[j + 2] = __float_as_uint(s2); v[j + 3] = __float_as_uint(s3);
-              any |= (s0 > tau) | (s1 > tau) | (s2 > tau) | (s3 > tau);
             }
-            if (p.dbg != nullptr && u == 0 && t == t0) {
+            if (DBG) {
+              if (u == 0 && t == t0) {
 #pragma unroll
-              for (int j = 0; j < TC_CW; ++j) p.dbg[(int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
-            }
-            if (__any_sync(0xffffffffu, any)) {
-              const uint32_t col_base = uint32_t(col0 + c);
-              if (ncols - c >= TC_CW) {
-                // full chunk: per group of 8 columns, a warp-uniform test, then predicated appends
-                if (__any_sync(0xffffffffu, max8(v, 0) > tau)) append_group8<0>(v, tau, buf, cnt, col_base);
-                if (__any_sync(0xffffffffu, max8(v, 1) > tau)) append_group8<1>(v, tau, buf, cnt, col_base);
-              } else {
-                // the ragged last tile of the corpus
-                const int lim = ncols - c;
-#pragma unroll
-                for (int j = 0; j < TC_CW; ++j) {
-                  float sj = __uint_as_float(v[j]);
-                  if (j < lim && sj > tau) { buf[cnt] = make_uint2(v[j], col_base + uint32_t(j)); ++cnt; }
-                }
+                for (int j = 0; j < TC_CW; ++j) p.dbg[(int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
               }
             }
+            if (ncols - c < TC_CW) {
+              // the ragged last tile of the corpus: columns past the last row can never pass
+#pragma unroll
+              for (int j = 0; j < TC_CW; ++j) if (c + j >= ncols) v[j] = 0xff800000u;   // -inf
+            }
+            const float m0 = max8(v, 0), m1 = max8(v, 1);
+            if (__any_sync(0xffffffffu, fmaxf(m0, m1) > tau)) {
+              // per group of 8 columns, a warp-uniform test, then predicated appends
+              const uint32_t col_base = uint32_t(col0 + c);
+              if (__any_sync(0xffffffffu, m0 > tau)) append_group8<0>(v, tau, buf, cnt, col_base);
+              if (__any_sync(0xffffffffu, m1 > tau)) append_group8<1>(v, tau, buf, cnt, col_base);
+            }
+          };
+          const uint32_t t_acc = t_lane + uint32_t(acc * TC_BN);
+#pragma unroll 1
+          for (int c = 0; c < TC_HALF_COLS; c += TC_CW) {
+            if (c >= ncols) break;
+            uint32_t va[TC_CW];
+            tmem_ld_32x32b_x16(t_acc + uint32_t(c), va);
+            tmem_ld_wait();
+            process(va, c);
           }
         }
         // release the accumulator stage (and its norm buffer) back to the MMA / TMA warps
@@ -573,27 +545,10 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           int new_cnt;
           uint32_t v_ord = (p.cap == 1024) ? warp_select_compact<32>(b, c_src, p.kp, new_cnt)
                                            : warp_select_compact<16>(b, c_src, p.kp, new_cnt);
-          // cross-list threshold: this list publishes its r-th best score; the m-th largest of the
-          // published values has >= m * r >= K' rows at or above it, so it is a valid (and far tighter)
-          // admission threshold for every list of the query
-          uint32_t w_ord = 0u;
-          const int list_id = slice * TC_SPLIT + half;
-          if (list_id < p.n_pub) {
-            const int q_src = __shfl_sync(0xffffffffu, q, src);
-            uint32_t* tu = p.tau_u + size_t(q_src) * p.n_pub;
-            __syncwarp();
-            const uint32_t u_ord = warp_kth_largest(reinterpret_cast<const uint32_t*>(b), new_cnt, 2, p.rank_r);
-            if (u_ord != 0u) {
-              if (lane == 0) atomicMax(tu + list_id, u_ord);
-              __syncwarp();
-              w_ord = warp_kth_largest(tu, p.n_pub, 1, p.rank_m);
-            }
-          }
           if (int(lane) == src) {
             cnt = new_cnt;
-            const uint32_t best = v_ord > w_ord ? v_ord : w_ord;
-            tau = fmaxf(tau, ord2f(best));
-            atomicMax(p.tau_g + q, best);
+            tau = fmaxf(tau, ord2f(v_ord));
+            atomicMax(p.tau_g + q, v_ord);
           }
         }
       }
@@ -616,7 +571,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // ---------------------------------------------------------------------------------------------
 __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, int pitch, float* __restrict__ Qp,
                                 uint32_t* __restrict__ tau_g, int* __restrict__ flags,
-                                uint32_t* __restrict__ tau_u, int n_pub, __nv_bfloat16* __restrict__ Qb, int pitch_b,
+                                __nv_bfloat16* __restrict__ Qb, int pitch_b,
                                 const uint32_t* __restrict__ tau_fixed) {
   // Rows are written in TILE order: row qt*128 + j holds query qt*128 + (j % 32) * 4 + j / 32 (zeros past the last
   // query), so that consecutive queries land in different TMEM lane groups.
@@ -640,8 +595,6 @@ __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, i
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += gridDim.x * blockDim.x) {
     tau_g[i] = tau_fixed ? tau_fixed[i] : ORD_NEG_INF; flags[i] = 0;
   }
-  const int64_t n_u = int64_t(n_q) * n_pub;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_u; i += int64_t(gridDim.x) * blockDim.x) tau_u[i] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -972,12 +925,12 @@ inline bool tc_init(TcState* st, int sm_count, std::string* err) {
     return false;
   }
   st->encode = fn;
-  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (a != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(tc kernels) failed: ") + cudaGetErrorString(a); return false; }
   return true;
@@ -1019,9 +972,9 @@ inline bool tc_supported(const TcState* st, const TcCorpus* tc, int64_t n_rows, 
 
 struct TcPlan {
   int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks;
-  int n_pub, rank_r, rank_m, qt_major;
+  int qt_major;
   int kp_list;   // candidates each (query, list) keeps at a selection (<= kp)
-  size_t off_qp, off_qb, off_tau, off_flags, off_tau_u, off_wcnt, off_wbuf, total;
+  size_t off_qp, off_qb, off_tau, off_flags, off_wcnt, off_wbuf, total;
 };
 
 inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
@@ -1082,12 +1035,6 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.off_qb = take(s.kind == 1 ? q_rows_p * s.pitch_b * 2 : 0);
   pl.off_tau = take(size_t(s.n_q) * 4);
   pl.off_flags = take(size_t(s.n_q) * 4);
-  // cross-list threshold publication is off by default: on C3 it costs more than it saves (120 vs 94 ms)
-  pl.n_pub = 0;
-  if (const char* e = std::getenv("FENIX_TC_PUBLISH")) { if (std::atoi(e) != 0) pl.n_pub = std::min(TC_SPLIT * pl.n_slices, 512); }
-  pl.rank_r = pl.n_pub ? (pl.kp + pl.n_pub - 1) / pl.n_pub : 1;
-  pl.rank_m = (pl.kp + pl.rank_r - 1) / pl.rank_r;
-  pl.off_tau_u = take(size_t(s.n_q) * std::max(pl.n_pub, 1) * 4);
   pl.off_wcnt = take(size_t(pl.units) * TC_SLOTS * 4);
   pl.off_wbuf = take(size_t(pl.units) * TC_SLOTS * pl.cap * 8);
   pl.total = off;
@@ -1113,7 +1060,6 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   float* qp = reinterpret_cast<float*>(base + pl.off_qp);
   uint32_t* tau_g = reinterpret_cast<uint32_t*>(base + pl.off_tau);
   int* flags = reinterpret_cast<int*>(base + pl.off_flags);
-  uint32_t* tau_u = reinterpret_cast<uint32_t*>(base + pl.off_tau_u);
   int* wcnt = reinterpret_cast<int*>(base + pl.off_wcnt);
   uint2* wbuf = reinterpret_cast<uint2*>(base + pl.off_wbuf);
 
@@ -1127,24 +1073,32 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   }
 
   const int prep_blocks = int(std::min<int64_t>((int64_t(pl.n_qt) * TC_BM * s.pitch + 255) / 256, 4 * 148));
-  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags, tau_u, pl.n_pub, qb, s.pitch_b, s.tau_fixed);
+  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed);
 
   TcParams p{};
   p.n_q = s.n_q; p.n_qt = pl.n_qt; p.n_rows = s.n_rows; p.n_tiles = pl.n_tiles; p.n_slices = pl.n_slices;
   p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.kp = pl.kp_list; p.cap = pl.cap;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
-  p.tau_u = tau_u; p.n_pub = pl.n_pub; p.rank_r = pl.rank_r; p.rank_m = pl.rank_m; p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
+  p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
   if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);
   const int epi = (s.metric == 2 && s.epi_add) ? 0 : s.metric;   // epilogue form: 0 add, 1 multiply, 2 none
-  if (s.kind == 0) {
-    if (epi == 0) knn_tc_filter_kernel<0, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
-    else if (epi == 1) knn_tc_filter_kernel<1, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
-    else knn_tc_filter_kernel<2, 0><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_x, p);
-  } else {
-    if (epi == 0) knn_tc_filter_kernel<0, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
-    else if (epi == 1) knn_tc_filter_kernel<1, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
-    else knn_tc_filter_kernel<2, 1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, tc->map_xb, p);
+  // dispatch on (epilogue form, operand kind, diagnostics dump)
+  auto launch = [&](auto kernel, const CUtensorMap& map_b) {
+    kernel<<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, map_b, p);
+  };
+  const bool dbg = s.dbg != nullptr;
+#define FX_TC_CASE(E, K, MAP)                                                       \
+  if (epi == E && s.kind == K) {                                                    \
+    if (dbg) {                                                                      \
+      cudaFuncSetAttribute(knn_tc_filter_kernel<E, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
+      launch(knn_tc_filter_kernel<E, K, true>, MAP);                                \
+    } else {                                                                        \
+      launch(knn_tc_filter_kernel<E, K, false>, MAP);                               \
+    }                                                                               \
   }
+  FX_TC_CASE(0, 0, tc->map_x) FX_TC_CASE(1, 0, tc->map_x) FX_TC_CASE(2, 0, tc->map_x)
+  FX_TC_CASE(0, 1, tc->map_xb) FX_TC_CASE(1, 1, tc->map_xb) FX_TC_CASE(2, 1, tc->map_xb)
+#undef FX_TC_CASE
   if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
 
   FinishParams f{};
