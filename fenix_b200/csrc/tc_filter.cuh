@@ -600,6 +600,8 @@ __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, i
 // ---------------------------------------------------------------------------------------------
 // finish: select K' by approximate score, exact rerank, sort, certificate
 // ---------------------------------------------------------------------------------------------
+constexpr int FIN_POOL = 2048;   // candidates the finish kernel can hold in shared memory
+
 struct FinishParams {
   const float* X; int pitch; int dim; int64_t row_base;
   const float* Qp; int n_q; int n_qt; int n_slices; int cap; int metric; int k; int kp; int sort2;  // sort2: pow2 >= kp
@@ -613,12 +615,13 @@ struct FinishParams {
 //     approximate score among the entries above the final shared threshold;
 //  2. the <= K' winners are re-ranked exactly (fp64 accumulation, one warp per candidate);
 //  3. bitonic sort by (distance, row), write top-k, evaluate the certificate.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 knn_tc_finish_kernel(FinishParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys2 = reinterpret_cast<uint64_t*>(smem_raw);                 // [sort2] (distance,row) keys
   uint32_t* cand = reinterpret_cast<uint32_t*>(keys2 + p.sort2);           // [sort2] candidate rows
   float* qs = reinterpret_cast<float*>(cand + p.sort2);                    // [pitch]
+  uint2* pool = reinterpret_cast<uint2*>(qs + p.pitch);                    // [FIN_POOL] gathered candidates (pitch is a multiple of 4 floats)
   __shared__ int hist[256];
   __shared__ int s_n_gt, s_n_tie, s_total;
   __shared__ uint32_t s_prefix;
@@ -654,20 +657,66 @@ knn_tc_finish_kernel(FinishParams p) {
     return p.wbuf + unit_slot * p.cap;
   };
 
-  // ---- 1. radix select of the kp-th largest ordered score among entries > tg ----
+  // ---- 0. gather: one pass over the query's lists copies every entry at or above the final threshold into a
+  // shared-memory pool, so the selection passes below never touch global memory again (with hundreds of short
+  // lists per query - the small-batch regime - five dependent sweeps over them dominated the search latency).
+  // If the pool overflows (thresholds still loose) the selection falls back to sweeping the lists.
+  __shared__ int s_pool_n;
+  if (tid == 0) s_pool_n = 0;
+  __syncthreads();
+  for (int l = warp; l < n_lists; l += n_warps) {
+    int count; const uint2* b = list_ptr(l, count);
+    for (int i0 = 0; i0 < count; i0 += 128) {
+      // four independent loads per lane in flight, then four warp-aggregated appends
+      uint2 ent[4]; bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 32 + lane;
+        ent[j] = (i < count) ? b[i] : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 32 + lane;
+        ok[j] = (i < count) && f2ord(__uint_as_float(ent[j].x)) >= tg;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, ok[j]);
+        if (ballot == 0u) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_pool_n, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(ballot & ((1u << lane) - 1u));
+        if (ok[j] && pos < FIN_POOL) pool[pos] = ent[j];
+      }
+    }
+  }
+  __syncthreads();
+  const int pool_n = s_pool_n;
+  const bool pooled = pool_n <= FIN_POOL;
+  // visit every candidate entry (o = ordered score, row): from the pool, or from the lists when it overflowed
+  auto for_each = [&](auto&& fn) {
+    if (pooled) {
+      for (int i = tid; i < pool_n; i += blockDim.x) fn(f2ord(__uint_as_float(pool[i].x)), pool[i].y);
+    } else {
+      for (int l = warp; l < n_lists; l += n_warps) {
+        int count; const uint2* b = list_ptr(l, count);
+        for (int i = lane; i < count; i += 32) {
+          const uint2 ent = b[i];
+          const uint32_t o = f2ord(__uint_as_float(ent.x));
+          if (o >= tg) fn(o, ent.y);
+        }
+      }
+    }
+  };
+
+  // ---- 1. radix select of the kp-th largest ordered score among entries >= tg ----
   uint32_t prefix = 0, mask = 0;
   bool keep_all = false;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int l = warp; l < n_lists; l += n_warps) {
-      int count; const uint2* b = list_ptr(l, count);
-      for (int i = lane; i < count; i += 32) {
-        uint32_t o = f2ord(__uint_as_float(b[i].x));
-        if (o >= tg && (o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 0xffu], 1);
-      }
-    }
+    for_each([&](uint32_t o, uint32_t) {
+      if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 0xffu], 1);
+    });
     __syncthreads();
     if (tid == 0) {
       int remaining = s_remaining;
@@ -697,20 +746,15 @@ knn_tc_finish_kernel(FinishParams p) {
   const int ties_wanted = keep_all ? 0 : s_remaining;      // entries == pivot still admitted
 
   // ---- collect winners: score > pivot, plus `ties_wanted` entries equal to the pivot ----
-  for (int l = warp; l < n_lists; l += n_warps) {
-    int count; const uint2* b = list_ptr(l, count);
-    for (int i = lane; i < count; i += 32) {
-      uint2 ent = b[i];
-      uint32_t o = f2ord(__uint_as_float(ent.x));
-      if (o > pivot || (keep_all && o == pivot)) {
-        int pos = atomicAdd(&s_n_gt, 1);
-        if (pos < p.sort2) cand[pos] = ent.y;
-      } else if (!keep_all && o == pivot) {
-        int t = atomicAdd(&s_n_tie, 1);
-        if (t < ties_wanted) cand[p.kp - 1 - t] = ent.y;    // ties fill the tail of the kp slots
-      }
+  for_each([&](uint32_t o, uint32_t row) {
+    if (o > pivot || (keep_all && o == pivot)) {
+      int pos = atomicAdd(&s_n_gt, 1);
+      if (pos < p.sort2) cand[pos] = row;
+    } else if (!keep_all && o == pivot) {
+      int t = atomicAdd(&s_n_tie, 1);
+      if (t < ties_wanted) cand[p.kp - 1 - t] = row;    // ties fill the tail of the kp slots
     }
-  }
+  });
   __syncthreads();
   // winners occupy cand[0, n_gt) and (when a pivot exists) cand[kp - n_tie_kept, kp)
   const int n_gt = min(s_n_gt, p.sort2);
@@ -954,8 +998,10 @@ inline bool tc_bind_corpus(TcState* st, TcCorpus* tc, const float* X, int64_t n_
 }
 
 // K' (candidates kept by each selection) and the buffer capacity that goes with it
-inline int tc_kp(int k, bool certify) {
-  int kp = certify ? k + std::max(16, k / 2) : k;
+inline int tc_kp(int k, bool certify, int kind = 0) {
+  // slack so that the certificate holds for (nearly) every query in one pass: the bf16 bound is ~1.8x looser than
+  // the TF32 one (measured on C3: K' = 32 flags 25 of 4096 queries per batch with bf16, K' = 64 none)
+  int kp = certify ? k + std::max(kind == 1 ? 48 : 16, k / 2) : k;
   return (kp + 31) & ~31;
 }
 inline int tc_cap(int kp) { return kp <= 128 ? 512 : 1024; }
@@ -981,7 +1027,8 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   TcPlan pl{};
   pl.n_qt = (s.n_q + TC_BM - 1) / TC_BM;
   pl.n_tiles = int((s.n_rows + TC_BN - 1) / TC_BN);
-  pl.kp = s.tau_fixed ? 1024 : tc_kp(s.k, s.certify);   // refinement reranks every survivor (up to 1024)
+  pl.kp = s.tau_fixed ? 1024 : tc_kp(s.k, s.certify, s.kind);   // refinement reranks every survivor (up to 1024)
+  if (!s.tau_fixed && s.certify) { if (const char* e = std::getenv("FENIX_TC_KP")) { int f = std::atoi(e); if (f >= s.k && f <= 512) pl.kp = (f + 31) & ~31; } }
   pl.cap = tc_cap(pl.kp);
   pl.n_kblocks = s.kind == 0 ? (s.pitch + TC_BK - 1) / TC_BK : (s.pitch_b + 2 * TC_BK - 1) / (2 * TC_BK);
   // Slices: units = n_qt * n_slices (query-tile major, so all slices of a query tile run at the same time and
@@ -1107,8 +1154,10 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   int sort2 = 2; while (sort2 < pl.kp) sort2 <<= 1;
   f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.qt_major = pl.qt_major; f.flags = flags; f.certify = s.certify ? 1 : 0;
   f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim, s.kind); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
-  const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + 16;
-  knn_tc_finish_kernel<<<s.n_q, 256, fin_smem, s.stream>>>(f);
+  const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + size_t(FIN_POOL) * 8 + 16;
+  // many short lists per query (small batches split over all SMs): more warps sweep them in parallel
+  const int fin_threads = TC_SPLIT * pl.n_slices > 32 ? 1024 : 256;
+  knn_tc_finish_kernel<<<s.n_q, fin_threads, fin_smem, s.stream>>>(f);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tensor-core path launch failed: ") + cudaGetErrorString(e); return false; }
   *launched = 3;
