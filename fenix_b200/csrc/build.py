@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-OUT = os.path.join(PKG, "libfenix_knn.so")
+OUT = os.environ.get("FENIX_BUILD_OUT") or os.path.join(PKG, "libfenix_knn.so")   # FENIX_BUILD_OUT: tuning variants
 SOURCES = ["fenix_knn.cu"]
 DEPS = ["fenix_knn.cu", "common.cuh", "exact_scan.cuh", "tc_filter.cuh", os.path.join(ROOT, "include", "fenix_knn.h")]
 
@@ -26,6 +26,7 @@ NVCC_FLAGS = [
     "-shared",
     *(["-DFENIX_TC_SPLIT=" + os.environ["FENIX_TC_SPLIT"]] if os.environ.get("FENIX_TC_SPLIT") else []),
     "--expt-relaxed-constexpr",
+    *os.environ.get("FENIX_NVCC_EXTRA", "").split(),
 ]
 
 

@@ -106,8 +106,10 @@ struct fx_corpus {
   int64_t cap = 0, n = 0, row_base = 0;
   int dim = 0, pitch = 0;
   float* X = nullptr;
-  void* Xb = nullptr;              // optional bf16 shadow of X for the bf16 filter ([n][pitch_b])
-  int pitch_b = 0;
+  void* Xb = nullptr;              // bf16 shadow of X (+ three -|x|^2/2 columns) for the bf16 filter, tiled (tc_filter.cuh)
+  void* Xn = nullptr;              // bf16 shadow of the normalised rows (cosine), built by the first cosine search
+  bool xn_failed = false;          // no memory for Xn: cosine keeps the plain shadow + multiplicative epilogue
+  int pitch_b = 0;                 // elements per row of the bf16 QUERY matrix that goes with the shadows (ShadowGeom::pitch_q)
   float* hx = nullptr;
   float* rx = nullptr;
   unsigned int* max_n2_bits = nullptr;
@@ -318,22 +320,24 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
     bool want = e ? std::atoi(e) != 0 : c->dim >= 16;
     if (want && !e) {
       size_t free_b = 0, total_b = 0;
-      const size_t need = size_t((c->n + 255) / 256) * size_t((((c->dim + 7) & ~7) + 63) / 64) * 256 * 64 * 2;
+      const fx::ShadowGeom g0 = fx::shadow_geom(c->dim);
+      const size_t need = size_t((c->n + 255) / 256) * size_t(g0.n_kb_data + (g0.aug_separate ? 1 : 0)) * 256 * 64 * 2;
       if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < need + (size_t(4) << 30)) want = false;
       cudaGetLastError();
     }
     if (want && c->n >= 4096) {
-      c->pitch_b = (c->dim + 7) & ~7;
-      const int n_kb = (c->pitch_b + 63) / 64;
+      const fx::ShadowGeom g = fx::shadow_geom(c->dim);
+      c->pitch_b = g.pitch_q;
+      const int n_kb = g.n_kb_data, aug_blocks = g.aug_separate ? 1 : 0;
       const int64_t n_tiles = (c->n + fx::TC_BN - 1) / fx::TC_BN;
-      const size_t shadow_bytes = size_t(n_tiles) * n_kb * fx::TC_BN * 64 * 2;
+      const size_t shadow_bytes = size_t(n_tiles) * (n_kb + aug_blocks) * fx::TC_BN * 64 * 2;
       cudaError_t me = cudaMalloc(&c->Xb, shadow_bytes);
       if (me != cudaSuccess) { cudaGetLastError(); c->Xb = nullptr; }   // not fatal: the TF32 filter needs no shadow
       if (c->Xb) {
         const int64_t total = int64_t(shadow_bytes / 4);
         int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
-        fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim,
-                                                                  static_cast<__nv_bfloat16*>(c->Xb), n_kb, n_tiles);
+        fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim, c->hx, c->rx, 0,
+                                                                  static_cast<__nv_bfloat16*>(c->Xb), n_kb, n_tiles, g.aug_col, aug_blocks);
         FX_CUDA(cudaGetLastError());
         FX_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->launches++; c->stats.kernel_launches++;
@@ -343,7 +347,8 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
   }
   {
     std::string err;
-    if (!fx::tc_bind_corpus(&ctx->tc, &c->tc, c->X, c->n, c->dim, c->pitch, c->Xb, c->pitch_b, &err))
+    const fx::ShadowGeom g = fx::shadow_geom(c->dim);
+    if (!fx::tc_bind_corpus(&ctx->tc, &c->tc, c->X, c->n, c->dim, c->pitch, c->Xb, g.n_kb_data + (g.aug_separate ? 1 : 0), &err))
       return fail(FX_ECUDA, "fx_corpus_finalize: %s", err.c_str());
   }
   c->stats.n_rows = c->n;
@@ -363,6 +368,7 @@ extern "C" int fx_corpus_destroy(fx_corpus* c) {
   }
   if (c->X) cudaFree(c->X);
   if (c->Xb) cudaFree(c->Xb);
+  if (c->Xn) cudaFree(c->Xn);
   if (c->hx) cudaFree(c->hx);
   if (c->rx) cudaFree(c->rx);
   if (c->max_n2_bits) cudaFree(c->max_n2_bits);
@@ -441,6 +447,64 @@ static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_
 // ----------------------------------------------------------------------------------------
 // search
 // ----------------------------------------------------------------------------------------
+// The normalised bf16 shadow (cosine scores straight out of the MMA) is built by the first cosine search that
+// can use it; when HBM is short the search keeps the plain shadow and the multiplicative epilogue.
+static bool ensure_norm_shadow(fx_corpus* c) {
+  fx_ctx* ctx = c->ctx;
+  if (c->tc.ok_n) return true;
+  if (c->xn_failed || !c->tc.ok_b || std::getenv("FENIX_NO_NORM_SHADOW")) return false;
+  const int n_kb = fx::shadow_geom(c->dim).n_kb_data;
+  const int64_t n_tiles = (c->n + fx::TC_BN - 1) / fx::TC_BN;
+  const size_t shadow_bytes = size_t(n_tiles) * n_kb * fx::TC_BN * 64 * 2;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < shadow_bytes + (size_t(4) << 30) ||
+      cudaMalloc(&c->Xn, shadow_bytes) != cudaSuccess) {
+    cudaGetLastError(); c->Xn = nullptr; c->xn_failed = true;
+    return false;
+  }
+  const int64_t total = int64_t(shadow_bytes / 4);
+  int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
+  fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim, c->hx, c->rx, 1,
+                                                            static_cast<__nv_bfloat16*>(c->Xn), n_kb, n_tiles, 0, 0);
+  std::string err;
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+      !fx::tc_bind_shadow(&ctx->tc, &c->tc.map_xn, c->Xn, c->n, n_kb, &err)) {
+    cudaGetLastError(); cudaFree(c->Xn); c->Xn = nullptr; c->xn_failed = true;
+    return false;
+  }
+  ctx->launches++; c->stats.kernel_launches++;
+  c->stats.device_bytes += int64_t(shadow_bytes);
+  c->tc.ok_n = true;
+  return true;
+}
+
+// Operand kind, shadow and epilogue form of one filter launch (see TcSearch). With a row mask the per-row
+// epilogue term carries the mask: masked rows get -inf (additive forms) or NaN (multiplicative form), which can
+// never pass the threshold test.
+static int configure_filter(fx_corpus* c, int metric, int kind, const uint8_t* d_mask, fx::TcSearch* s) {
+  fx_ctx* ctx = c->ctx;
+  s->kind = kind; s->pitch_b = c->pitch_b; s->shadow = 0; s->aug = 0; s->epi = metric;
+  s->hx = c->hx; s->rx = c->rx;
+  if (kind == 1) {
+    if (metric == 0) { s->aug = 1; s->epi = 2; }                       // -|x|^2/2 rides in the shadow's extra columns
+    else if (metric == 1) { if (ensure_norm_shadow(c)) { s->shadow = 1; s->epi = 2; } }
+  }
+  if (d_mask) {
+    const int64_t n_alloc = ((c->n + 255) / 256) * 256;
+    FX_TRY(ctx->d_maskn.ensure(size_t(n_alloc) * sizeof(float)));
+    float* mn = static_cast<float*>(ctx->d_maskn.p);
+    // mode 0: hx or -inf (added), 1: rx or NaN (multiplied), 2: 0 or -inf (added)
+    const int mode = s->epi == 2 ? 2 : s->epi;
+    fx::masked_norms_kernel<<<int(std::min<int64_t>((n_alloc + 255) / 256, int64_t(ctx->sm_count) * 8)), 256, 0, ctx->stream>>>(
+        d_mask, mode == 1 ? c->rx : c->hx, c->n, n_alloc, mode, mn);
+    FX_CUDA(cudaGetLastError());
+    ctx->launches++; c->stats.kernel_launches++;
+    s->hx = mn; s->rx = mn;
+    if (s->epi == 2) s->epi = 0;
+  }
+  return FX_OK;
+}
+
 static int check_search_args(fx_corpus* c, const void* q, int64_t n_q, int metric, int k, int precision,
                              const void* out_rows, const void* out_dist) {
   if (!c) return fail(FX_EINVAL, "fx_search: corpus is NULL");
@@ -473,25 +537,13 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
     fx::TcSearch s{};
     s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
     s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = d_q; s.n_q = int(n_q); s.metric = metric; s.k = k;
-    if (d_mask) {
-      // predicate filter: masked rows get an epilogue term that can never pass (-inf / NaN)
-      const int64_t n_alloc = ((c->n + 255) / 256) * 256;
-      FX_TRY(ctx->d_maskn.ensure(size_t(n_alloc) * sizeof(float)));
-      float* mn = static_cast<float*>(ctx->d_maskn.p);
-      const int mode = metric == 0 ? 0 : (metric == 1 ? 1 : 2);
-      fx::masked_norms_kernel<<<int(std::min<int64_t>((n_alloc + 255) / 256, int64_t(ctx->sm_count) * 8)), 256, 0, ctx->stream>>>(
-          d_mask, metric == 1 ? c->rx : c->hx, c->n, n_alloc, mode, mn);
-      FX_CUDA(cudaGetLastError());
-      ctx->launches++; c->stats.kernel_launches++;
-      s.hx = mn; s.rx = mn; s.epi_add = 1;
-    }
     s.certify = precision == FX_PREC_FP32; s.out_rows = d_out_rows; s.out_dist = d_out_dist;
     s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.dbg = nullptr; s.tau_fixed = nullptr;
     // operand kind of the filter: exact mode takes the bf16 shadow when the shard has one
-    s.pitch_b = c->pitch_b;
-    s.kind = (precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && c->tc.ok_b && !std::getenv("FENIX_FP32_FILTER_TF32"))) ? 1 : 0;
-    path = 1 + s.kind;
-    if (s.kind == 1 && !c->tc.ok_b) return fail(FX_ESTATE, "fx_search: FX_PREC_BF16 needs the bf16 shadow (FENIX_BF16_SHADOW=1 at finalize)");
+    const int kind = (precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && c->tc.ok_b && !std::getenv("FENIX_FP32_FILTER_TF32"))) ? 1 : 0;
+    path = 1 + kind;
+    if (kind == 1 && !c->tc.ok_b) return fail(FX_ESTATE, "fx_search: FX_PREC_BF16 needs the bf16 shadow (FENIX_BF16_SHADOW=1 at finalize)");
+    FX_TRY(configure_filter(c, metric, kind, d_mask, &s));
     std::string err;
     size_t need = fx::tc_scratch_bytes(&ctx->tc, s);
     FX_TRY(ctx->d_tc.ensure(need));
@@ -524,7 +576,8 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
         int64_t* rows2 = reinterpret_cast<int64_t*>(rb + o_rows);
         float* dist2 = reinterpret_cast<float*>(rb + o_dist);
         fx::refine_prep_kernel<<<n_f, 128, 0, ctx->stream>>>(d_q, static_cast<const int*>(ctx->d_qlist.p), c->dim, metric, k,
-                                                            d_out_dist, c->max_norm, fx::tc_c_err(c->dim, s.kind), q_r, tau_fixed);
+                                                            d_out_dist, c->max_norm, fx::tc_c_err(c->dim, s.kind),
+                                                            fx::tc_c_add(c->dim, s.kind == 1 && s.aug), q_r, tau_fixed);
         FX_CUDA(cudaGetLastError());
         fx::TcSearch s2 = s;
         s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.tau_fixed = tau_fixed; s2.certify = true;
@@ -693,8 +746,8 @@ extern "C" int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, 
   s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = static_cast<const float*>(ctx->d_q.p); s.n_q = int(n_q);
   s.metric = metric; s.k = 10; s.certify = false; s.out_rows = static_cast<int64_t*>(ctx->d_rows.p);
   s.out_dist = static_cast<float*>(ctx->d_dist.p); s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1;
-  s.dbg = d_dbg; s.kind = 0; s.pitch_b = c->pitch_b; s.tau_fixed = nullptr;
-  if (std::getenv("FENIX_DEBUG_BF16") && c->tc.ok_b) s.kind = 1;
+  s.dbg = d_dbg; s.tau_fixed = nullptr;
+  FX_TRY(configure_filter(c, metric, (std::getenv("FENIX_DEBUG_BF16") && c->tc.ok_b) ? 1 : 0, nullptr, &s));
   FX_TRY(ctx->d_tc.ensure(fx::tc_scratch_bytes(&ctx->tc, s)));
   std::string err; int launched = 0;
   if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err)) return fail(FX_ECUDA, "fx_debug_scores: %s", err.c_str());

@@ -43,6 +43,12 @@ constexpr int TC_ACC_STAGES = 2;           // 2 x 256 TMEM columns = all 512
 #define FENIX_TC_SPLIT 2                   // column split of an accumulator among epilogue warp groups (2 or 4)
 #endif
 constexpr int TC_SPLIT = FENIX_TC_SPLIT;
+#ifndef FENIX_TC_BACKOFF
+#define FENIX_TC_BACKOFF 1                 // 1: producer / MMA polling loops sleep between polls
+#endif
+#ifndef FENIX_TC_PIPE
+#define FENIX_TC_PIPE 0                    // 1: software-pipelined TMEM loads in the epilogue
+#endif
 constexpr int TC_EPI_WARPS = 4 * TC_SPLIT; // 4 warps cover the 128 TMEM lanes; TC_SPLIT groups split the columns
 constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
 constexpr int TC_EPI_FIRST_WARP = 4;
@@ -58,6 +64,26 @@ constexpr uint32_t TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_B
 constexpr int TC_MAX_WAVES = 4;            // units per CTA at most (bounds the candidate-buffer scratch)
 constexpr uint32_t ORD_NEG_INF = 0x007fffffu;  // f2ord(-inf)
 
+// Geometry of a bf16 shadow of a [n][dim] shard (see to_bf16_tiled_kernel). The three -|x|^2/2 columns sit right
+// after the data when the last 64-column k-block has room for them; otherwise (dim % 64 == 0 or > 61) they get
+// one block per tile in a separate region behind the data blocks, so that searches that do not need them (inner
+// product, cosine) stream exactly the data blocks, back to back.
+struct ShadowGeom {
+  int n_kb_data;     // 64-column k-blocks that hold data, per tile
+  int aug_col;       // query / shadow column of the first augmented term (dim, or 64 * n_kb_data when separate)
+  bool aug_separate;
+  int pitch_q;       // elements per row of the bf16 query matrix (multiple of 64, covers the augmented columns)
+};
+inline ShadowGeom shadow_geom(int dim) {
+  ShadowGeom g;
+  g.n_kb_data = (dim + 63) / 64;
+  const int used = dim - 64 * (g.n_kb_data - 1);      // columns of the last data block that hold data
+  g.aug_separate = used + 3 > 64;
+  g.aug_col = g.aug_separate ? 64 * g.n_kb_data : dim;
+  g.pitch_q = 64 * ((g.aug_col + 3 + 63) / 64);   // whole 128-byte k-blocks: query tile rows stay 128 B aligned for TMA
+  return g;
+}
+
 struct TcState {
   int sm_count = 0;
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -65,8 +91,10 @@ struct TcState {
 struct TcCorpus {
   CUtensorMap map_x;       // [n_rows][pitch] fp32, box 32 x 256, 128B swizzle
   CUtensorMap map_xb;      // bf16 shadow, tiled [tile][k-block][256 rows][64], box 64 x 256 = one contiguous 32 KB block
+  CUtensorMap map_xn;      // bf16 shadow of the NORMALISED rows x/|x| (cosine), same layout, built on first use
   bool ok = false;
   bool ok_b = false;
+  bool ok_n = false;
 };
 struct TcSearch {
   const float* X; const float* hx; const float* rx; int64_t n_rows; int dim; int pitch; int64_t row_base;
@@ -76,7 +104,9 @@ struct TcSearch {
   int kind;                // 0: TF32 filter over the fp32 rows, 1: bf16 filter over the bf16 shadow
   int pitch_b;             // elements per row of the bf16 shadow (multiple of 8)
   const uint32_t* tau_fixed; // refinement pass: preset per-query admission thresholds (ordered encoding) or null
-  int epi_add;               // 1: inner-product search with a row mask -> epilogue adds hx (0 / -inf) like L2
+  int epi;                   // epilogue form: 0 score = acc + hx[row], 1 score = acc * rx[row], 2 score = acc
+  int shadow;                // kind 1: 0 = plain shadow (+ augmented columns), 1 = normalised shadow
+  int aug;                   // kind 1, L2: the query gets three 1.0 columns that pick up the shadow's -|x|^2/2 columns
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -103,6 +133,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Polling wait for the single-thread producer / MMA roles: between polls the thread sleeps, so its spin loop
+// does not take issue slots from the epilogue warps that share its SM sub-partition (measured on C2: the two
+// spin loops were 23 % of all executed instructions).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+#if FENIX_TC_BACKOFF
+    __nanosleep(ns);
+#endif
+  }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -202,6 +250,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, with the loaded registers as in/out operands: the compiler cannot move a use of v[] above it.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
@@ -209,39 +264,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   return v;
 }
 
-// Branch-free candidate append: if (s > tau) { buf[cnt] = (s, col_base + J); ++cnt; } as predicated SASS.
-template <int J>
-__device__ __forceinline__ void append_if_above(uint32_t s_bits, float tau, uint2* buf, int& cnt, uint32_t col_base) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .u64 a;\n\t"
-      ".reg .u32 c;\n\t"
-      "setp.gt.f32 p, %1, %2;\n\t"
-      "@p mad.wide.s32 a, %0, 8, %3;\n\t"
-      "@p add.u32 c, %5, %6;\n\t"
-      "@p st.global.v2.u32 [a], {%4, c};\n\t"
-      "@p add.s32 %0, %0, 1;\n\t"
-      "}"
-      : "+r"(cnt)
-      : "f"(__uint_as_float(s_bits)), "f"(tau), "l"(buf), "r"(s_bits), "r"(col_base), "n"(J)
-      : "memory");
-}
 template <int G>
-__device__ __forceinline__ void append_group8(const uint32_t (&v)[TC_CW], float tau, uint2* buf, int& cnt, uint32_t col_base) {
-  append_if_above<8 * G + 0>(v[8 * G + 0], tau, buf, cnt, col_base);
-  append_if_above<8 * G + 1>(v[8 * G + 1], tau, buf, cnt, col_base);
-  append_if_above<8 * G + 2>(v[8 * G + 2], tau, buf, cnt, col_base);
-  append_if_above<8 * G + 3>(v[8 * G + 3], tau, buf, cnt, col_base);
-  append_if_above<8 * G + 4>(v[8 * G + 4], tau, buf, cnt, col_base);
-  append_if_above<8 * G + 5>(v[8 * G + 5], tau, buf, cnt, col_base);
-  append_if_above<8 * G + 6>(v[8 * G + 6], tau, buf, cnt, col_base);
-  append_if_above<8 * G + 7>(v[8 * G + 7], tau, buf, cnt, col_base);
+__device__ __forceinline__ void append_quad(const uint32_t (&v)[TC_CW], float tau, uint2*& wp, uint32_t col_base) {
+#pragma unroll
+  for (int j = 4 * G; j < 4 * G + 4; ++j) {
+    if (__uint_as_float(v[j]) > tau) { *wp = make_uint2(v[j], col_base + uint32_t(j)); ++wp; }
+  }
 }
-__device__ __forceinline__ float max8(const uint32_t (&v)[TC_CW], int g) {
-  float a = fmaxf(fmaxf(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), fmaxf(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])));
-  float b = fmaxf(fmaxf(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-  return fmaxf(a, b);
+__device__ __forceinline__ float max4(const uint32_t (&v)[TC_CW], int g) {
+  return fmaxf(fmaxf(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1])),
+               fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,7 +286,10 @@ struct TcParams {
   int n_tiles;            // corpus tiles of 256 rows
   int n_slices;           // corpus slices (units = n_slices * n_qt)
   int tiles_per_slice;
-  int n_kblocks;          // ceil(pitch / 32)
+  int n_kblocks;          // k-blocks (128 B of K per row) loaded per tile: n_kb_data (+ 1 when a separate augmented block is used)
+  int n_kb_data;          // data k-blocks per tile (the tile stride of the tiled shadow)
+  int nk_last;            // MMA instructions (32 B of K each) of the last data block: only columns that hold data are multiplied
+  int aug_line0;          // first 128-byte line of the separate augmented region of the shadow (one block per tile)
   int kp;                 // K': candidates kept per (query, unit-half) selection
   int cap;                // candidate buffer capacity per epilogue thread (512 or 1024)
   const float* hx;        // [n_rows padded to 256] -0.5|x|^2
@@ -391,19 +426,20 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int t = t0; t < t1; ++t) {
           if (METRIC != 2) {
             // per-column norm terms of this tile ride along, one buffer per accumulator stage
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 64);
             mbar_expect_tx(&norm_full[acc], TC_NORM_BYTES);
             const float* src = (METRIC == 0 ? p.hx : p.rx) + size_t(t) * TC_BN;
             bulk_load_1d(norm_smem + acc * TC_BN, src, TC_NORM_BYTES, &norm_full[acc]);
           }
           for (int kb = 0; kb < p.n_kblocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
             mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
             unsigned char* a_dst = tiles + stage * TC_STAGE_BYTES;
             constexpr int kElemsPerBlock = KIND == 0 ? TC_BK : 2 * TC_BK;
             tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * kElemsPerBlock, qt * TC_BM);
             if (KIND == 0) tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * kElemsPerBlock, t * TC_BN);
-            else tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0, (t * p.n_kblocks + kb) * TC_BN);  // tiled shadow: one contiguous 32 KB block
+            else tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0,                 // tiled shadow: one contiguous 32 KB block
+                             kb < p.n_kb_data ? (t * p.n_kb_data + kb) * TC_BN : p.aug_line0 + t * TC_BN);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -420,7 +456,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
         const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 32);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc * TC_BN);
           for (int kb = 0; kb < p.n_kblocks; ++kb) {
@@ -429,8 +465,10 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const uint32_t a_addr = smem_u32(tiles + stage * TC_STAGE_BYTES);
             const uint64_t a_desc = make_smem_desc(a_addr);
             const uint64_t b_desc = make_smem_desc(a_addr + TC_A_BYTES);
+            const int nk = kb < p.n_kb_data - 1 ? TC_BK / TC_UMMA_K : (kb == p.n_kb_data - 1 ? p.nk_last : 1);
 #pragma unroll
             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              if (k >= nk) break;   // the last k-block may hold fewer than 4 x 32 B of data
               // advance 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
               if (KIND == 0) umma_tf32(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
               else umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -461,7 +499,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const int q = qt * TC_BM + int(lane) * 4 + lane_grp;
       const bool active = q < p.n_q;
       uint2* buf = p.wbuf + (size_t(u) * TC_SLOTS + slot) * p.cap;
-      int cnt = 0;
+      uint2* wp = buf;   // append cursor: the buffer holds wp - buf entries
       float tau = active ? -INFINITY : INFINITY;   // lanes past the last query never admit anything
       if (p.fixed && active) tau = ord2f(p.tau_g[q]);
       // the shared threshold is re-read once per tile; the load is issued a tile ahead so its L2 latency
@@ -507,15 +545,36 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
               for (int j = 0; j < TC_CW; ++j) if (c + j >= ncols) v[j] = 0xff800000u;   // -inf
             }
-            const float m0 = max8(v, 0), m1 = max8(v, 1);
-            if (__any_sync(0xffffffffu, fmaxf(m0, m1) > tau)) {
-              // per group of 8 columns, a warp-uniform test, then predicated appends
+            // Four quad maxima -> chunk maximum. Appends are inherently frequent at large k / small N (a
+            // query admits ~K' ln(N/K') rows over the scan, and 32 queries share a warp), so the hit path
+            // must be cheap: only lanes that hold a hit enter it (divergent branch, no warp vote), and
+            // they touch only the quads whose maximum passes.
+            const float q0 = max4(v, 0), q1 = max4(v, 1), q2 = max4(v, 2), q3 = max4(v, 3);
+            if (fmaxf(fmaxf(q0, q1), fmaxf(q2, q3)) > tau) {
               const uint32_t col_base = uint32_t(col0 + c);
-              if (__any_sync(0xffffffffu, m0 > tau)) append_group8<0>(v, tau, buf, cnt, col_base);
-              if (__any_sync(0xffffffffu, m1 > tau)) append_group8<1>(v, tau, buf, cnt, col_base);
+              if (q0 > tau) append_quad<0>(v, tau, wp, col_base);
+              if (q1 > tau) append_quad<1>(v, tau, wp, col_base);
+              if (q2 > tau) append_quad<2>(v, tau, wp, col_base);
+              if (q3 > tau) append_quad<3>(v, tau, wp, col_base);
             }
           };
           const uint32_t t_acc = t_lane + uint32_t(acc * TC_BN);
+#if FENIX_TC_PIPE
+          // two register sets: the TMEM load of chunk c+1 is in flight while chunk c is processed
+          uint32_t va[TC_CW], vb[TC_CW];
+          tmem_ld_32x32b_x16(t_acc, va);
+#pragma unroll 1
+          for (int c = 0; c < TC_HALF_COLS; c += 2 * TC_CW) {
+            if (c >= ncols) break;
+            tmem_ld_wait_dep(va);
+            if (c + TC_CW < ncols) tmem_ld_32x32b_x16(t_acc + uint32_t(c + TC_CW), vb);
+            process(va, c);
+            if (c + TC_CW >= ncols) break;
+            tmem_ld_wait_dep(vb);
+            if (c + 2 * TC_CW < ncols && c + 2 * TC_CW < TC_HALF_COLS) tmem_ld_32x32b_x16(t_acc + uint32_t(c + 2 * TC_CW), va);
+            process(vb, c + TC_CW);
+          }
+#else
 #pragma unroll 1
           for (int c = 0; c < TC_HALF_COLS; c += TC_CW) {
             if (c >= ncols) break;
@@ -524,6 +583,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             tmem_ld_wait();
             process(va, c);
           }
+#endif
         }
         // release the accumulator stage (and its norm buffer) back to the MMA / TMA warps
         tc_fence_before();
@@ -534,6 +594,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         __syncwarp();
         // tighten thresholds: a lane whose buffer could overflow next tile, or that holds >= K'
         // candidates but no threshold yet, gets a warp-cooperative selection
+        int cnt = int(wp - buf);
         if (p.fixed && active && cnt > p.cap - TC_HALF_COLS) { p.flags[q] = 1; tau = INFINITY; }   // more survivors than the buffer holds
         bool need = active && !p.fixed && ((cnt > p.cap - TC_HALF_COLS) || (tau == -INFINITY && cnt >= p.kp));
         uint32_t need_mask = __ballot_sync(0xffffffffu, need);
@@ -546,7 +607,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           uint32_t v_ord = (p.cap == 1024) ? warp_select_compact<32>(b, c_src, p.kp, new_cnt)
                                            : warp_select_compact<16>(b, c_src, p.kp, new_cnt);
           if (int(lane) == src) {
-            cnt = new_cnt;
+            wp = buf + new_cnt;
             tau = fmaxf(tau, ord2f(v_ord));
             atomicMax(p.tau_g + q, v_ord);
           }
@@ -554,7 +615,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
 
       // end of unit: the finish kernel reads the buffer in place
-      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? cnt : 0;
+      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wp - buf) : 0;
     }
   }
 
@@ -572,7 +633,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, int pitch, float* __restrict__ Qp,
                                 uint32_t* __restrict__ tau_g, int* __restrict__ flags,
                                 __nv_bfloat16* __restrict__ Qb, int pitch_b,
-                                const uint32_t* __restrict__ tau_fixed) {
+                                const uint32_t* __restrict__ tau_fixed, int keep_tau, int aug_col) {
   // Rows are written in TILE order: row qt*128 + j holds query qt*128 + (j % 32) * 4 + j / 32 (zeros past the last
   // query), so that consecutive queries land in different TMEM lane groups.
   const int n_rows_p = ((n_q + TC_BM - 1) / TC_BM) * TC_BM;
@@ -589,11 +650,14 @@ __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, i
       int row = int(i / pitch_b), d = int(i - int64_t(row) * pitch_b);
       int j = row % TC_BM;
       int q = row - j + (j % 32) * 4 + j / 32;
-      Qb[i] = __float2bfloat16_rn((d < dim && q < n_q) ? Q[size_t(q) * dim + d] : 0.f);
+      float v = (d < dim && q < n_q) ? Q[size_t(q) * dim + d] : 0.f;
+      if (aug_col > 0 && q < n_q && d >= aug_col && d < aug_col + 3) v = 1.f;   // picks up the shadow's three -|x|^2/2 columns
+      Qb[i] = __float2bfloat16_rn(v);
     }
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += gridDim.x * blockDim.x) {
-    tau_g[i] = tau_fixed ? tau_fixed[i] : ORD_NEG_INF; flags[i] = 0;
+    if (!keep_tau) tau_g[i] = tau_fixed ? tau_fixed[i] : ORD_NEG_INF;
+    flags[i] = 0;
   }
 }
 
@@ -606,7 +670,7 @@ struct FinishParams {
   const float* X; int pitch; int dim; int64_t row_base;
   const float* Qp; int n_q; int n_qt; int n_slices; int cap; int metric; int k; int kp; int sort2;  // sort2: pow2 >= kp
   const uint32_t* tau_g; const uint2* wbuf; const int* wcnt; int qt_major;
-  int* flags; int certify; float max_norm; double c_err;
+  int* flags; int certify; float max_norm; double c_err; double c_add;
   int64_t* out_rows; float* out_dist;
 };
 
@@ -817,7 +881,7 @@ knn_tc_finish_kernel(FinishParams p) {
       const double xm = double(p.max_norm);
       double e_abs, lb;
       if (p.metric == 0) {
-        e_abs = p.c_err * nq * xm + 4.8e-7 * (0.5 * xm * xm + nq * xm);
+        e_abs = p.c_err * nq * xm + p.c_add * (0.5 * xm * xm + nq * xm);
         double d2 = qq - 2.0 * (double(t_score) + e_abs);
         lb = sqrt(d2 > 0.0 ? d2 : 0.0);
       } else if (p.metric == 1) {
@@ -844,7 +908,7 @@ knn_tc_finish_kernel(FinishParams p) {
 // every row that can still beat d_k has exact score > s(d_k), hence filter score > s(d_k) - E.
 __global__ void __launch_bounds__(128)
 refine_prep_kernel(const float* __restrict__ Q, const int* __restrict__ qlist, int dim, int metric, int k,
-                   const float* __restrict__ dist, float max_norm, double c_err,
+                   const float* __restrict__ dist, float max_norm, double c_err, double c_add,
                    float* __restrict__ Qr, uint32_t* __restrict__ tau_fixed) {
   __shared__ double part[4];
   const int i = blockIdx.x, q = qlist[i];
@@ -865,7 +929,7 @@ refine_prep_kernel(const float* __restrict__ Q, const int* __restrict__ qlist, i
     dk = dk + 1e-6 * fabs(dk) + 1e-37;            // a row at distance <= dk (after fp32 rounding) must survive
     double score, e_abs;
     if (metric == 0) {
-      e_abs = c_err * nq * xm + 4.8e-7 * (0.5 * xm * xm + nq * xm);
+      e_abs = c_err * nq * xm + c_add * (0.5 * xm * xm + nq * xm);
       score = 0.5 * (qq - dk * dk);
     } else if (metric == 1) {
       e_abs = nq * (c_err + 1e-6);
@@ -915,23 +979,42 @@ __global__ void masked_norms_kernel(const uint8_t* __restrict__ mask, const floa
 // 256 rows and every k-block of 64 elements, the 256 x 64 sub-block is stored contiguously (32 KB), i.e.
 //   element (r, d) lives at ((tile * KB + kb) * 256 + r % 256) * 64 + d % 64,  tile = r / 256, kb = d / 64.
 // One TMA box of the filter kernel is then a single contiguous 32 KB read. Pad rows / columns are zero.
+//   mode 0 (plain + augmented): columns [0, dim) = x, columns dim..dim+2 = -|x|^2/2 split into three bf16 terms
+//          (hi + mid + lo reproduce the fp32 value exactly), so that an L2 query [q, 1, 1, 1] gets
+//          q.x - |x|^2/2 straight out of the MMA and the epilogue needs no per-row term; an inner-product query
+//          (zeros there) ignores them.
+//   mode 1 (normalised): columns [0, dim) = x / max(|x|, eps): cosine scores straight out of the MMA.
 __global__ void to_bf16_tiled_kernel(const float* __restrict__ X, int64_t n_rows, int pitch, int dim,
-                                     __nv_bfloat16* __restrict__ Xb, int n_kb, int64_t n_tiles) {
-  const int64_t total = n_tiles * n_kb * int64_t(TC_BN) * 32;   // bf16 pairs
+                                     const float* __restrict__ hx, const float* __restrict__ rx, int mode,
+                                     __nv_bfloat16* __restrict__ Xb, int n_kb, int64_t n_tiles, int aug_col, int aug_blocks) {
+  const int64_t total = n_tiles * (n_kb + aug_blocks) * int64_t(TC_BN) * 32;   // bf16 pairs
+  const int64_t main_pairs = n_tiles * n_kb * int64_t(TC_BN) * 32;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int dd = int(i & 31) * 2;
-    const int64_t line = i >> 5;                      // (tile * KB + kb) * 256 + rr
+    int64_t line = i >> 5;                            // (tile * KB + kb) * 256 + rr, or past the data: tile * 256 + rr
+    const bool in_aug = i >= main_pairs;
+    if (in_aug) line -= main_pairs >> 5;
     const int rr = int(line % TC_BN);
     const int64_t blk = line / TC_BN;
-    const int kb = int(blk % n_kb);
-    const int64_t r = (blk / n_kb) * TC_BN + rr;
+    const int kb = in_aug ? n_kb : int(blk % n_kb);
+    const int64_t r = (in_aug ? blk : blk / n_kb) * TC_BN + rr;
     const int d = kb * 64 + dd;
-    float a = 0.f, b = 0.f;
+    float ab[2] = {0.f, 0.f};
     if (r < n_rows) {
-      if (d < dim) a = X[size_t(r) * pitch + d];
-      if (d + 1 < dim) b = X[size_t(r) * pitch + d + 1];
+      const float scale = mode == 1 ? rx[r] : 1.f;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int de = d + e;
+        if (de < dim) ab[e] = X[size_t(r) * pitch + de] * scale;
+        else if (mode == 0 && de >= aug_col && de < aug_col + 3) {
+          const float h = hx[r];
+          const float hi = __bfloat162float(__float2bfloat16_rn(h));
+          const float mid = __bfloat162float(__float2bfloat16_rn(h - hi));
+          ab[e] = de == aug_col ? hi : (de == aug_col + 1 ? mid : (h - hi) - mid);
+        }
+      }
     }
-    reinterpret_cast<__nv_bfloat162*>(Xb)[i] = __floats2bfloat162_rn(a, b);
+    reinterpret_cast<__nv_bfloat162*>(Xb)[i] = __floats2bfloat162_rn(ab[0], ab[1]);
   }
 }
 
@@ -980,18 +1063,22 @@ inline bool tc_init(TcState* st, int sm_count, std::string* err) {
   return true;
 }
 
+// tiled shadow: a flat list of 128-byte lines, 256 lines per (tile, k-block)
+inline bool tc_bind_shadow(const TcState* st, CUtensorMap* map, const void* Xb, int64_t n_rows, int blocks_per_tile, std::string* err) {
+  const uint64_t lines = uint64_t((n_rows + TC_BN - 1) / TC_BN) * uint64_t(blocks_per_tile) * TC_BN;
+  if (lines >= (uint64_t(1) << 31)) { *err = "shard too large for the tiled bf16 shadow (32-bit TMA coordinates)"; return false; }
+  return tc_encode_2d(st, map, Xb, uint64_t(2 * TC_BK), lines, uint64_t(2 * TC_BK), 2 * TC_BK, TC_BN, err, true);
+}
+
 inline bool tc_bind_corpus(TcState* st, TcCorpus* tc, const float* X, int64_t n_rows, int dim, int pitch,
-                           const void* Xb, int pitch_b, std::string* err) {
+                           const void* Xb, int blocks_per_tile, std::string* err) {
   (void)dim;
   tc->ok = false; tc->ok_b = false;
   if (n_rows < 1) return true;
   if (!tc_encode_2d(st, &tc->map_x, X, uint64_t(pitch), uint64_t(n_rows), uint64_t(pitch), TC_BK, TC_BN, err)) return false;
   tc->ok = true;
   if (Xb != nullptr) {
-    // tiled shadow: a flat list of 128-byte lines, 256 lines per (tile, k-block)
-    const uint64_t n_kb = uint64_t((pitch_b + 2 * TC_BK - 1) / (2 * TC_BK));
-    const uint64_t lines = uint64_t((n_rows + TC_BN - 1) / TC_BN) * n_kb * TC_BN;
-    if (!tc_encode_2d(st, &tc->map_xb, Xb, uint64_t(2 * TC_BK), lines, uint64_t(2 * TC_BK), 2 * TC_BK, TC_BN, err, true)) return false;
+    if (!tc_bind_shadow(st, &tc->map_xb, Xb, n_rows, blocks_per_tile, err)) return false;
     tc->ok_b = true;
   }
   return true;
@@ -1017,7 +1104,7 @@ inline bool tc_supported(const TcState* st, const TcCorpus* tc, int64_t n_rows, 
 }
 
 struct TcPlan {
-  int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks;
+  int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks, n_kb_data, nk_last, aug_line0, aug_col;
   int qt_major;
   int kp_list;   // candidates each (query, list) keeps at a selection (<= kp)
   size_t off_qp, off_qb, off_tau, off_flags, off_wcnt, off_wbuf, total;
@@ -1030,7 +1117,22 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.kp = s.tau_fixed ? 1024 : tc_kp(s.k, s.certify, s.kind);   // refinement reranks every survivor (up to 1024)
   if (!s.tau_fixed && s.certify) { if (const char* e = std::getenv("FENIX_TC_KP")) { int f = std::atoi(e); if (f >= s.k && f <= 512) pl.kp = (f + 31) & ~31; } }
   pl.cap = tc_cap(pl.kp);
-  pl.n_kblocks = s.kind == 0 ? (s.pitch + TC_BK - 1) / TC_BK : (s.pitch_b + 2 * TC_BK - 1) / (2 * TC_BK);
+  // MMA instructions per tile: 32 B of K each (8 fp32 / 16 bf16 elements); only columns that hold data
+  pl.aug_line0 = 0; pl.aug_col = 0;
+  if (s.kind == 0) {
+    pl.n_kb_data = (s.pitch + TC_BK - 1) / TC_BK;
+    pl.nk_last = (s.pitch - TC_BK * (pl.n_kb_data - 1) + TC_UMMA_K - 1) / TC_UMMA_K;
+    pl.n_kblocks = pl.n_kb_data;
+  } else {
+    const ShadowGeom g = shadow_geom(s.dim);
+    pl.n_kb_data = g.n_kb_data;
+    const int used = s.dim - 64 * (g.n_kb_data - 1) + ((s.aug && !g.aug_separate) ? 3 : 0);
+    pl.nk_last = (used + 15) / 16;
+    pl.n_kblocks = g.n_kb_data + ((s.aug && g.aug_separate) ? 1 : 0);
+    pl.aug_line0 = pl.n_tiles * g.n_kb_data * TC_BN;
+    pl.aug_col = g.aug_col;
+  }
+  if (std::getenv("FENIX_TC_FULLK")) pl.nk_last = TC_BK / TC_UMMA_K;   // tuning knob: multiply the zero padding too
   // Slices: units = n_qt * n_slices (query-tile major, so all slices of a query tile run at the same time and
   // share thresholds) are dealt round-robin to min(units, #SM) persistent CTAs.
   // Maximise SM utilisation units / (G * ceil(units / G)); few slices are preferred (longer units give
@@ -1096,6 +1198,9 @@ inline const int* tc_flags(const TcState* st, const TcSearch& s, void* scratch) 
 // (operands truncated to 10 mantissa bits: 2^-10 each -> 2^-9 on the product, 25% margin;
 //  fp32 accumulation of D terms: D * 2^-21)
 // bf16 operands are rounded to nearest (2^-9 each -> 2^-8 on the product, 10% margin).
+// L2 only: rounding of the -|x|^2/2 term and of its addition, relative to |x|^2/2 + |q||x|. When the term rides
+// through the MMA (augmented shadow) every one of the tile's accumulation steps may round it again.
+inline double tc_c_add(int dim, bool aug) { return 4.8e-7 + (aug ? double((dim + 3 + 15) / 16) * 1.2e-7 : 0.0); }
 inline double tc_c_err(int dim, int kind = 0) {
   const double prod = kind == 0 ? 1.25 * std::ldexp(1.0, -9) : 1.10 * std::ldexp(1.0, -8);
   return prod + double(dim) * std::ldexp(1.0, -21);
@@ -1115,20 +1220,24 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   if (s.kind == 0) {
     if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(pl.n_qt) * TC_BM, uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
   } else {
-    if (!tc->ok_b) { *err = "bf16 filter requested but the shard has no bf16 shadow"; return false; }
+    if (s.shadow == 1 ? !tc->ok_n : !tc->ok_b) { *err = "bf16 filter requested but the shard has no bf16 shadow"; return false; }
     if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(pl.n_qt) * TC_BM, uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
   }
 
   const int prep_blocks = int(std::min<int64_t>((int64_t(pl.n_qt) * TC_BM * s.pitch + 255) / 256, 4 * 148));
-  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed);
+  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed,
+                                                                  (!s.tau_fixed && std::getenv("FENIX_TC_WARM")) ? 1 : 0,
+                                                                  (s.kind == 1 && s.aug) ? pl.aug_col : 0);
 
   TcParams p{};
   p.n_q = s.n_q; p.n_qt = pl.n_qt; p.n_rows = s.n_rows; p.n_tiles = pl.n_tiles; p.n_slices = pl.n_slices;
-  p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.kp = pl.kp_list; p.cap = pl.cap;
+  p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.n_kb_data = pl.n_kb_data; p.nk_last = pl.nk_last;
+  p.aug_line0 = pl.aug_line0;
+  p.kp = pl.kp_list; p.cap = pl.cap;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
   p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
   if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);
-  const int epi = (s.metric == 2 && s.epi_add) ? 0 : s.metric;   // epilogue form: 0 add, 1 multiply, 2 none
+  const int epi = s.epi;   // epilogue form: 0 add, 1 multiply, 2 none
   // dispatch on (epilogue form, operand kind, diagnostics dump)
   auto launch = [&](auto kernel, const CUtensorMap& map_b) {
     kernel<<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, map_b, p);
@@ -1144,7 +1253,8 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
     }                                                                               \
   }
   FX_TC_CASE(0, 0, tc->map_x) FX_TC_CASE(1, 0, tc->map_x) FX_TC_CASE(2, 0, tc->map_x)
-  FX_TC_CASE(0, 1, tc->map_xb) FX_TC_CASE(1, 1, tc->map_xb) FX_TC_CASE(2, 1, tc->map_xb)
+  const CUtensorMap& map_s = s.shadow == 1 ? tc->map_xn : tc->map_xb;
+  FX_TC_CASE(0, 1, map_s) FX_TC_CASE(1, 1, map_s) FX_TC_CASE(2, 1, map_s)
 #undef FX_TC_CASE
   if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
 
@@ -1153,7 +1263,7 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   f.n_slices = pl.n_slices; f.cap = pl.cap; f.metric = s.metric; f.k = s.k; f.kp = pl.kp;
   int sort2 = 2; while (sort2 < pl.kp) sort2 <<= 1;
   f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.qt_major = pl.qt_major; f.flags = flags; f.certify = s.certify ? 1 : 0;
-  f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim, s.kind); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
+  f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim, s.kind); f.c_add = tc_c_add(s.dim, s.kind == 1 && s.aug); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
   const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + size_t(FIN_POOL) * 8 + 16;
   // many short lists per query (small batches split over all SMs): more warps sweep them in parallel
   const int fin_threads = TC_SPLIT * pl.n_slices > 32 ? 1024 : 256;
