@@ -54,7 +54,7 @@ constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
 constexpr int TC_EPI_FIRST_WARP = 4;
 constexpr int TC_HALF_COLS = TC_BN / TC_SPLIT;   // columns per epilogue warp group ("part")
 constexpr int TC_SLOTS = TC_SPLIT * TC_BM;       // candidate buffers per unit
-constexpr int TC_CW = 16;                  // accumulator columns per tcgen05.ld in the epilogue
+constexpr int TC_CW = 32;                  // accumulator columns per tcgen05.ld in the epilogue
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -251,10 +251,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Same wait, with the loaded registers as in/out operands: the compiler cannot move a use of v[] above it.
-__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                :: "memory");
 }
 
@@ -264,13 +266,6 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   return v;
 }
 
-template <int G>
-__device__ __forceinline__ void append_quad(const uint32_t (&v)[TC_CW], float tau, uint2*& wp, uint32_t col_base) {
-#pragma unroll
-  for (int j = 4 * G; j < 4 * G + 4; ++j) {
-    if (__uint_as_float(v[j]) > tau) { *wp = make_uint2(v[j], col_base + uint32_t(j)); ++wp; }
-  }
-}
 __device__ __forceinline__ float max4(const uint32_t (&v)[TC_CW], int g) {
   return fmaxf(fmaxf(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1])),
                fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
@@ -519,20 +514,24 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int ncols = int(min(int64_t(TC_HALF_COLS), p.n_rows - int64_t(col0)));  // valid columns (<=0: none)
         const float* nrm = norm_smem + acc * TC_BN + half * TC_HALF_COLS;
         if (__any_sync(0xffffffffu, active) && ncols > 0) {
-          // One chunk = 16 accumulator columns of this thread's query. Scores are formed in place, the two
-          // 8-column group maxima (independent 3-level trees) give the fast-path test and are reused by the
-          // slow path. The TMEM load of the next chunk is issued before the current one is processed.
-          auto process = [&](uint32_t (&v)[TC_CW], int c) {
+          // One chunk = 32 accumulator columns of this thread's query (one tcgen05.ld.x32). Straight-line code
+          // per chunk: per-row terms (masked / TF32 variants only), eight quad maxima, one test. With two
+          // epilogue warps per SM sub-partition nothing hides a branch, so there is one per 32 columns.
+          // Appends are inherently frequent at large k / small N (a query admits ~K' ln(N/K') rows over the
+          // scan, and 32 queries share a warp), so the hit path must be cheap: only lanes that hold a hit
+          // enter it (divergent branch, no warp vote), and they touch only the quads whose maximum passes.
+          auto process = [&](uint32_t (&v)[TC_CW], int c, bool ragged) {
+            if (METRIC != 2) {
 #pragma unroll
-            for (int j = 0; j < TC_CW; j += 4) {
-              float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (METRIC != 2) n4 = *reinterpret_cast<const float4*>(nrm + c + j);
-              float s0 = __uint_as_float(v[j + 0]), s1 = __uint_as_float(v[j + 1]);
-              float s2 = __uint_as_float(v[j + 2]), s3 = __uint_as_float(v[j + 3]);
-              if (METRIC == 0) { s0 += n4.x; s1 += n4.y; s2 += n4.z; s3 += n4.w; }
-              if (METRIC == 1) { s0 *= n4.x; s1 *= n4.y; s2 *= n4.z; s3 *= n4.w; }
-              v[j + 0] = __float_as_uint(s0); v[j + 1] = __float_as_uint(s1);
-              v[j + 2] = __float_as_uint(s2); v[j + 3] = __float_as_uint(s3);
+              for (int j = 0; j < TC_CW; j += 4) {
+                const float4 n4 = *reinterpret_cast<const float4*>(nrm + c + j);
+                float s0 = __uint_as_float(v[j + 0]), s1 = __uint_as_float(v[j + 1]);
+                float s2 = __uint_as_float(v[j + 2]), s3 = __uint_as_float(v[j + 3]);
+                if (METRIC == 0) { s0 += n4.x; s1 += n4.y; s2 += n4.z; s3 += n4.w; }
+                if (METRIC == 1) { s0 *= n4.x; s1 *= n4.y; s2 *= n4.z; s3 *= n4.w; }
+                v[j + 0] = __float_as_uint(s0); v[j + 1] = __float_as_uint(s1);
+                v[j + 2] = __float_as_uint(s2); v[j + 3] = __float_as_uint(s3);
+              }
             }
             if (DBG) {
               if (u == 0 && t == t0) {
@@ -540,55 +539,77 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int j = 0; j < TC_CW; ++j) p.dbg[(int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
               }
             }
-            if (ncols - c < TC_CW) {
-              // the ragged last tile of the corpus: columns past the last row can never pass
+            if (ragged) {
+              // the last tile of the corpus: columns past the last row can never pass
 #pragma unroll
               for (int j = 0; j < TC_CW; ++j) if (c + j >= ncols) v[j] = 0xff800000u;   // -inf
             }
-            // Four quad maxima -> chunk maximum. Appends are inherently frequent at large k / small N (a
-            // query admits ~K' ln(N/K') rows over the scan, and 32 queries share a warp), so the hit path
-            // must be cheap: only lanes that hold a hit enter it (divergent branch, no warp vote), and
-            // they touch only the quads whose maximum passes.
-            const float q0 = max4(v, 0), q1 = max4(v, 1), q2 = max4(v, 2), q3 = max4(v, 3);
-            if (fmaxf(fmaxf(q0, q1), fmaxf(q2, q3)) > tau) {
+            float qm[TC_CW / 4];
+#pragma unroll
+            for (int g = 0; g < TC_CW / 4; ++g) qm[g] = max4(v, g);
+            float m = qm[0];
+#pragma unroll
+            for (int g = 1; g < TC_CW / 4; ++g) m = fmaxf(m, qm[g]);
+            if (m > tau) {
               const uint32_t col_base = uint32_t(col0 + c);
-              if (q0 > tau) append_quad<0>(v, tau, wp, col_base);
-              if (q1 > tau) append_quad<1>(v, tau, wp, col_base);
-              if (q2 > tau) append_quad<2>(v, tau, wp, col_base);
-              if (q3 > tau) append_quad<3>(v, tau, wp, col_base);
+#pragma unroll
+              for (int g = 0; g < TC_CW / 4; ++g) {
+                if (qm[g] > tau) {
+#pragma unroll
+                  for (int j = 4 * g; j < 4 * g + 4; ++j) {
+                    if (__uint_as_float(v[j]) > tau) { *wp = make_uint2(v[j], col_base + uint32_t(j)); ++wp; }
+                  }
+                }
+              }
             }
           };
           const uint32_t t_acc = t_lane + uint32_t(acc * TC_BN);
-#if FENIX_TC_PIPE
-          // two register sets: the TMEM load of chunk c+1 is in flight while chunk c is processed
-          uint32_t va[TC_CW], vb[TC_CW];
-          tmem_ld_32x32b_x16(t_acc, va);
+          if (ncols >= TC_HALF_COLS) {
+            // full tile: two register sets, the TMEM load of chunk i+1 is in flight while chunk i is processed
+            static_assert(TC_HALF_COLS % (2 * TC_CW) == 0, "chunk pairs");
+            uint32_t va[TC_CW], vb[TC_CW];
+            tmem_ld_32x32b_x32(t_acc, va);
+#pragma unroll
+            for (int c = 0; c < TC_HALF_COLS; c += 2 * TC_CW) {
+              tmem_ld_wait_dep(va);
+              tmem_ld_32x32b_x32(t_acc + uint32_t(c + TC_CW), vb);
+              process(va, c, false);
+              tmem_ld_wait_dep(vb);
+              if (c + 2 * TC_CW < TC_HALF_COLS) tmem_ld_32x32b_x32(t_acc + uint32_t(c + 2 * TC_CW), va);
+              else if (METRIC == 2) {
+                // the accumulator stage has been read completely: hand it back to the MMA warp before the last chunk
+                // is processed (variants with per-row terms release it together with their norm buffer, below)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+              }
+              process(vb, c + TC_CW, false);
+            }
+          } else {
 #pragma unroll 1
-          for (int c = 0; c < TC_HALF_COLS; c += 2 * TC_CW) {
-            if (c >= ncols) break;
-            tmem_ld_wait_dep(va);
-            if (c + TC_CW < ncols) tmem_ld_32x32b_x16(t_acc + uint32_t(c + TC_CW), vb);
-            process(va, c);
-            if (c + TC_CW >= ncols) break;
-            tmem_ld_wait_dep(vb);
-            if (c + 2 * TC_CW < ncols && c + 2 * TC_CW < TC_HALF_COLS) tmem_ld_32x32b_x16(t_acc + uint32_t(c + 2 * TC_CW), va);
-            process(vb, c + TC_CW);
+            for (int c = 0; c < ncols; c += TC_CW) {
+              uint32_t va[TC_CW];
+              tmem_ld_32x32b_x32(t_acc + uint32_t(c), va);
+              tmem_ld_wait_dep(va);
+              process(va, c, true);
+            }
+            if (METRIC == 2) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
           }
-#else
-#pragma unroll 1
-          for (int c = 0; c < TC_HALF_COLS; c += TC_CW) {
-            if (c >= ncols) break;
-            uint32_t va[TC_CW];
-            tmem_ld_32x32b_x16(t_acc + uint32_t(c), va);
-            tmem_ld_wait();
-            process(va, c);
-          }
-#endif
+        } else if (METRIC == 2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         // release the accumulator stage (and its norm buffer) back to the MMA / TMA warps
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (METRIC != 2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
 
         __syncwarp();
