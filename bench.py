@@ -401,8 +401,14 @@ def main() -> None:
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "scan"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows", type=int, default=0, help="tuning only: override the corpus row count of the config")
+    ap.add_argument("--queries", type=int, default=0, help="tuning only: override the query batch of the config")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.rows or args.queries:
+        cfg["n"] = args.rows or cfg["n"]
+        cfg["q"] = args.queries or cfg["q"]
+        cfg["label"] += f" [TUNING OVERRIDE rows={cfg['n']} queries={cfg['q']}: not a benchmark configuration]"
     out = run_reference(args, cfg) if args.impl == "reference" else run_ours(args, cfg)
     if out is not None:
         print(json.dumps(out), flush=True)

@@ -468,7 +468,7 @@ static bool ensure_norm_shadow(fx_corpus* c) {
                                                             static_cast<__nv_bfloat16*>(c->Xn), n_kb, n_tiles, 0, 0);
   std::string err;
   if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
-      !fx::tc_bind_shadow(&ctx->tc, &c->tc.map_xn, c->Xn, c->n, n_kb, &err)) {
+      !fx::tc_bind_shadow(&ctx->tc, &c->tc.map_xn, &c->tc.map_xn_h, c->Xn, c->n, n_kb, &err)) {
     cudaGetLastError(); cudaFree(c->Xn); c->Xn = nullptr; c->xn_failed = true;
     return false;
   }
@@ -484,10 +484,10 @@ static bool ensure_norm_shadow(fx_corpus* c) {
 static int configure_filter(fx_corpus* c, int metric, int kind, const uint8_t* d_mask, fx::TcSearch* s) {
   fx_ctx* ctx = c->ctx;
   s->kind = kind; s->pitch_b = c->pitch_b; s->shadow = 0; s->aug = 0; s->epi = metric;
-  s->hx = c->hx; s->rx = c->rx;
+  s->hx = c->hx; s->rx = c->rx; s->Xb = c->Xb; s->Xn = c->Xn;
   if (kind == 1) {
     if (metric == 0) { s->aug = 1; s->epi = 2; }                       // -|x|^2/2 rides in the shadow's extra columns
-    else if (metric == 1) { if (ensure_norm_shadow(c)) { s->shadow = 1; s->epi = 2; } }
+    else if (metric == 1) { if (ensure_norm_shadow(c)) { s->shadow = 1; s->epi = 2; s->Xn = c->Xn; } }
   }
   if (d_mask) {
     const int64_t n_alloc = ((c->n + 255) / 256) * 256;

@@ -46,6 +46,10 @@ constexpr int TC_SPLIT = FENIX_TC_SPLIT;
 #ifndef FENIX_TC_BACKOFF
 #define FENIX_TC_BACKOFF 1                 // 1: producer / MMA polling loops sleep between polls
 #endif
+#ifndef FENIX_EPI_UNROLL
+#define FENIX_EPI_UNROLL 1                 // unroll factor of the epilogue's chunk-pair loop (1 = rolled)
+#endif
+constexpr int TC_EPI_UNROLL = FENIX_EPI_UNROLL;
 #ifndef FENIX_TC_PIPE
 #define FENIX_TC_PIPE 0                    // 1: software-pipelined TMEM loads in the epilogue
 #endif
@@ -92,6 +96,7 @@ struct TcCorpus {
   CUtensorMap map_x;       // [n_rows][pitch] fp32, box 32 x 256, 128B swizzle
   CUtensorMap map_xb;      // bf16 shadow, tiled [tile][k-block][256 rows][64], box 64 x 256 = one contiguous 32 KB block
   CUtensorMap map_xn;      // bf16 shadow of the NORMALISED rows x/|x| (cosine), same layout, built on first use
+  CUtensorMap map_xb_h, map_xn_h;   // the same shadows seen through 128-row boxes (resident-query kernel)
   bool ok = false;
   bool ok_b = false;
   bool ok_n = false;
@@ -106,6 +111,7 @@ struct TcSearch {
   const uint32_t* tau_fixed; // refinement pass: preset per-query admission thresholds (ordered encoding) or null
   int epi;                   // epilogue form: 0 score = acc + hx[row], 1 score = acc * rx[row], 2 score = acc
   int shadow;                // kind 1: 0 = plain shadow (+ augmented columns), 1 = normalised shadow
+  const void* Xb; const void* Xn;   // device addresses of the two shadows (L2 prefetch)
   int aug;                   // kind 1, L2: the query gets three 1.0 columns that pick up the shadow's -|x|^2/2 columns
 };
 
@@ -176,6 +182,10 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Pull `bytes` (multiple of 16) at a global address into L2 without occupying shared memory.
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -285,6 +295,9 @@ struct TcParams {
   int n_kb_data;          // data k-blocks per tile (the tile stride of the tiled shadow)
   int nk_last;            // MMA instructions (32 B of K each) of the last data block: only columns that hold data are multiplied
   int aug_line0;          // first 128-byte line of the separate augmented region of the shadow (one block per tile)
+  const unsigned char* xb; // base of the tiled bf16 shadow in use (L2 prefetch), or null
+  int pf_tiles;           // L2 prefetch distance in tiles (0: off): the TMA ring only covers ~2 tiles, far less than a DRAM miss
+  int rq_stages;          // resident-query kernel: depth of the corpus-block ring
   int kp;                 // K': candidates kept per (query, unit-half) selection
   int cap;                // candidate buffer capacity per epilogue thread (512 or 1024)
   const float* hx;        // [n_rows padded to 256] -0.5|x|^2
@@ -368,6 +381,124 @@ __device__ __noinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp
 }
 
 // ---------------------------------------------------------------------------------------------
+// epilogue building blocks shared by the two filter kernels
+// ---------------------------------------------------------------------------------------------
+// One call handles the TC_HALF_COLS (128) accumulator columns at TMEM address t_acc that belong to this thread's
+// query: score, compare with the running threshold, append survivors at wp, hand the accumulator back (arrive on
+// release_bar, one arrival per warp). ncols = valid columns (<= 0: nothing to look at, only the release).
+//
+// One chunk = 32 columns (one tcgen05.ld.x32), straight-line code per chunk: per-row terms (METRIC 0 add / 1 multiply,
+// read from nrm in shared memory; METRIC 2: the score is the accumulator), eight quad maxima, one test. With two
+// epilogue warps per SM sub-partition nothing hides a branch, so there is one per 32 columns. Appends are inherently
+// frequent at large k / small N (a query admits ~K' ln(N/K') rows over the scan, and 32 queries share a warp), so
+// the hit path must be cheap: only lanes that hold a hit enter it (divergent branch, no warp vote), and they touch
+// only the quads whose maximum passes.
+template <int METRIC, bool DBG>
+__device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float* nrm, int col0, float tau, uint2*& wp,
+                                         uint64_t* release_bar, uint32_t lane, float* dbg_row) {
+  auto release = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release_bar);
+  };
+  auto process = [&](uint32_t (&v)[TC_CW], int c, bool ragged) {
+    if (METRIC != 2) {
+#pragma unroll
+      for (int j = 0; j < TC_CW; j += 4) {
+        const float4 n4 = *reinterpret_cast<const float4*>(nrm + c + j);
+        float s0 = __uint_as_float(v[j + 0]), s1 = __uint_as_float(v[j + 1]);
+        float s2 = __uint_as_float(v[j + 2]), s3 = __uint_as_float(v[j + 3]);
+        if (METRIC == 0) { s0 += n4.x; s1 += n4.y; s2 += n4.z; s3 += n4.w; }
+        if (METRIC == 1) { s0 *= n4.x; s1 *= n4.y; s2 *= n4.z; s3 *= n4.w; }
+        v[j + 0] = __float_as_uint(s0); v[j + 1] = __float_as_uint(s1);
+        v[j + 2] = __float_as_uint(s2); v[j + 3] = __float_as_uint(s3);
+      }
+    }
+    if (DBG) {
+      if (dbg_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < TC_CW; ++j) dbg_row[c + j] = __uint_as_float(v[j]);
+      }
+    }
+    if (ragged) {
+      // the last tile of the corpus: columns past the last row can never pass
+#pragma unroll
+      for (int j = 0; j < TC_CW; ++j) if (c + j >= ncols) v[j] = 0xff800000u;   // -inf
+    }
+    float qm[TC_CW / 4];
+#pragma unroll
+    for (int g = 0; g < TC_CW / 4; ++g) qm[g] = max4(v, g);
+    float m = qm[0];
+#pragma unroll
+    for (int g = 1; g < TC_CW / 4; ++g) m = fmaxf(m, qm[g]);
+    if (m > tau) {
+      const uint32_t col_base = uint32_t(col0 + c);
+#pragma unroll
+      for (int g = 0; g < TC_CW / 4; ++g) {
+        if (qm[g] > tau) {
+#pragma unroll
+          for (int j = 4 * g; j < 4 * g + 4; ++j) {
+            if (__uint_as_float(v[j]) > tau) { *wp = make_uint2(v[j], col_base + uint32_t(j)); ++wp; }
+          }
+        }
+      }
+    }
+  };
+  if (ncols >= TC_HALF_COLS) {
+    // full tile: two register sets, the TMEM load of chunk i+1 is in flight while chunk i is processed
+    static_assert(TC_HALF_COLS % (2 * TC_CW) == 0, "chunk pairs");
+    uint32_t va[TC_CW], vb[TC_CW];
+    tmem_ld_32x32b_x32(t_acc, va);
+    // NOT unrolled: the chunk body (with its 32 append sites) is large, and the kernel's hot code must stay inside
+    // the instruction cache (measured: a build whose epilogue grew from ~24 KB to ~28 KB of SASS ran 28 % slower)
+#pragma unroll TC_EPI_UNROLL
+    for (int c = 0; c < TC_HALF_COLS; c += 2 * TC_CW) {
+      tmem_ld_wait_dep(va);
+      tmem_ld_32x32b_x32(t_acc + uint32_t(c + TC_CW), vb);
+      process(va, c, false);
+      tmem_ld_wait_dep(vb);
+      if (c + 2 * TC_CW < TC_HALF_COLS) tmem_ld_32x32b_x32(t_acc + uint32_t(c + 2 * TC_CW), va);
+      else if (METRIC == 2) release();   // the accumulator has been read completely: hand it back before the last chunk
+      process(vb, c + TC_CW, false);
+    }
+    if (METRIC != 2) release();          // variants with per-row terms release their norm buffer with it
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < ncols; c += TC_CW) {
+      uint32_t va[TC_CW];
+      tmem_ld_32x32b_x32(t_acc + uint32_t(c), va);
+      tmem_ld_wait_dep(va);
+      process(va, c, true);
+    }
+    release();
+  }
+}
+
+// Tighten thresholds after a tile: a lane whose buffer could overflow during the next tile, or that holds >= K'
+// candidates but no threshold yet, gets a warp-cooperative selection; the new threshold is shared through tau_g.
+__device__ __forceinline__ void epi_tighten(const TcParams& p, bool active, int q, uint2* buf, uint2*& wp, float& tau, uint32_t lane) {
+  __syncwarp();
+  int cnt = int(wp - buf);
+  if (p.fixed && active && cnt > p.cap - TC_HALF_COLS) { p.flags[q] = 1; tau = INFINITY; }   // more survivors than the buffer holds
+  bool need = active && !p.fixed && ((cnt > p.cap - TC_HALF_COLS) || (tau == -INFINITY && cnt >= p.kp));
+  uint32_t need_mask = __ballot_sync(0xffffffffu, need);
+  while (need_mask) {
+    const int src = __ffs(need_mask) - 1;
+    need_mask &= need_mask - 1;
+    uint2* b = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
+    const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+    int new_cnt;
+    uint32_t v_ord = (p.cap == 1024) ? warp_select_compact<32>(b, c_src, p.kp, new_cnt)
+                                     : warp_select_compact<16>(b, c_src, p.kp, new_cnt);
+    if (int(lane) == src) {
+      wp = buf + new_cnt;
+      tau = fmaxf(tau, ord2f(v_ord));
+      atomicMax(p.tau_g + q, v_ord);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the filter kernel
 // ---------------------------------------------------------------------------------------------
 // KIND 0: fp32 operands read as TF32 (k-block = 32 elements, UMMA K = 8)
@@ -433,8 +564,17 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             constexpr int kElemsPerBlock = KIND == 0 ? TC_BK : 2 * TC_BK;
             tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * kElemsPerBlock, qt * TC_BM);
             if (KIND == 0) tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * kElemsPerBlock, t * TC_BN);
-            else tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0,                 // tiled shadow: one contiguous 32 KB block
-                             kb < p.n_kb_data ? (t * p.n_kb_data + kb) * TC_BN : p.aug_line0 + t * TC_BN);
+            else {
+              tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0,                   // tiled shadow: one contiguous 32 KB block
+                          kb < p.n_kb_data ? (t * p.n_kb_data + kb) * TC_BN : p.aug_line0 + t * TC_BN);
+#ifndef FENIX_NO_PFCODE
+              if (p.pf_tiles > 0 && t + p.pf_tiles < t1) {
+                const int tp = t + p.pf_tiles;
+                const int64_t line = kb < p.n_kb_data ? (int64_t(tp) * p.n_kb_data + kb) * TC_BN : int64_t(p.aug_line0) + int64_t(tp) * TC_BN;
+                prefetch_l2(p.xb + line * 128, TC_B_BYTES);
+              }
+#endif
+            }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -513,126 +653,12 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int col0 = t * TC_BN + half * TC_HALF_COLS;                  // global row of column 0 of this half
         const int ncols = int(min(int64_t(TC_HALF_COLS), p.n_rows - int64_t(col0)));  // valid columns (<=0: none)
         const float* nrm = norm_smem + acc * TC_BN + half * TC_HALF_COLS;
-        if (__any_sync(0xffffffffu, active) && ncols > 0) {
-          // One chunk = 32 accumulator columns of this thread's query (one tcgen05.ld.x32). Straight-line code
-          // per chunk: per-row terms (masked / TF32 variants only), eight quad maxima, one test. With two
-          // epilogue warps per SM sub-partition nothing hides a branch, so there is one per 32 columns.
-          // Appends are inherently frequent at large k / small N (a query admits ~K' ln(N/K') rows over the
-          // scan, and 32 queries share a warp), so the hit path must be cheap: only lanes that hold a hit
-          // enter it (divergent branch, no warp vote), and they touch only the quads whose maximum passes.
-          auto process = [&](uint32_t (&v)[TC_CW], int c, bool ragged) {
-            if (METRIC != 2) {
-#pragma unroll
-              for (int j = 0; j < TC_CW; j += 4) {
-                const float4 n4 = *reinterpret_cast<const float4*>(nrm + c + j);
-                float s0 = __uint_as_float(v[j + 0]), s1 = __uint_as_float(v[j + 1]);
-                float s2 = __uint_as_float(v[j + 2]), s3 = __uint_as_float(v[j + 3]);
-                if (METRIC == 0) { s0 += n4.x; s1 += n4.y; s2 += n4.z; s3 += n4.w; }
-                if (METRIC == 1) { s0 *= n4.x; s1 *= n4.y; s2 *= n4.z; s3 *= n4.w; }
-                v[j + 0] = __float_as_uint(s0); v[j + 1] = __float_as_uint(s1);
-                v[j + 2] = __float_as_uint(s2); v[j + 3] = __float_as_uint(s3);
-              }
-            }
-            if (DBG) {
-              if (u == 0 && t == t0) {
-#pragma unroll
-                for (int j = 0; j < TC_CW; ++j) p.dbg[(int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS + c + j] = __uint_as_float(v[j]);
-              }
-            }
-            if (ragged) {
-              // the last tile of the corpus: columns past the last row can never pass
-#pragma unroll
-              for (int j = 0; j < TC_CW; ++j) if (c + j >= ncols) v[j] = 0xff800000u;   // -inf
-            }
-            float qm[TC_CW / 4];
-#pragma unroll
-            for (int g = 0; g < TC_CW / 4; ++g) qm[g] = max4(v, g);
-            float m = qm[0];
-#pragma unroll
-            for (int g = 1; g < TC_CW / 4; ++g) m = fmaxf(m, qm[g]);
-            if (m > tau) {
-              const uint32_t col_base = uint32_t(col0 + c);
-#pragma unroll
-              for (int g = 0; g < TC_CW / 4; ++g) {
-                if (qm[g] > tau) {
-#pragma unroll
-                  for (int j = 4 * g; j < 4 * g + 4; ++j) {
-                    if (__uint_as_float(v[j]) > tau) { *wp = make_uint2(v[j], col_base + uint32_t(j)); ++wp; }
-                  }
-                }
-              }
-            }
-          };
-          const uint32_t t_acc = t_lane + uint32_t(acc * TC_BN);
-          if (ncols >= TC_HALF_COLS) {
-            // full tile: two register sets, the TMEM load of chunk i+1 is in flight while chunk i is processed
-            static_assert(TC_HALF_COLS % (2 * TC_CW) == 0, "chunk pairs");
-            uint32_t va[TC_CW], vb[TC_CW];
-            tmem_ld_32x32b_x32(t_acc, va);
-#pragma unroll
-            for (int c = 0; c < TC_HALF_COLS; c += 2 * TC_CW) {
-              tmem_ld_wait_dep(va);
-              tmem_ld_32x32b_x32(t_acc + uint32_t(c + TC_CW), vb);
-              process(va, c, false);
-              tmem_ld_wait_dep(vb);
-              if (c + 2 * TC_CW < TC_HALF_COLS) tmem_ld_32x32b_x32(t_acc + uint32_t(c + 2 * TC_CW), va);
-              else if (METRIC == 2) {
-                // the accumulator stage has been read completely: hand it back to the MMA warp before the last chunk
-                // is processed (variants with per-row terms release it together with their norm buffer, below)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-              }
-              process(vb, c + TC_CW, false);
-            }
-          } else {
-#pragma unroll 1
-            for (int c = 0; c < ncols; c += TC_CW) {
-              uint32_t va[TC_CW];
-              tmem_ld_32x32b_x32(t_acc + uint32_t(c), va);
-              tmem_ld_wait_dep(va);
-              process(va, c, true);
-            }
-            if (METRIC == 2) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            }
-          }
-        } else if (METRIC == 2) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        // release the accumulator stage (and its norm buffer) back to the MMA / TMA warps
-        if (METRIC != 2) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
+        float* dbg_row = nullptr;
+        if (DBG) { if (u == 0 && t == t0) dbg_row = p.dbg + (int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS; }
+        epi_tile<METRIC, DBG>(t_lane + uint32_t(acc * TC_BN), __any_sync(0xffffffffu, active) ? ncols : 0, nrm, col0, tau, wp,
+                              &tmem_empty[acc], lane, dbg_row);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-
-        __syncwarp();
-        // tighten thresholds: a lane whose buffer could overflow next tile, or that holds >= K'
-        // candidates but no threshold yet, gets a warp-cooperative selection
-        int cnt = int(wp - buf);
-        if (p.fixed && active && cnt > p.cap - TC_HALF_COLS) { p.flags[q] = 1; tau = INFINITY; }   // more survivors than the buffer holds
-        bool need = active && !p.fixed && ((cnt > p.cap - TC_HALF_COLS) || (tau == -INFINITY && cnt >= p.kp));
-        uint32_t need_mask = __ballot_sync(0xffffffffu, need);
-        while (need_mask) {
-          const int src = __ffs(need_mask) - 1;
-          need_mask &= need_mask - 1;
-          uint2* b = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
-          const int c_src = __shfl_sync(0xffffffffu, cnt, src);
-          int new_cnt;
-          uint32_t v_ord = (p.cap == 1024) ? warp_select_compact<32>(b, c_src, p.kp, new_cnt)
-                                           : warp_select_compact<16>(b, c_src, p.kp, new_cnt);
-          if (int(lane) == src) {
-            wp = buf + new_cnt;
-            tau = fmaxf(tau, ord2f(v_ord));
-            atomicMax(p.tau_g + q, v_ord);
-          }
-        }
+        epi_tighten(p, active, q, buf, wp, tau, lane);
       }
 
       // end of unit: the finish kernel reads the buffer in place
@@ -649,15 +675,213 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// the resident-query filter kernel (narrow rows: D + 3 <= 192 bf16 columns, at least two query tiles)
+// ---------------------------------------------------------------------------------------------
+// At small D the streaming kernel above is bound by L2 -> SM operand traffic, not by the tensor pipe: every
+// 128 x 256 tile re-reads its query block and a corpus block that serves only 128 queries (C2: 9.6 TB/s of
+// operand traffic at 0.40 of the bf16 peak). Here one CTA keeps TWO query tiles (256 queries) resident in shared
+// memory for a whole unit and streams only corpus blocks of 128 rows; each block feeds two MMAs (one per query
+// tile), so operand bytes per flop drop 3-4.5x:
+//   smem   A: 2 query tiles x n_kb x 16 KB (loaded once per unit)      B: ring of RQ_STAGES x 16 KB (128 rows x 128 B)
+//   TMEM   4 accumulators of 128 columns: (stage 0/1) x (query tile 0/1)
+//   warps  0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue of query tile 0, 8-11 of query tile 1;
+//          every epilogue warp owns 32 queries and scans all 128 columns of its accumulator.
+// Units: (query pair) x (corpus slice of 128-row tiles), slice-major like the streaming kernel; candidate lists:
+// one per (unit, query).
+constexpr int RQ_BN = 128;                       // corpus rows per accumulator
+constexpr int RQ_MAX_KB = 3;                     // k-blocks (64 bf16 columns) per row at most
+constexpr int RQ_MAX_STAGES = 12;               // ring depth is chosen at launch: whatever shared memory the query tiles leave
+constexpr uint32_t RQ_BLOCK_BYTES = 128 * 128;   // 128 rows x 128 B: one k-block of a query tile or of a corpus tile
+constexpr uint32_t RQ_NORM_BYTES = RQ_BN * 4;
+constexpr uint32_t RQ_SMEM_MAX = 227 * 1024;
+constexpr uint32_t RQ_FIXED_BYTES = 1024 /*align slack*/ + 2 * RQ_NORM_BYTES + 512 /*barriers*/;
+inline int rq_stages(int n_kblocks) {
+  const int s = int((RQ_SMEM_MAX - RQ_FIXED_BYTES - 2u * uint32_t(n_kblocks) * RQ_BLOCK_BYTES) / RQ_BLOCK_BYTES);
+  return s < RQ_MAX_STAGES ? s : RQ_MAX_STAGES;
+}
+inline uint32_t rq_smem_bytes(int n_kblocks) {
+  return RQ_FIXED_BYTES + uint32_t(2 * n_kblocks + rq_stages(n_kblocks)) * RQ_BLOCK_BYTES;
+}
+
+template <int METRIC>   // 0: score = acc + hx[row] (masked searches), 2: score = acc
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int n_stages = p.rq_stages;
+  unsigned char* a_tiles = smem;                                      // [2][n_kblocks] blocks
+  unsigned char* b_ring = smem + 2 * p.n_kblocks * RQ_BLOCK_BYTES;    // [n_stages] blocks
+  float* norm_smem = reinterpret_cast<float*>(b_ring + n_stages * RQ_BLOCK_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(norm_smem) + 2 * RQ_NORM_BYTES);
+  uint64_t* full_bar = bars;                      // [RQ_MAX_STAGES] TMA -> MMA
+  uint64_t* empty_bar = full_bar + RQ_MAX_STAGES; // [RQ_MAX_STAGES] MMA -> TMA
+  uint64_t* a_full = empty_bar + RQ_MAX_STAGES;   // [1]  query tiles of the unit have landed
+  uint64_t* a_empty = a_full + 1;                 // [1]  the unit's last MMA has retired
+  uint64_t* tmem_full = a_empty + 1;              // [2]  per stage (both query tiles)
+  uint64_t* tmem_empty = tmem_full + 2;           // [2][2] per (stage, query tile), 4 warps each
+  uint64_t* norm_full = tmem_empty + 4;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_x);
+    for (int i = 0; i < n_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&norm_full[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&tmem_empty[i], 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_qp = (p.n_qt + 1) >> 1;
+  const int n_units = p.n_slices * n_qp;
+  const int n_t128 = int((p.n_rows + RQ_BN - 1) / RQ_BN);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t a_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int qp = u % n_qp, slice = u / n_qp;
+        const int t0 = slice * p.tiles_per_slice, t1 = min(n_t128, t0 + p.tiles_per_slice);
+        // the unit's two query tiles (the previous unit's MMAs must have retired first)
+        mbar_wait_backoff(a_empty, a_phase ^ 1, 64);
+        mbar_expect_tx(a_full, uint32_t(2 * p.n_kblocks) * RQ_BLOCK_BYTES);
+        for (int qt = 0; qt < 2; ++qt)
+          for (int kb = 0; kb < p.n_kblocks; ++kb)
+            tma_load_2d(&map_q, a_full, a_tiles + (qt * p.n_kblocks + kb) * RQ_BLOCK_BYTES, kb * 64, (qp * 2 + qt) * TC_BM);
+        a_phase ^= 1;
+        for (int t = t0; t < t1; ++t) {
+          if (METRIC != 2) {
+            // per-row terms of this tile, one buffer per accumulator stage; both query-tile groups must have left it
+            mbar_wait_backoff(&tmem_empty[acc * 2 + 0], acc_phase ^ 1, 64);
+            mbar_wait_backoff(&tmem_empty[acc * 2 + 1], acc_phase ^ 1, 64);
+            mbar_expect_tx(&norm_full[acc], RQ_NORM_BYTES);
+            bulk_load_1d(norm_smem + acc * RQ_BN, p.hx + size_t(t) * RQ_BN, RQ_NORM_BYTES, &norm_full[acc]);
+          }
+          // corpus tile t = rows [128 t, 128 t + 128) = half (t & 1) of the shadow's 256-row block t >> 1
+          const int blk = t >> 1, hrow = (t & 1) * RQ_BN;
+          for (int kb = 0; kb < p.n_kblocks; ++kb) {
+            mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
+            mbar_expect_tx(&full_bar[stage], RQ_BLOCK_BYTES);
+            const int line = (kb < p.n_kb_data ? (blk * p.n_kb_data + kb) * TC_BN : p.aug_line0 + blk * TC_BN) + hrow;
+            tma_load_2d(&map_x, &full_bar[stage], b_ring + stage * RQ_BLOCK_BYTES, 0, line);
+            if (p.pf_tiles > 0 && t + p.pf_tiles < t1) {
+              const int tp = t + p.pf_tiles, blkp = tp >> 1;
+              const int64_t linep = (kb < p.n_kb_data ? (int64_t(blkp) * p.n_kb_data + kb) * TC_BN : int64_t(p.aug_line0) + int64_t(blkp) * TC_BN) + (tp & 1) * RQ_BN;
+              prefetch_l2(p.xb + linep * 128, RQ_BLOCK_BYTES);
+            }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, RQ_BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t a_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int slice = u / n_qp;
+        const int t0 = slice * p.tiles_per_slice, t1 = min(n_t128, t0 + p.tiles_per_slice);
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait_backoff(&tmem_empty[acc * 2 + 0], acc_phase ^ 1, 32);
+          mbar_wait_backoff(&tmem_empty[acc * 2 + 1], acc_phase ^ 1, 32);
+          tc_fence_after();
+          for (int kb = 0; kb < p.n_kblocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t b_desc = make_smem_desc(smem_u32(b_ring + stage * RQ_BLOCK_BYTES));
+            const int nk = kb < p.n_kb_data - 1 ? 4 : (kb == p.n_kb_data - 1 ? p.nk_last : 1);
+#pragma unroll
+            for (int qt = 0; qt < 2; ++qt) {
+              const uint32_t d_tmem = tmem_base + uint32_t((acc * 2 + qt) * RQ_BN);
+              const uint64_t a_desc = make_smem_desc(smem_u32(a_tiles + (qt * p.n_kblocks + kb) * RQ_BLOCK_BYTES));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k >= nk) break;
+                umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        umma_commit(a_empty);   // the resident query tiles may be replaced once everything issued so far has retired
+      }
+    }
+  } else if (warp >= TC_EPI_FIRST_WARP) {
+    // ===================== epilogue =====================
+    const int e = warp - TC_EPI_FIRST_WARP;
+    const int lane_grp = warp & 3;
+    const int qt_l = e >> 2;                      // which of the unit's two query tiles
+    const int slot = qt_l * TC_BM + lane_grp * 32 + int(lane);
+    const uint32_t t_lane = tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(qt_l * RQ_BN);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int qp = u % n_qp, slice = u / n_qp;
+      const int t0 = slice * p.tiles_per_slice, t1 = min(n_t128, t0 + p.tiles_per_slice);
+      const int q = (qp * 2 + qt_l) * TC_BM + int(lane) * 4 + lane_grp;
+      const bool active = q < p.n_q;
+      uint2* buf = p.wbuf + (size_t(u) * TC_SLOTS + slot) * p.cap;
+      uint2* wp = buf;
+      float tau = active ? -INFINITY : INFINITY;
+      if (p.fixed && active) tau = ord2f(p.tau_g[q]);
+      const bool poll = active && !p.fixed;
+      uint32_t tg_next = poll ? ld_relaxed_u32(p.tau_g + q) : ORD_NEG_INF;
+      for (int t = t0; t < t1; ++t) {
+        if (poll) {
+          tau = fmaxf(tau, ord2f(tg_next));
+          tg_next = ld_relaxed_u32(p.tau_g + q);
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        if (METRIC != 2) mbar_wait(&norm_full[acc], acc_phase);
+        tc_fence_after();
+        const int col0 = t * RQ_BN;
+        const int ncols = int(min(int64_t(RQ_BN), p.n_rows - int64_t(col0)));
+        epi_tile<METRIC, false>(t_lane + uint32_t(acc * 2 * RQ_BN), __any_sync(0xffffffffu, active) ? ncols : 0,
+                                norm_smem + acc * RQ_BN, col0, tau, wp, &tmem_empty[acc * 2 + qt_l], lane, nullptr);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        epi_tighten(p, active, q, buf, wp, tau, lane);
+      }
+      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wp - buf) : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // query preparation: pad to the TMA pitch, reset per-query state
 // ---------------------------------------------------------------------------------------------
-__global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int dim, int pitch, float* __restrict__ Qp,
+__global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int n_rows_p, int dim, int pitch, float* __restrict__ Qp,
                                 uint32_t* __restrict__ tau_g, int* __restrict__ flags,
                                 __nv_bfloat16* __restrict__ Qb, int pitch_b,
                                 const uint32_t* __restrict__ tau_fixed, int keep_tau, int aug_col) {
   // Rows are written in TILE order: row qt*128 + j holds query qt*128 + (j % 32) * 4 + j / 32 (zeros past the last
   // query), so that consecutive queries land in different TMEM lane groups.
-  const int n_rows_p = ((n_q + TC_BM - 1) / TC_BM) * TC_BM;
+  // n_rows_p: rows of the padded query matrices (whole tile pairs)
   const int64_t total = int64_t(n_rows_p) * pitch;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     int row = int(i / pitch), d = int(i - int64_t(row) * pitch);
@@ -690,7 +914,7 @@ constexpr int FIN_POOL = 2048;   // candidates the finish kernel can hold in sha
 struct FinishParams {
   const float* X; int pitch; int dim; int64_t row_base;
   const float* Qp; int n_q; int n_qt; int n_slices; int cap; int metric; int k; int kp; int sort2;  // sort2: pow2 >= kp
-  const uint32_t* tau_g; const uint2* wbuf; const int* wcnt; int qt_major;
+  const uint32_t* tau_g; const uint2* wbuf; const int* wcnt; int qt_major; int rq; int n_qp;
   int* flags; int certify; float max_norm; double c_err; double c_add;
   int64_t* out_rows; float* out_dist;
 };
@@ -718,7 +942,7 @@ knn_tc_finish_kernel(FinishParams p) {
   const int qt = q / TC_BM, w = q - qt * TC_BM;
   const int r = (w % 4) * 32 + w / 4;               // tile row / candidate-buffer slot of this query
   const size_t q_row = size_t(qt) * TC_BM + r;      // its row in the (tile-ordered) padded query matrix
-  const int n_lists = TC_SPLIT * p.n_slices;
+  const int n_lists = (p.rq ? 1 : TC_SPLIT) * p.n_slices;
 
   for (int d = tid; d < p.pitch; d += blockDim.x) qs[d] = p.Qp[q_row * p.pitch + d];
   if (tid == 0) { s_n_gt = 0; s_n_tie = 0; s_prefix = 0; s_remaining = p.kp; }
@@ -735,9 +959,14 @@ knn_tc_finish_kernel(FinishParams p) {
 
   // list l = (slice, half): buffer of thread slot half*128 + r of unit slice*n_qt + qt
   auto list_ptr = [&](int l, int& count) -> const uint2* {
-    const int slice = l / TC_SPLIT, half = l % TC_SPLIT;
-    const size_t unit = p.qt_major ? size_t(qt) * p.n_slices + slice : size_t(slice) * p.n_qt + qt;
-    const size_t unit_slot = unit * TC_SLOTS + half * TC_BM + r;
+    size_t unit_slot;
+    if (p.rq) {   // one list per slice; the unit holds two query tiles
+      unit_slot = (size_t(l) * p.n_qp + (qt >> 1)) * TC_SLOTS + (qt & 1) * TC_BM + r;
+    } else {
+      const int slice = l / TC_SPLIT, half = l % TC_SPLIT;
+      const size_t unit = p.qt_major ? size_t(qt) * p.n_slices + slice : size_t(slice) * p.n_qt + qt;
+      unit_slot = unit * TC_SLOTS + half * TC_BM + r;
+    }
     count = p.wcnt[unit_slot];
     return p.wbuf + unit_slot * p.cap;
   };
@@ -1079,15 +1308,19 @@ inline bool tc_init(TcState* st, int sm_count, std::string* err) {
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (a != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(tc kernels) failed: ") + cudaGetErrorString(a); return false; }
   return true;
 }
 
 // tiled shadow: a flat list of 128-byte lines, 256 lines per (tile, k-block)
-inline bool tc_bind_shadow(const TcState* st, CUtensorMap* map, const void* Xb, int64_t n_rows, int blocks_per_tile, std::string* err) {
+inline bool tc_bind_shadow(const TcState* st, CUtensorMap* map, CUtensorMap* map_half, const void* Xb, int64_t n_rows,
+                           int blocks_per_tile, std::string* err) {
   const uint64_t lines = uint64_t((n_rows + TC_BN - 1) / TC_BN) * uint64_t(blocks_per_tile) * TC_BN;
   if (lines >= (uint64_t(1) << 31)) { *err = "shard too large for the tiled bf16 shadow (32-bit TMA coordinates)"; return false; }
+  if (!tc_encode_2d(st, map_half, Xb, uint64_t(2 * TC_BK), lines, uint64_t(2 * TC_BK), 2 * TC_BK, TC_BN / 2, err, true)) return false;
   return tc_encode_2d(st, map, Xb, uint64_t(2 * TC_BK), lines, uint64_t(2 * TC_BK), 2 * TC_BK, TC_BN, err, true);
 }
 
@@ -1099,7 +1332,7 @@ inline bool tc_bind_corpus(TcState* st, TcCorpus* tc, const float* X, int64_t n_
   if (!tc_encode_2d(st, &tc->map_x, X, uint64_t(pitch), uint64_t(n_rows), uint64_t(pitch), TC_BK, TC_BN, err)) return false;
   tc->ok = true;
   if (Xb != nullptr) {
-    if (!tc_bind_shadow(st, &tc->map_xb, Xb, n_rows, blocks_per_tile, err)) return false;
+    if (!tc_bind_shadow(st, &tc->map_xb, &tc->map_xb_h, Xb, n_rows, blocks_per_tile, err)) return false;
     tc->ok_b = true;
   }
   return true;
@@ -1127,6 +1360,8 @@ inline bool tc_supported(const TcState* st, const TcCorpus* tc, int64_t n_rows, 
 struct TcPlan {
   int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks, n_kb_data, nk_last, aug_line0, aug_col;
   int qt_major;
+  int rq;        // 1: resident-query kernel (units = query pairs x slices of 128-row tiles, one list per unit and query)
+  int n_qp;      // query pairs
   int kp_list;   // candidates each (query, list) keeps at a selection (<= kp)
   size_t off_qp, off_qb, off_tau, off_flags, off_wcnt, off_wbuf, total;
 };
@@ -1154,21 +1389,28 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     pl.aug_col = g.aug_col;
   }
   if (std::getenv("FENIX_TC_FULLK")) pl.nk_last = TC_BK / TC_UMMA_K;   // tuning knob: multiply the zero padding too
+  // narrow rows and at least two query tiles: the resident-query kernel (operand traffic, not the tensor pipe, binds
+  // the streaming kernel there); its tiles are 128 corpus rows, its units pair two query tiles
+  pl.rq = (s.kind == 1 && pl.n_kblocks <= RQ_MAX_KB && pl.n_qt >= 2 && s.epi != 1 && s.dbg == nullptr &&
+           !std::getenv("FENIX_TC_NO_RQ")) ? 1 : 0;
+  pl.n_qp = (pl.n_qt + 1) / 2;
+  const int n_tiles_u = pl.rq ? int((s.n_rows + RQ_BN - 1) / RQ_BN) : pl.n_tiles;   // tiles in the kernel's own unit
+  const int n_qu = pl.rq ? pl.n_qp : pl.n_qt;                                       // query blocks per slice
   // Slices: units = n_qt * n_slices (query-tile major, so all slices of a query tile run at the same time and
   // share thresholds) are dealt round-robin to min(units, #SM) persistent CTAs.
   // Maximise SM utilisation units / (G * ceil(units / G)); few slices are preferred (longer units give
   // tighter thresholds and fewer candidate lists), and every unit should span enough tiles for its
   // threshold to become selective.
   const int sms = st->sm_count;
-  const int min_tiles = std::max(4, (8 * pl.kp + TC_BN - 1) / TC_BN);
-  const int s_cap = std::max(1, (TC_MAX_WAVES * sms) / pl.n_qt);
-  const int s_max = std::max(1, std::min(pl.n_tiles / min_tiles, s_cap));
+  const int min_tiles = std::max(4, (8 * pl.kp + TC_BN - 1) / TC_BN) * (pl.rq ? 2 : 1);
+  const int s_cap = std::max(1, (TC_MAX_WAVES * sms) / n_qu);
+  const int s_max = std::max(1, std::min(n_tiles_u / min_tiles, s_cap));
   double best = -1.0; int best_s = 1;
   for (int sl = 1; sl <= s_max; ++sl) {
-    int tps = (pl.n_tiles + sl - 1) / sl;
-    int eff_s = (pl.n_tiles + tps - 1) / tps;
+    int tps = (n_tiles_u + sl - 1) / sl;
+    int eff_s = (n_tiles_u + tps - 1) / tps;
     if (eff_s != sl) continue;
-    long units = long(sl) * pl.n_qt;
+    long units = long(sl) * n_qu;
     long g = std::min<long>(units, sms);
     double eff = double(units) / double(sms * ((units + g - 1) / g));
     if (eff > best + 0.02) { best = eff; best_s = sl; }
@@ -1176,21 +1418,22 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   if (const char* e = std::getenv("FENIX_TC_SLICES")) {   // tuning knob: force the slice count
     int forced = std::atoi(e);
     if (forced >= 1 && forced <= s_max) {
-      int tps = (pl.n_tiles + forced - 1) / forced;
-      best_s = (pl.n_tiles + tps - 1) / tps;
+      int tps = (n_tiles_u + forced - 1) / forced;
+      best_s = (n_tiles_u + tps - 1) / tps;
     }
   }
   pl.qt_major = 0;   // measured on C3: slice-major 94 ms vs query-tile-major 112 ms (profiles/r01_c3_sweep.txt)
   if (const char* e = std::getenv("FENIX_TC_ORDER")) pl.qt_major = std::atoi(e) != 0;
   pl.n_slices = best_s;
-  pl.tiles_per_slice = (pl.n_tiles + best_s - 1) / best_s;
-  pl.units = pl.n_slices * pl.n_qt;
+  pl.tiles_per_slice = (n_tiles_u + best_s - 1) / best_s;
+  pl.units = pl.n_slices * n_qu;
+  if (pl.rq) pl.qt_major = 0;
   // Each query's candidates are spread over L = TC_SPLIT * n_slices lists. A list does not need to keep K'
   // entries: the global top-k lands ~k/L per list, so keeping 2k/L + 16 (>= 32) per list gives much tighter
   // local thresholds (fewer appends and selections). If a query's neighbours are concentrated in few lists
   // the certificate fails and the refinement pass settles it.
   {
-    const int lists = TC_SPLIT * pl.n_slices;
+    const int lists = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices;
     int m = std::max(32, (2 * s.k + lists - 1) / lists + 16);
     m = (m + 31) & ~31;
     pl.kp_list = s.tau_fixed ? pl.kp : std::min(pl.kp, m);
@@ -1200,7 +1443,7 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.grid = int(std::min<long>(pl.units, sms));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-  const size_t q_rows_p = size_t(pl.n_qt) * TC_BM;   // queries are stored in whole tiles
+  const size_t q_rows_p = size_t(pl.n_qp) * 2 * TC_BM;   // queries are stored in whole tile pairs
   pl.off_qp = take(q_rows_p * s.pitch * 4);
   pl.off_qb = take(s.kind == 1 ? q_rows_p * s.pitch_b * 2 : 0);
   pl.off_tau = take(size_t(s.n_q) * 4);
@@ -1239,14 +1482,15 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   __nv_bfloat16* qb = s.kind == 1 ? reinterpret_cast<__nv_bfloat16*>(base + pl.off_qb) : nullptr;
   CUtensorMap map_q;
   if (s.kind == 0) {
-    if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(pl.n_qt) * TC_BM, uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
+    if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(pl.n_qp) * 2 * TC_BM, uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
   } else {
     if (s.shadow == 1 ? !tc->ok_n : !tc->ok_b) { *err = "bf16 filter requested but the shard has no bf16 shadow"; return false; }
-    if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(pl.n_qt) * TC_BM, uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
+    if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(pl.n_qp) * 2 * TC_BM, uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
   }
 
-  const int prep_blocks = int(std::min<int64_t>((int64_t(pl.n_qt) * TC_BM * s.pitch + 255) / 256, 4 * 148));
-  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed,
+  const int n_rows_p = pl.n_qp * 2 * TC_BM;
+  const int prep_blocks = int(std::min<int64_t>((int64_t(n_rows_p) * s.pitch + 255) / 256, 4 * 148));
+  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, n_rows_p, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed,
                                                                   (!s.tau_fixed && std::getenv("FENIX_TC_WARM")) ? 1 : 0,
                                                                   (s.kind == 1 && s.aug) ? pl.aug_col : 0);
 
@@ -1254,6 +1498,9 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   p.n_q = s.n_q; p.n_qt = pl.n_qt; p.n_rows = s.n_rows; p.n_tiles = pl.n_tiles; p.n_slices = pl.n_slices;
   p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.n_kb_data = pl.n_kb_data; p.nk_last = pl.nk_last;
   p.aug_line0 = pl.aug_line0;
+  p.xb = s.kind == 1 ? static_cast<const unsigned char*>(s.shadow == 1 ? s.Xn : s.Xb) : nullptr;
+  p.pf_tiles = 0;   // off: measured neutral where operands come from L2 (C2, C4) and 1.9x slower where HBM binds (C5)
+  if (const char* e = std::getenv("FENIX_TC_PF")) p.pf_tiles = p.xb ? std::max(0, std::atoi(e)) : 0;
   p.kp = pl.kp_list; p.cap = pl.cap;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
   p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
@@ -1264,6 +1511,14 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
     kernel<<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, map_b, p);
   };
   const bool dbg = s.dbg != nullptr;
+  if (pl.rq) {
+    const CUtensorMap& map_h = s.shadow == 1 ? tc->map_xn_h : tc->map_xb_h;
+    p.rq_stages = rq_stages(pl.n_kblocks);
+    if (const char* e = std::getenv("FENIX_RQ_STAGES")) { int f = std::atoi(e); if (f >= 2 && f <= p.rq_stages) p.rq_stages = f; }
+    const uint32_t rq_smem = rq_smem_bytes(pl.n_kblocks);
+    if (epi == 0) knn_rq_filter_kernel<0><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+    else knn_rq_filter_kernel<2><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+  } else {
 #define FX_TC_CASE(E, K, MAP)                                                       \
   if (epi == E && s.kind == K) {                                                    \
     if (dbg) {                                                                      \
@@ -1277,17 +1532,18 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   const CUtensorMap& map_s = s.shadow == 1 ? tc->map_xn : tc->map_xb;
   FX_TC_CASE(0, 1, map_s) FX_TC_CASE(1, 1, map_s) FX_TC_CASE(2, 1, map_s)
 #undef FX_TC_CASE
+  }
   if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
 
   FinishParams f{};
   f.X = s.X; f.pitch = s.pitch; f.dim = s.dim; f.row_base = s.row_base; f.Qp = qp; f.n_q = s.n_q; f.n_qt = pl.n_qt;
   f.n_slices = pl.n_slices; f.cap = pl.cap; f.metric = s.metric; f.k = s.k; f.kp = pl.kp;
   int sort2 = 2; while (sort2 < pl.kp) sort2 <<= 1;
-  f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.qt_major = pl.qt_major; f.flags = flags; f.certify = s.certify ? 1 : 0;
+  f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.qt_major = pl.qt_major; f.rq = pl.rq; f.n_qp = pl.n_qp; f.flags = flags; f.certify = s.certify ? 1 : 0;
   f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim, s.kind); f.c_add = tc_c_add(s.dim, s.kind == 1 && s.aug); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
   const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + size_t(FIN_POOL) * 8 + 16;
   // many short lists per query (small batches split over all SMs): more warps sweep them in parallel
-  const int fin_threads = TC_SPLIT * pl.n_slices > 32 ? 1024 : 256;
+  const int fin_threads = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices > 32 ? 1024 : 256;
   knn_tc_finish_kernel<<<s.n_q, fin_threads, fin_smem, s.stream>>>(f);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tensor-core path launch failed: ") + cudaGetErrorString(e); return false; }
