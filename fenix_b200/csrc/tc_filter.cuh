@@ -47,7 +47,7 @@ constexpr int TC_SPLIT = FENIX_TC_SPLIT;
 #define FENIX_TC_BACKOFF 1                 // 1: producer / MMA polling loops sleep between polls
 #endif
 #ifndef FENIX_EPI_UNROLL
-#define FENIX_EPI_UNROLL 1                 // unroll factor of the epilogue's chunk-pair loop (1 = rolled)
+#define FENIX_EPI_UNROLL 2                 // unroll factor of the epilogue's chunk-pair loop (1 = rolled, 2 = all four chunks)
 #endif
 constexpr int TC_EPI_UNROLL = FENIX_EPI_UNROLL;
 #ifndef FENIX_TC_PIPE
@@ -259,6 +259,10 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Same wait, with the loaded registers as in/out operands: the compiler cannot move a use of v[] above it.
 __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
@@ -387,21 +391,25 @@ __device__ __noinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp
 // query: score, compare with the running threshold, append survivors at wp, hand the accumulator back (arrive on
 // release_bar, one arrival per warp). ncols = valid columns (<= 0: nothing to look at, only the release).
 //
-// One chunk = 32 columns (one tcgen05.ld.x32), straight-line code per chunk: per-row terms (METRIC 0 add / 1 multiply,
-// read from nrm in shared memory; METRIC 2: the score is the accumulator), eight quad maxima, one test. With two
-// epilogue warps per SM sub-partition nothing hides a branch, so there is one per 32 columns. Appends are inherently
-// frequent at large k / small N (a query admits ~K' ln(N/K') rows over the scan, and 32 queries share a warp), so
-// the hit path must be cheap: only lanes that hold a hit enter it (divergent branch, no warp vote), and they touch
-// only the quads whose maximum passes.
+// The hot code must be SMALL: with two epilogue warps per SM sub-partition nothing hides an instruction-cache miss
+// or a branch (a build whose epilogue grew from 24 KB to 28 KB of SASS ran 28 % slower). So:
+//  * scan: one chunk = 32 columns (one tcgen05.ld.x32, the next chunk's load already in flight), per-row terms
+//    (METRIC 0 add / 1 multiply, from nrm in shared memory; METRIC 2: the score is the accumulator), eight quad
+//    maxima, one warp vote. About 30 instructions per chunk, no per-element work.
+//  * hits: appends are inherently frequent at large k / small N (a query admits ~K' ln(N/K') rows over the scan and
+//    32 queries share a warp), yet a chunk rarely holds more than one or two. The warp ORs the lanes' 8-bit masks of
+//    passing quads and, per quad in the union, re-reads those four columns from TMEM (tcgen05.ld.x4 takes a runtime
+//    column address, registers cannot be indexed) and appends what passes: one compact loop instead of 32 unrolled
+//    append sites per chunk. Columns past the shard's last row are rejected here, so the scan needs no tail handling.
 template <int METRIC, bool DBG>
-__device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float* nrm, int col0, float tau, uint2*& wp,
-                                         uint64_t* release_bar, uint32_t lane, float* dbg_row) {
+__device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float* nrm, int col0, float tau, uint2* buf,
+                                         uint32_t& wn, uint64_t* release_bar, uint32_t lane, float* dbg_row) {
   auto release = [&]() {
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(release_bar);
   };
-  auto process = [&](uint32_t (&v)[TC_CW], int c, bool ragged) {
+  auto scan = [&](uint32_t (&v)[TC_CW], int c) {
     if (METRIC != 2) {
 #pragma unroll
       for (int j = 0; j < TC_CW; j += 4) {
@@ -420,80 +428,87 @@ __device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float*
         for (int j = 0; j < TC_CW; ++j) dbg_row[c + j] = __uint_as_float(v[j]);
       }
     }
-    if (ragged) {
-      // the last tile of the corpus: columns past the last row can never pass
-#pragma unroll
-      for (int j = 0; j < TC_CW; ++j) if (c + j >= ncols) v[j] = 0xff800000u;   // -inf
-    }
     float qm[TC_CW / 4];
 #pragma unroll
     for (int g = 0; g < TC_CW / 4; ++g) qm[g] = max4(v, g);
     float m = qm[0];
 #pragma unroll
     for (int g = 1; g < TC_CW / 4; ++g) m = fmaxf(m, qm[g]);
-    if (m > tau) {
-      const uint32_t col_base = uint32_t(col0 + c);
+    if (__any_sync(0xffffffffu, m > tau)) {
+      uint32_t mine = 0;
 #pragma unroll
-      for (int g = 0; g < TC_CW / 4; ++g) {
-        if (qm[g] > tau) {
+      for (int g = 0; g < TC_CW / 4; ++g) mine |= (qm[g] > tau) ? (1u << g) : 0u;
+      uint32_t quads = __reduce_or_sync(0xffffffffu, mine);
+      while (quads) {                       // warp-uniform
+        const int g = __ffs(quads) - 1;
+        quads &= quads - 1;
+        const int cq = c + 4 * g;           // first column of the quad within these 128 columns
+        uint32_t w[4];
+        tmem_ld_32x32b_x4(t_acc + uint32_t(cq), w);
+        tmem_ld_wait();
+        float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (METRIC != 2) n4 = *reinterpret_cast<const float4*>(nrm + cq);
+        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
-          for (int j = 4 * g; j < 4 * g + 4; ++j) {
-            if (__uint_as_float(v[j]) > tau) { *wp = make_uint2(v[j], col_base + uint32_t(j)); ++wp; }
-          }
+        for (int j = 0; j < 4; ++j) {
+          float sc = __uint_as_float(w[j]);
+          if (METRIC == 0) sc += nn[j];
+          if (METRIC == 1) sc *= nn[j];
+          if (sc > tau && cq + j < ncols) { buf[wn] = make_uint2(__float_as_uint(sc), uint32_t(col0 + cq + j)); ++wn; }
         }
       }
     }
   };
-  if (ncols >= TC_HALF_COLS) {
-    // full tile: two register sets, the TMEM load of chunk i+1 is in flight while chunk i is processed
+  if (ncols > 0) {
+    // two register sets: the TMEM load of chunk i+1 is in flight while chunk i is scanned. The hit loop re-reads
+    // the accumulator, so it goes back to the MMA warp only after the last chunk.
     static_assert(TC_HALF_COLS % (2 * TC_CW) == 0, "chunk pairs");
     uint32_t va[TC_CW], vb[TC_CW];
     tmem_ld_32x32b_x32(t_acc, va);
-    // NOT unrolled: the chunk body (with its 32 append sites) is large, and the kernel's hot code must stay inside
-    // the instruction cache (measured: a build whose epilogue grew from ~24 KB to ~28 KB of SASS ran 28 % slower)
 #pragma unroll TC_EPI_UNROLL
     for (int c = 0; c < TC_HALF_COLS; c += 2 * TC_CW) {
       tmem_ld_wait_dep(va);
       tmem_ld_32x32b_x32(t_acc + uint32_t(c + TC_CW), vb);
-      process(va, c, false);
+      scan(va, c);
       tmem_ld_wait_dep(vb);
       if (c + 2 * TC_CW < TC_HALF_COLS) tmem_ld_32x32b_x32(t_acc + uint32_t(c + 2 * TC_CW), va);
-      else if (METRIC == 2) release();   // the accumulator has been read completely: hand it back before the last chunk
-      process(vb, c + TC_CW, false);
+      scan(vb, c + TC_CW);
     }
-    if (METRIC != 2) release();          // variants with per-row terms release their norm buffer with it
-  } else {
-#pragma unroll 1
-    for (int c = 0; c < ncols; c += TC_CW) {
-      uint32_t va[TC_CW];
-      tmem_ld_32x32b_x32(t_acc + uint32_t(c), va);
-      tmem_ld_wait_dep(va);
-      process(va, c, true);
-    }
-    release();
   }
+  release();
 }
 
-// Tighten thresholds after a tile: a lane whose buffer could overflow during the next tile, or that holds >= K'
-// candidates but no threshold yet, gets a warp-cooperative selection; the new threshold is shared through tau_g.
-__device__ __forceinline__ void epi_tighten(const TcParams& p, bool active, int q, uint2* buf, uint2*& wp, float& tau, uint32_t lane) {
-  __syncwarp();
-  int cnt = int(wp - buf);
-  if (p.fixed && active && cnt > p.cap - TC_HALF_COLS) { p.flags[q] = 1; tau = INFINITY; }   // more survivors than the buffer holds
-  bool need = active && !p.fixed && ((cnt > p.cap - TC_HALF_COLS) || (tau == -INFINITY && cnt >= p.kp));
-  uint32_t need_mask = __ballot_sync(0xffffffffu, need);
+// Tighten thresholds after a tile. The common case costs one compare and one vote: every lane keeps the entry count
+// at which it needs attention (wn_trig): K' while it has no threshold yet, cap - 127 (the next tile could overflow
+// the buffer) afterwards. A lane that got there receives a warp-cooperative selection; its new threshold is shared
+// through tau_g. In the refinement pass (preset thresholds) an overflowing lane flags its query instead.
+__device__ __forceinline__ uint32_t epi_trigger(const TcParams& p, bool active, float tau) {
+  if (!active) return 0xffffffffu;
+  return (!p.fixed && tau == -INFINITY) ? uint32_t(p.kp) : uint32_t(p.cap - TC_HALF_COLS + 1);
+}
+__device__ __forceinline__ void epi_tighten(const TcParams& p, bool active, int q, uint2* buf, uint32_t& wn, uint32_t& wn_trig,
+                                            float& tau, uint32_t lane) {
+  if (!__any_sync(0xffffffffu, wn >= wn_trig)) return;
+  wn_trig = epi_trigger(p, active, tau);   // a threshold may have arrived through tau_g since the trigger was set
+  const bool hit = active && wn >= wn_trig;
+  if (p.fixed) {
+    if (hit) { p.flags[q] = 1; tau = INFINITY; wn_trig = 0xffffffffu; }   // more survivors than the buffer holds
+    return;
+  }
+  uint32_t need_mask = __ballot_sync(0xffffffffu, hit);
   while (need_mask) {
     const int src = __ffs(need_mask) - 1;
     need_mask &= need_mask - 1;
     uint2* b = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
-    const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+    const int c_src = __shfl_sync(0xffffffffu, int(wn), src);
     int new_cnt;
     uint32_t v_ord = (p.cap == 1024) ? warp_select_compact<32>(b, c_src, p.kp, new_cnt)
                                      : warp_select_compact<16>(b, c_src, p.kp, new_cnt);
     if (int(lane) == src) {
-      wp = buf + new_cnt;
+      wn = uint32_t(new_cnt);
       tau = fmaxf(tau, ord2f(v_ord));
       atomicMax(p.tau_g + q, v_ord);
+      wn_trig = epi_trigger(p, active, tau);
     }
   }
 }
@@ -540,6 +555,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_units = p.n_slices * p.n_qt;
+  const int n_rows_i = int(p.n_rows);   // < 2^31 (tc_supported)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -583,8 +599,14 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps descriptors and addresses in uniform registers;
+    // under `if (lane == 0)` the compiler wraps every MMA in a register-broadcast loop), one elected lane issues.
+    {
       constexpr uint32_t idesc = KIND == 0 ? make_idesc_tf32(TC_BM, TC_BN) : make_idesc_bf16(TC_BM, TC_BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t desc0 = make_smem_desc(0);
+      const uint32_t tiles_lo = smem_u32(tiles) >> 4;
+      const int n_kb = p.n_kblocks, n_kb_data = p.n_kb_data, nk_last = p.nk_last;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -592,26 +614,32 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
         for (int t = t0; t < t1; ++t) {
           mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 32);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + uint32_t(acc * TC_BN);
-          for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          const uint32_t d_tmem = tmem_u + uint32_t(acc * TC_BN);
+          for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(tiles + stage * TC_STAGE_BYTES);
-            const uint64_t a_desc = make_smem_desc(a_addr);
-            const uint64_t b_desc = make_smem_desc(a_addr + TC_A_BYTES);
-            const int nk = kb < p.n_kb_data - 1 ? TC_BK / TC_UMMA_K : (kb == p.n_kb_data - 1 ? p.nk_last : 1);
-#pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-              if (k >= nk) break;   // the last k-block may hold fewer than 4 x 32 B of data
+            const uint64_t a_desc = desc0 | uint64_t(tiles_lo + uint32_t(stage) * (TC_STAGE_BYTES >> 4));
+            const uint64_t b_desc = a_desc + (TC_A_BYTES >> 4);
+            const int nk = kb < n_kb_data - 1 ? TC_BK / TC_UMMA_K : (kb == n_kb_data - 1 ? nk_last : 1);
+            if (elect_one()) {
               // advance 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-              if (KIND == 0) umma_tf32(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              if (KIND == 0) {
+                umma_tf32(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                if (nk > 1) umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                if (nk > 2) umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                if (nk > 3) umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              } else {
+                umma_bf16(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                if (nk > 1) umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                if (nk > 2) umma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                if (nk > 3) umma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              }
+              umma_commit(&empty_bar[stage]);                       // frees the smem stage once these MMAs retire
+              if (kb == n_kb - 1) umma_commit(&tmem_full[acc]);     // accumulator ready for the epilogue
             }
-            umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+            __syncwarp();
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[acc]);       // accumulator ready for the epilogue
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -633,10 +661,12 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       // batch is spread over all four lane groups, i.e. over all epilogue warps and SM sub-partitions
       const int q = qt * TC_BM + int(lane) * 4 + lane_grp;
       const bool active = q < p.n_q;
+      const bool any_active = __any_sync(0xffffffffu, active);
       uint2* buf = p.wbuf + (size_t(u) * TC_SLOTS + slot) * p.cap;
-      uint2* wp = buf;   // append cursor: the buffer holds wp - buf entries
+      uint32_t wn = 0;   // entries in the buffer
       float tau = active ? -INFINITY : INFINITY;   // lanes past the last query never admit anything
       if (p.fixed && active) tau = ord2f(p.tau_g[q]);
+      uint32_t wn_trig = epi_trigger(p, active, tau);
       // the shared threshold is re-read once per tile; the load is issued a tile ahead so its L2 latency
       // (hundreds of cycles) never sits on the critical path of the first compare
       const bool poll = active && !p.fixed;
@@ -651,18 +681,18 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         if (METRIC != 2) mbar_wait(&norm_full[acc], acc_phase);
         tc_fence_after();
         const int col0 = t * TC_BN + half * TC_HALF_COLS;                  // global row of column 0 of this half
-        const int ncols = int(min(int64_t(TC_HALF_COLS), p.n_rows - int64_t(col0)));  // valid columns (<=0: none)
+        const int ncols = min(TC_HALF_COLS, n_rows_i - col0);                 // valid columns (<=0: none)
         const float* nrm = norm_smem + acc * TC_BN + half * TC_HALF_COLS;
         float* dbg_row = nullptr;
         if (DBG) { if (u == 0 && t == t0) dbg_row = p.dbg + (int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS; }
-        epi_tile<METRIC, DBG>(t_lane + uint32_t(acc * TC_BN), __any_sync(0xffffffffu, active) ? ncols : 0, nrm, col0, tau, wp,
+        epi_tile<METRIC, DBG>(t_lane + uint32_t(acc * TC_BN), any_active ? ncols : 0, nrm, col0, tau, buf, wn,
                               &tmem_empty[acc], lane, dbg_row);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-        epi_tighten(p, active, q, buf, wp, tau, lane);
+        epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
       }
 
       // end of unit: the finish kernel reads the buffer in place
-      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wp - buf) : 0;
+      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wn) : 0;
     }
   }
 
@@ -684,7 +714,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // tile), so operand bytes per flop drop 3-4.5x:
 //   smem   A: 2 query tiles x n_kb x 16 KB (loaded once per unit)      B: ring of RQ_STAGES x 16 KB (128 rows x 128 B)
 //   TMEM   4 accumulators of 128 columns: (stage 0/1) x (query tile 0/1)
-//   warps  0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue of query tile 0, 8-11 of query tile 1;
+//   warps  0 TMA producer, 1 and 3 MMA issuers (one per query tile), 2 TMEM allocator, 4-7 epilogue of query tile 0,
+//          8-11 of query tile 1;
 //          every epilogue warp owns 32 queries and scans all 128 columns of its accumulator.
 // Units: (query pair) x (corpus slice of 128-row tiles), slice-major like the streaming kernel; candidate lists:
 // one per (unit, query).
@@ -716,9 +747,9 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* full_bar = bars;                      // [RQ_MAX_STAGES] TMA -> MMA
   uint64_t* empty_bar = full_bar + RQ_MAX_STAGES; // [RQ_MAX_STAGES] MMA -> TMA
   uint64_t* a_full = empty_bar + RQ_MAX_STAGES;   // [1]  query tiles of the unit have landed
-  uint64_t* a_empty = a_full + 1;                 // [1]  the unit's last MMA has retired
-  uint64_t* tmem_full = a_empty + 1;              // [2]  per stage (both query tiles)
-  uint64_t* tmem_empty = tmem_full + 2;           // [2][2] per (stage, query tile), 4 warps each
+  uint64_t* a_empty = a_full + 1;                 // [1]  the unit's last MMAs (both issuers) have retired
+  uint64_t* tmem_full = a_empty + 1;              // [2][2] per (stage, query tile)
+  uint64_t* tmem_empty = tmem_full + 4;           // [2][2] per (stage, query tile), 4 warps each
   uint64_t* norm_full = tmem_empty + 4;           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
 
@@ -727,10 +758,10 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_q);
     prefetch_tmap(&map_x);
-    for (int i = 0; i < n_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&norm_full[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&tmem_empty[i], 4);
+    for (int i = 0; i < n_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 2); }   // two MMA issuers free a stage
+    mbar_init(a_full, 1); mbar_init(a_empty, 2);
+    for (int i = 0; i < 2; ++i) mbar_init(&norm_full[i], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -742,6 +773,7 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int n_qp = (p.n_qt + 1) >> 1;
   const int n_units = p.n_slices * n_qp;
   const int n_t128 = int((p.n_rows + RQ_BN - 1) / RQ_BN);
+  const int n_rows_i = int(p.n_rows);   // < 2^31 (tc_supported)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -785,10 +817,21 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers: warp 1 feeds query tile 0, warp 3 query tile 1 =====================
+    // One thread issuing every tcgen05.mma of the CTA was the bottleneck of this kernel (about 18 scalar instructions
+    // per MMA, 80 % busy): the two query tiles are independent GEMMs over the same corpus block, so each gets its
+    // own issuer and accumulator barriers. The whole warp runs the loop (warp-uniform control flow keeps descriptors
+    // and addresses in uniform registers; under `if (lane == 0)` the compiler wraps every MMA in a broadcast loop);
+    // one elected lane issues.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, RQ_BN);
+      const int qt = warp >> 1;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t desc0 = make_smem_desc(0);
+      const uint32_t a_lo = (smem_u32(a_tiles) + uint32_t(qt * p.n_kblocks) * RQ_BLOCK_BYTES) >> 4;   // k-block kb: + kb * 1024
+      const uint32_t b_lo = smem_u32(b_ring) >> 4;                                                    // stage s:    + s * 1024
+      const int n_kb = p.n_kblocks, n_kb_data = p.n_kb_data, nk_last = p.nk_last;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t a_phase = 0;
@@ -797,33 +840,30 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int t0 = slice * p.tiles_per_slice, t1 = min(n_t128, t0 + p.tiles_per_slice);
         mbar_wait(a_full, a_phase);
         a_phase ^= 1;
-        tc_fence_after();
         for (int t = t0; t < t1; ++t) {
-          mbar_wait_backoff(&tmem_empty[acc * 2 + 0], acc_phase ^ 1, 32);
-          mbar_wait_backoff(&tmem_empty[acc * 2 + 1], acc_phase ^ 1, 32);
-          tc_fence_after();
-          for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          mbar_wait_backoff(&tmem_empty[acc * 2 + qt], acc_phase ^ 1, 32);
+          const uint32_t d_tmem = tmem_u + uint32_t((acc * 2 + qt) * RQ_BN);
+          for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint64_t b_desc = make_smem_desc(smem_u32(b_ring + stage * RQ_BLOCK_BYTES));
-            const int nk = kb < p.n_kb_data - 1 ? 4 : (kb == p.n_kb_data - 1 ? p.nk_last : 1);
-#pragma unroll
-            for (int qt = 0; qt < 2; ++qt) {
-              const uint32_t d_tmem = tmem_base + uint32_t((acc * 2 + qt) * RQ_BN);
-              const uint64_t a_desc = make_smem_desc(smem_u32(a_tiles + (qt * p.n_kblocks + kb) * RQ_BLOCK_BYTES));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k >= nk) break;
-                umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-              }
+            const uint64_t a_desc = desc0 | uint64_t(a_lo + uint32_t(kb) * (RQ_BLOCK_BYTES >> 4));
+            const uint64_t b_desc = desc0 | uint64_t(b_lo + uint32_t(stage) * (RQ_BLOCK_BYTES >> 4));
+            const int nk = kb < n_kb_data - 1 ? 4 : (kb == n_kb_data - 1 ? nk_last : 1);
+            if (elect_one()) {
+              umma_bf16(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+              if (nk > 1) umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+              if (nk > 2) umma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+              if (nk > 3) umma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              umma_commit(&empty_bar[stage]);
+              if (kb == n_kb - 1) umma_commit(&tmem_full[acc * 2 + qt]);
             }
-            umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[acc]);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(a_empty);   // the resident query tiles may be replaced once everything issued so far has retired
+        if (elect_one()) umma_commit(a_empty);   // the resident query tiles may be replaced once everything issued so far has retired
+        __syncwarp();
       }
     }
   } else if (warp >= TC_EPI_FIRST_WARP) {
@@ -840,9 +880,11 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const int q = (qp * 2 + qt_l) * TC_BM + int(lane) * 4 + lane_grp;
       const bool active = q < p.n_q;
       uint2* buf = p.wbuf + (size_t(u) * TC_SLOTS + slot) * p.cap;
-      uint2* wp = buf;
+      uint32_t wn = 0;
       float tau = active ? -INFINITY : INFINITY;
       if (p.fixed && active) tau = ord2f(p.tau_g[q]);
+      uint32_t wn_trig = epi_trigger(p, active, tau);
+      const bool any_active = __any_sync(0xffffffffu, active);
       const bool poll = active && !p.fixed;
       uint32_t tg_next = poll ? ld_relaxed_u32(p.tau_g + q) : ORD_NEG_INF;
       for (int t = t0; t < t1; ++t) {
@@ -850,17 +892,17 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tau = fmaxf(tau, ord2f(tg_next));
           tg_next = ld_relaxed_u32(p.tau_g + q);
         }
-        mbar_wait(&tmem_full[acc], acc_phase);
+        mbar_wait(&tmem_full[acc * 2 + qt_l], acc_phase);
         if (METRIC != 2) mbar_wait(&norm_full[acc], acc_phase);
         tc_fence_after();
         const int col0 = t * RQ_BN;
-        const int ncols = int(min(int64_t(RQ_BN), p.n_rows - int64_t(col0)));
-        epi_tile<METRIC, false>(t_lane + uint32_t(acc * 2 * RQ_BN), __any_sync(0xffffffffu, active) ? ncols : 0,
-                                norm_smem + acc * RQ_BN, col0, tau, wp, &tmem_empty[acc * 2 + qt_l], lane, nullptr);
+        const int ncols = min(RQ_BN, n_rows_i - col0);
+        epi_tile<METRIC, false>(t_lane + uint32_t(acc * 2 * RQ_BN), any_active ? ncols : 0,
+                                norm_smem + acc * RQ_BN, col0, tau, buf, wn, &tmem_empty[acc * 2 + qt_l], lane, nullptr);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        epi_tighten(p, active, q, buf, wp, tau, lane);
+        epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
       }
-      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wp - buf) : 0;
+      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wn) : 0;
     }
   }
 
