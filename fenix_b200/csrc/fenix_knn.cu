@@ -559,9 +559,14 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
       FX_CUDA(cudaStreamSynchronize(ctx->stream));
       std::vector<int> bad;
       for (int64_t i = 0; i < n_q; ++i) if (h_flags[i]) bad.push_back(int(i));
-      if (!bad.empty() && !std::getenv("FENIX_NO_REFINE")) {
-        // tier 1: second filter pass for the flagged queries only, with the admission threshold preset from
-        // their k-th distance minus the error bound; every survivor is reranked, so the result is exact
+      // Flagged queries are settled by up to two more filter passes over their own (small) batch:
+      //  tier 0 (only when the main pass took its thresholds from the sample prepass): the adaptive search without
+      //         prepass - a sample threshold that came out too tight leaves a query with fewer than k candidates,
+      //         and then there is no k-th distance to refine from;
+      //  tier 1: preset-threshold refinement: the admission threshold is the query's k-th distance minus the error
+      //         bound and every survivor is reranked, so the result is exact.
+      const bool had_prepass = fx::tc_uses_prepass(&ctx->tc, s);
+      for (int tier = had_prepass ? 0 : 1; tier <= 1 && !bad.empty() && !std::getenv("FENIX_NO_REFINE"); ++tier) {
         const int n_f = int(bad.size());
         FX_TRY(ctx->d_qlist.ensure(size_t(n_f) * sizeof(int)));
         FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), size_t(n_f) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -575,19 +580,23 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
         uint32_t* tau_fixed = reinterpret_cast<uint32_t*>(rb + o_tau);
         int64_t* rows2 = reinterpret_cast<int64_t*>(rb + o_rows);
         float* dist2 = reinterpret_cast<float*>(rb + o_dist);
+        // gathers the flagged queries (and derives the preset thresholds tier 1 uses)
         fx::refine_prep_kernel<<<n_f, 128, 0, ctx->stream>>>(d_q, static_cast<const int*>(ctx->d_qlist.p), c->dim, metric, k,
                                                             d_out_dist, c->max_norm, fx::tc_c_err(c->dim, s.kind),
                                                             fx::tc_c_add(c->dim, s.kind == 1 && s.aug), q_r, tau_fixed);
         FX_CUDA(cudaGetLastError());
         fx::TcSearch s2 = s;
-        s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.tau_fixed = tau_fixed; s2.certify = true;
+        s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.certify = true;
+        s2.tau_fixed = tier == 1 ? tau_fixed : nullptr; s2.no_prepass = 1;
         s2.ev_k0 = nullptr; s2.ev_k1 = nullptr;   // keep the timing of the main pass
         FX_TRY(ctx->d_tc.ensure(fx::tc_scratch_bytes(&ctx->tc, s2)));
         int launched2 = 0;
         if (!fx::tc_search(&ctx->tc, &c->tc, s2, ctx->d_tc.p, &launched2, &err)) return fail(FX_ECUDA, "fx_search (refine): %s", err.c_str());
         const int* d_flags2 = fx::tc_flags(&ctx->tc, s2, ctx->d_tc.p);
+        // tier 0 results replace the first pass's in any case (they hold k real neighbours for tier 1 to refine from);
+        // tier 1 results only where their certificate holds
         fx::refine_scatter_kernel<<<std::min((n_f * k + 255) / 256, 1024), 256, 0, ctx->stream>>>(
-            static_cast<const int*>(ctx->d_qlist.p), d_flags2, n_f, k, rows2, dist2, d_out_rows, d_out_dist);
+            static_cast<const int*>(ctx->d_qlist.p), tier == 1 ? d_flags2 : nullptr, n_f, k, rows2, dist2, d_out_rows, d_out_dist);
         FX_CUDA(cudaGetLastError());
         ctx->launches += launched2 + 2; c->stats.kernel_launches += launched2 + 2;
         FX_CUDA(cudaMemcpyAsync(h_flags, d_flags2, size_t(n_f) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -598,7 +607,7 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
           cudaMemcpy(d2.data(), dist2, size_t(n_f) * k * 4, cudaMemcpyDeviceToHost);
           cudaMemcpy(r2.data(), rows2, size_t(n_f) * k * 8, cudaMemcpyDeviceToHost);
           for (int i = 0; i < std::min(n_f, 4); ++i)
-            fprintf(stderr, "[refine] q=%d tau=%g flag=%d rows %lld %lld .. %lld dist %g .. %g\n", bad[i], fx::ord2f(tf[i]), h_flags[i],
+            fprintf(stderr, "[refine tier %d] q=%d tau=%g flag=%d rows %lld %lld .. %lld dist %g .. %g\n", tier, bad[i], fx::ord2f(tf[i]), h_flags[i],
                     (long long)r2[size_t(i) * k], (long long)r2[size_t(i) * k + 1], (long long)r2[size_t(i) * k + k - 1],
                     d2[size_t(i) * k], d2[size_t(i) * k + k - 1]);
         }

@@ -113,6 +113,9 @@ struct TcSearch {
   int shadow;                // kind 1: 0 = plain shadow (+ augmented columns), 1 = normalised shadow
   const void* Xb; const void* Xn;   // device addresses of the two shadows (L2 prefetch)
   int aug;                   // kind 1, L2: the query gets three 1.0 columns that pick up the shadow's -|x|^2/2 columns
+  int sample_stride;         // > 1: threshold prepass over every sample_stride-th corpus tile (set by tc_search)
+  int pre_m;                 // prepass: rank of the sample's block maximum that becomes the query's initial threshold
+  int no_prepass;            // 1: adaptive thresholds only (re-run of queries the sample threshold failed)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -295,6 +298,10 @@ struct TcParams {
   int n_tiles;            // corpus tiles of 256 rows
   int n_slices;           // corpus slices (units = n_slices * n_qt)
   int tiles_per_slice;
+  int n_vtiles;           // tiles the units iterate over: all of them, or every tile_stride-th one (threshold prepass)
+  int tile_stride;
+  float* pre_max;         // threshold prepass (PRE kernels): [query][record] maximum score of every 128-column block
+  int pre_pitch;          // records per query
   int n_kblocks;          // k-blocks (128 B of K per row) loaded per tile: n_kb_data (+ 1 when a separate augmented block is used)
   int n_kb_data;          // data k-blocks per tile (the tile stride of the tiled shadow)
   int nk_last;            // MMA instructions (32 B of K each) of the last data block: only columns that hold data are multiplied
@@ -401,9 +408,11 @@ __device__ __noinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp
 //    passing quads and, per quad in the union, re-reads those four columns from TMEM (tcgen05.ld.x4 takes a runtime
 //    column address, registers cannot be indexed) and appends what passes: one compact loop instead of 32 unrolled
 //    append sites per chunk. Columns past the shard's last row are rejected here, so the scan needs no tail handling.
-template <int METRIC, bool DBG>
+template <int METRIC, int MODE>   // MODE 0: filter, 1: filter + raw score dump (diagnostics), 2: threshold prepass (block maximum only)
 __device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float* nrm, int col0, float tau, uint2* buf,
-                                         uint32_t& wn, uint64_t* release_bar, uint32_t lane, float* dbg_row) {
+                                         uint32_t& wn, uint64_t* release_bar, uint32_t lane, float* dbg_row, float* pre_out) {
+  constexpr bool DBG = MODE == 1;
+  float blk_max = -INFINITY;
   auto release = [&]() {
     tc_fence_before();
     __syncwarp();
@@ -434,6 +443,7 @@ __device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float*
     float m = qm[0];
 #pragma unroll
     for (int g = 1; g < TC_CW / 4; ++g) m = fmaxf(m, qm[g]);
+    if (MODE == 2) { blk_max = fmaxf(blk_max, m); return; }
     if (__any_sync(0xffffffffu, m > tau)) {
       uint32_t mine = 0;
 #pragma unroll
@@ -476,6 +486,9 @@ __device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float*
     }
   }
   release();
+  // prepass: a block that reaches past the shard's last row is not recorded (its pad columns score 0, which can
+  // exceed every real score, e.g. L2 scores q.x - |x|^2/2)
+  if (MODE == 2) { if (pre_out != nullptr) *pre_out = ncols >= TC_HALF_COLS ? blk_max : -INFINITY; }
 }
 
 // Tighten thresholds after a tile. The common case costs one compare and one vote: every lane keeps the entry count
@@ -518,7 +531,7 @@ __device__ __forceinline__ void epi_tighten(const TcParams& p, bool active, int 
 // ---------------------------------------------------------------------------------------------
 // KIND 0: fp32 operands read as TF32 (k-block = 32 elements, UMMA K = 8)
 // KIND 1: bf16 operands          (k-block = 64 elements, UMMA K = 16); both are 128 B rows / 32 B per MMA
-template <int METRIC, int KIND, bool DBG>
+template <int METRIC, int KIND, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -564,8 +577,9 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int qt = p.qt_major ? u / p.n_slices : u % p.n_qt, slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
-        const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
-        for (int t = t0; t < t1; ++t) {
+        const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_vtiles, t0 + p.tiles_per_slice);
+        for (int tv = t0; tv < t1; ++tv) {
+          const int t = tv * p.tile_stride;
           if (METRIC != 2) {
             // per-column norm terms of this tile ride along, one buffer per accumulator stage
             mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 64);
@@ -584,8 +598,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
               tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0,                   // tiled shadow: one contiguous 32 KB block
                           kb < p.n_kb_data ? (t * p.n_kb_data + kb) * TC_BN : p.aug_line0 + t * TC_BN);
 #ifndef FENIX_NO_PFCODE
-              if (p.pf_tiles > 0 && t + p.pf_tiles < t1) {
-                const int tp = t + p.pf_tiles;
+              if (p.pf_tiles > 0 && tv + p.pf_tiles < t1) {
+                const int tp = (tv + p.pf_tiles) * p.tile_stride;
                 const int64_t line = kb < p.n_kb_data ? (int64_t(tp) * p.n_kb_data + kb) * TC_BN : int64_t(p.aug_line0) + int64_t(tp) * TC_BN;
                 prefetch_l2(p.xb + line * 128, TC_B_BYTES);
               }
@@ -611,7 +625,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
-        const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
+        const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_vtiles, t0 + p.tiles_per_slice);
         for (int t = t0; t < t1; ++t) {
           mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 32);
           const uint32_t d_tmem = tmem_u + uint32_t(acc * TC_BN);
@@ -656,7 +670,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int qt = p.qt_major ? u / p.n_slices : u % p.n_qt, slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
-      const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_tiles, t0 + p.tiles_per_slice);
+      const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_vtiles, t0 + p.tiles_per_slice);
       // tile row j = lane_grp*32 + lane holds query qt*128 + lane*4 + lane_grp (see knn_prep_kernel): a small
       // batch is spread over all four lane groups, i.e. over all epilogue warps and SM sub-partitions
       const int q = qt * TC_BM + int(lane) * 4 + lane_grp;
@@ -672,7 +686,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const bool poll = active && !p.fixed;
       uint32_t tg_next = poll ? ld_relaxed_u32(p.tau_g + q) : ORD_NEG_INF;
 
-      for (int t = t0; t < t1; ++t) {
+      for (int tv = t0; tv < t1; ++tv) {
+        const int t = tv * p.tile_stride;
         if (poll) {
           tau = fmaxf(tau, ord2f(tg_next));
           tg_next = ld_relaxed_u32(p.tau_g + q);
@@ -684,15 +699,17 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int ncols = min(TC_HALF_COLS, n_rows_i - col0);                 // valid columns (<=0: none)
         const float* nrm = norm_smem + acc * TC_BN + half * TC_HALF_COLS;
         float* dbg_row = nullptr;
-        if (DBG) { if (u == 0 && t == t0) dbg_row = p.dbg + (int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS; }
-        epi_tile<METRIC, DBG>(t_lane + uint32_t(acc * TC_BN), any_active ? ncols : 0, nrm, col0, tau, buf, wn,
-                              &tmem_empty[acc], lane, dbg_row);
+        if (MODE == 1) { if (u == 0 && tv == t0) dbg_row = p.dbg + (int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS; }
+        float* pre_out = nullptr;
+        if (MODE == 2) { if (active) pre_out = p.pre_max + size_t(q) * p.pre_pitch + (tv * TC_SPLIT + half); }
+        epi_tile<METRIC, MODE>(t_lane + uint32_t(acc * TC_BN), any_active ? ncols : 0, nrm, col0, tau, buf, wn,
+                               &tmem_empty[acc], lane, dbg_row, pre_out);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-        epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
+        if (MODE != 2) epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
       }
 
       // end of unit: the finish kernel reads the buffer in place
-      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wn) : 0;
+      if (MODE != 2) p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wn) : 0;
     }
   }
 
@@ -734,7 +751,7 @@ inline uint32_t rq_smem_bytes(int n_kblocks) {
   return RQ_FIXED_BYTES + uint32_t(2 * n_kblocks + rq_stages(n_kblocks)) * RQ_BLOCK_BYTES;
 }
 
-template <int METRIC>   // 0: score = acc + hx[row] (masked searches), 2: score = acc
+template <int METRIC, int MODE>   // METRIC 0: score = acc + hx[row] (masked searches), 2: score = acc; MODE 0 filter, 2 prepass
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -772,7 +789,7 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
   const int n_qp = (p.n_qt + 1) >> 1;
   const int n_units = p.n_slices * n_qp;
-  const int n_t128 = int((p.n_rows + RQ_BN - 1) / RQ_BN);
+  const int n_t128 = p.n_vtiles;   // 128-row tiles the units iterate over
   const int n_rows_i = int(p.n_rows);   // < 2^31 (tc_supported)
 
   if (warp == 0) {
@@ -791,7 +808,8 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           for (int kb = 0; kb < p.n_kblocks; ++kb)
             tma_load_2d(&map_q, a_full, a_tiles + (qt * p.n_kblocks + kb) * RQ_BLOCK_BYTES, kb * 64, (qp * 2 + qt) * TC_BM);
         a_phase ^= 1;
-        for (int t = t0; t < t1; ++t) {
+        for (int tv = t0; tv < t1; ++tv) {
+          const int t = tv * p.tile_stride;
           if (METRIC != 2) {
             // per-row terms of this tile, one buffer per accumulator stage; both query-tile groups must have left it
             mbar_wait_backoff(&tmem_empty[acc * 2 + 0], acc_phase ^ 1, 64);
@@ -806,8 +824,8 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             mbar_expect_tx(&full_bar[stage], RQ_BLOCK_BYTES);
             const int line = (kb < p.n_kb_data ? (blk * p.n_kb_data + kb) * TC_BN : p.aug_line0 + blk * TC_BN) + hrow;
             tma_load_2d(&map_x, &full_bar[stage], b_ring + stage * RQ_BLOCK_BYTES, 0, line);
-            if (p.pf_tiles > 0 && t + p.pf_tiles < t1) {
-              const int tp = t + p.pf_tiles, blkp = tp >> 1;
+            if (p.pf_tiles > 0 && tv + p.pf_tiles < t1) {
+              const int tp = (tv + p.pf_tiles) * p.tile_stride, blkp = tp >> 1;
               const int64_t linep = (kb < p.n_kb_data ? (int64_t(blkp) * p.n_kb_data + kb) * TC_BN : int64_t(p.aug_line0) + int64_t(blkp) * TC_BN) + (tp & 1) * RQ_BN;
               prefetch_l2(p.xb + linep * 128, RQ_BLOCK_BYTES);
             }
@@ -887,7 +905,8 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const bool any_active = __any_sync(0xffffffffu, active);
       const bool poll = active && !p.fixed;
       uint32_t tg_next = poll ? ld_relaxed_u32(p.tau_g + q) : ORD_NEG_INF;
-      for (int t = t0; t < t1; ++t) {
+      for (int tv = t0; tv < t1; ++tv) {
+        const int t = tv * p.tile_stride;
         if (poll) {
           tau = fmaxf(tau, ord2f(tg_next));
           tg_next = ld_relaxed_u32(p.tau_g + q);
@@ -897,12 +916,14 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tc_fence_after();
         const int col0 = t * RQ_BN;
         const int ncols = min(RQ_BN, n_rows_i - col0);
-        epi_tile<METRIC, false>(t_lane + uint32_t(acc * 2 * RQ_BN), any_active ? ncols : 0,
-                                norm_smem + acc * RQ_BN, col0, tau, buf, wn, &tmem_empty[acc * 2 + qt_l], lane, nullptr);
+        float* pre_out = nullptr;
+        if (MODE == 2) { if (active) pre_out = p.pre_max + size_t(q) * p.pre_pitch + tv; }
+        epi_tile<METRIC, MODE>(t_lane + uint32_t(acc * 2 * RQ_BN), any_active ? ncols : 0,
+                               norm_smem + acc * RQ_BN, col0, tau, buf, wn, &tmem_empty[acc * 2 + qt_l], lane, nullptr, pre_out);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
+        if (MODE != 2) epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
       }
-      p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wn) : 0;
+      if (MODE != 2) p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wn) : 0;
     }
   }
 
@@ -1195,6 +1216,40 @@ knn_tc_finish_kernel(FinishParams p) {
   }
 }
 
+// Threshold prepass, second half: one block per query picks the m-th largest of the query's n_rec (<= 4096) block
+// maxima - held in registers, bisection on the order-preserving uint encoding - and makes it the query's initial
+// threshold. The m-th largest block maximum is never above the m-th largest sample score, so it errs on the loose
+// (safe, cheap) side.
+constexpr int TAU0_PER = 16;   // records per thread: 256 threads x 16 = 4096
+__global__ void __launch_bounds__(256)
+knn_tc_tau0_kernel(const float* __restrict__ pre_max, int n_rec, int m, uint32_t* __restrict__ tau_g) {
+  __shared__ int s_cnt[2][8];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const float* rec = pre_max + size_t(q) * n_rec;
+  uint32_t o[TAU0_PER];
+#pragma unroll
+  for (int i = 0; i < TAU0_PER; ++i) {
+    const int idx = i * 256 + tid;
+    o[i] = idx < n_rec ? f2ord(rec[idx]) : 0u;
+  }
+  uint32_t v = 0;   // largest value with count(x >= v) >= m
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = v | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < TAU0_PER; ++i) c += o[i] >= cand ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    int* cnt = s_cnt[bit & 1];
+    if ((tid & 31) == 0) cnt[tid >> 5] = c;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += cnt[w];
+    if (tot >= m) v = cand;
+  }
+  if (tid == 0) tau_g[q] = v > ORD_NEG_INF ? v : ORD_NEG_INF;
+}
+
 // Refinement of flagged queries. One block per flagged query i (original index qlist[i]): gathers the query
 // into Qr[i] and derives the preset admission threshold from the k-th distance d_k of the first pass:
 // every row that can still beat d_k has exact score > s(d_k), hence filter score > s(d_k) - E.
@@ -1245,7 +1300,7 @@ __global__ void refine_scatter_kernel(const int* __restrict__ qlist, const int* 
   const int64_t total = int64_t(n_f) * k;
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
     const int i = int(t / k), j = int(t - int64_t(i) * k);
-    if (flags2[i] == 0) {
+    if (flags2 == nullptr || flags2[i] == 0) {
       out_rows[size_t(qlist[i]) * k + j] = rows2[t];
       out_dist[size_t(qlist[i]) * k + j] = dist2[t];
     }
@@ -1344,14 +1399,16 @@ inline bool tc_init(TcState* st, int sm_count, std::string* err) {
     return false;
   }
   st->encode = fn;
-  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
+  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
+  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (a != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(tc kernels) failed: ") + cudaGetErrorString(a); return false; }
   return true;
@@ -1401,11 +1458,13 @@ inline bool tc_supported(const TcState* st, const TcCorpus* tc, int64_t n_rows, 
 
 struct TcPlan {
   int n_qt, n_tiles, n_slices, tiles_per_slice, grid, units, kp, cap, n_kblocks, n_kb_data, nk_last, aug_line0, aug_col;
+  int n_vtiles, tile_stride;
   int qt_major;
   int rq;        // 1: resident-query kernel (units = query pairs x slices of 128-row tiles, one list per unit and query)
   int n_qp;      // query pairs
   int kp_list;   // candidates each (query, list) keeps at a selection (<= kp)
-  size_t off_qp, off_qb, off_tau, off_flags, off_wcnt, off_wbuf, total;
+  size_t off_qp, off_qb, off_tau, off_flags, off_wcnt, off_wbuf, off_pre, total;
+  int n_rec, pre_pitch;   // threshold prepass: block-maximum records per query (= row pitch of the record matrix)
 };
 
 inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
@@ -1413,7 +1472,9 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.n_qt = (s.n_q + TC_BM - 1) / TC_BM;
   pl.n_tiles = int((s.n_rows + TC_BN - 1) / TC_BN);
   pl.kp = s.tau_fixed ? 1024 : tc_kp(s.k, s.certify, s.kind);   // refinement reranks every survivor (up to 1024)
-  if (!s.tau_fixed && s.certify) { if (const char* e = std::getenv("FENIX_TC_KP")) { int f = std::atoi(e); if (f >= s.k && f <= 512) pl.kp = (f + 31) & ~31; } }
+  const bool pre = s.sample_stride > 1;                          // threshold prepass over a strided sample
+  if (pre) pl.kp = 32;   // unused by the prepass kernels (no candidate lists); keeps the slice heuristics below sane
+  if (!s.tau_fixed && s.certify && !pre) { if (const char* e = std::getenv("FENIX_TC_KP")) { int f = std::atoi(e); if (f >= s.k && f <= 512) pl.kp = (f + 31) & ~31; } }
   pl.cap = tc_cap(pl.kp);
   // MMA instructions per tile: 32 B of K each (8 fp32 / 16 bf16 elements); only columns that hold data
   pl.aug_line0 = 0; pl.aug_col = 0;
@@ -1436,7 +1497,10 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.rq = (s.kind == 1 && pl.n_kblocks <= RQ_MAX_KB && pl.n_qt >= 2 && s.epi != 1 && s.dbg == nullptr &&
            !std::getenv("FENIX_TC_NO_RQ")) ? 1 : 0;
   pl.n_qp = (pl.n_qt + 1) / 2;
-  const int n_tiles_u = pl.rq ? int((s.n_rows + RQ_BN - 1) / RQ_BN) : pl.n_tiles;   // tiles in the kernel's own unit
+  const int n_tiles_full = pl.rq ? int((s.n_rows + RQ_BN - 1) / RQ_BN) : pl.n_tiles;   // tiles in the kernel's own unit
+  pl.tile_stride = pre ? s.sample_stride : 1;
+  const int n_tiles_u = (n_tiles_full + pl.tile_stride - 1) / pl.tile_stride;          // tiles the units iterate over
+  pl.n_vtiles = n_tiles_u;
   const int n_qu = pl.rq ? pl.n_qp : pl.n_qt;                                       // query blocks per slice
   // Slices: units = n_qt * n_slices (query-tile major, so all slices of a query tile run at the same time and
   // share thresholds) are dealt round-robin to min(units, #SM) persistent CTAs.
@@ -1444,7 +1508,7 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   // tighter thresholds and fewer candidate lists), and every unit should span enough tiles for its
   // threshold to become selective.
   const int sms = st->sm_count;
-  const int min_tiles = std::max(4, (8 * pl.kp + TC_BN - 1) / TC_BN) * (pl.rq ? 2 : 1);
+  const int min_tiles = pre ? 4 : std::max(4, (8 * pl.kp + TC_BN - 1) / TC_BN) * (pl.rq ? 2 : 1);
   const int s_cap = std::max(1, (TC_MAX_WAVES * sms) / n_qu);
   const int s_max = std::max(1, std::min(n_tiles_u / min_tiles, s_cap));
   double best = -1.0; int best_s = 1;
@@ -1478,9 +1542,9 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     const int lists = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices;
     int m = std::max(32, (2 * s.k + lists - 1) / lists + 16);
     m = (m + 31) & ~31;
-    pl.kp_list = s.tau_fixed ? pl.kp : std::min(pl.kp, m);
-    if (const char* e = std::getenv("FENIX_TC_KP_LIST")) { int f = std::atoi(e); if (f >= 32) pl.kp_list = std::min(pl.kp, (f + 31) & ~31); }
-    pl.cap = s.tau_fixed ? pl.cap : tc_cap(pl.kp_list);
+    pl.kp_list = (s.tau_fixed || pre) ? pl.kp : std::min(pl.kp, m);   // prepass: every list keeps the m best it sees
+    if (!pre) if (const char* e = std::getenv("FENIX_TC_KP_LIST")) { int f = std::atoi(e); if (f >= 32) pl.kp_list = std::min(pl.kp, (f + 31) & ~31); }
+    pl.cap = (s.tau_fixed || pre) ? pl.cap : tc_cap(pl.kp_list);
   }
   pl.grid = int(std::min<long>(pl.units, sms));
   size_t off = 0;
@@ -1490,13 +1554,32 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.off_qb = take(s.kind == 1 ? q_rows_p * s.pitch_b * 2 : 0);
   pl.off_tau = take(size_t(s.n_q) * 4);
   pl.off_flags = take(size_t(s.n_q) * 4);
-  pl.off_wcnt = take(size_t(pl.units) * TC_SLOTS * 4);
-  pl.off_wbuf = take(size_t(pl.units) * TC_SLOTS * pl.cap * 8);
+  pl.n_rec = pl.n_vtiles * (pl.rq ? 1 : TC_SPLIT);
+  pl.pre_pitch = pl.n_rec;
+  if (pre) {
+    pl.off_wcnt = pl.off_wbuf = off;
+    pl.off_pre = take(size_t(s.n_q) * pl.pre_pitch * 4);
+  } else {
+    pl.off_wcnt = take(size_t(pl.units) * TC_SLOTS * 4);
+    pl.off_wbuf = take(size_t(pl.units) * TC_SLOTS * pl.cap * 8);
+    pl.off_pre = off;
+  }
   pl.total = off;
   return pl;
 }
 
-inline size_t tc_scratch_bytes(const TcState* st, const TcSearch& s) { return tc_plan(st, s).total; }
+inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan& main_pl, TcSearch* pre);
+inline bool tc_uses_prepass(const TcState* st, const TcSearch& s) {
+  TcSearch pre;
+  return tc_prepass_config(st, s, tc_plan(st, s), &pre);
+}
+inline size_t tc_scratch_bytes(const TcState* st, const TcSearch& s) {
+  const TcPlan pl = tc_plan(st, s);
+  TcSearch pre;
+  size_t total = pl.total;
+  if (tc_prepass_config(st, s, pl, &pre)) total = std::max(total, tc_plan(st, pre).total);
+  return total;
+}
 inline const int* tc_flags(const TcState* st, const TcSearch& s, void* scratch) {
   return reinterpret_cast<const int*>(static_cast<char*>(scratch) + tc_plan(st, s).off_flags);
 }
@@ -1512,33 +1595,51 @@ inline double tc_c_err(int dim, int kind = 0) {
   return prod + double(dim) * std::ldexp(1.0, -21);
 }
 
-inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratch, int* launched, std::string* err) {
-  const TcPlan pl = tc_plan(st, s);
+// Threshold prepass (narrow rows, where the epilogue - not the tensor pipe - binds): the same filter kernel runs over
+// every stride-th corpus tile, and the m-th best sample score of a query becomes its initial threshold for the main
+// pass. With S sampled rows the threshold passes ~ m N / S rows of the shard; stride and m are chosen so that this is
+// `safety` x K' with m ~ 10 (relative spread ~ 1/sqrt(m); a threshold that turns out too tight only costs the query
+// a refinement pass, one that is too loose more appends - exactness never depends on the sample).
+inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan& main_pl, TcSearch* pre) {
+  (void)st;
+  if (s.tau_fixed || s.no_prepass || s.sample_stride > 1 || s.kind != 1 || s.dbg != nullptr) return false;
+  if (main_pl.n_kblocks > 4) return false;                 // wide rows: the tensor pipe binds, thresholds are not the issue
+  if (const char* e = std::getenv("FENIX_TC_PRE")) { if (std::atoi(e) == 0) return false; }
+  double safety = 3.0;
+  if (const char* e = std::getenv("FENIX_TC_PRE_SAFETY")) { double f = std::atof(e); if (f >= 1.0 && f <= 64.0) safety = f; }
+  const int tile_rows = main_pl.rq ? RQ_BN : TC_BN;
+  double target_m = 16.0;
+  if (const char* e = std::getenv("FENIX_TC_PRE_M")) { double f = std::atof(e); if (f >= 2.0 && f <= 256.0) target_m = f; }
+  int stride = int(double(main_pl.kp) * safety / target_m);         // S = N / stride, m = safety K' S / N
+  const int64_t n_tiles_full = (s.n_rows + tile_rows - 1) / tile_rows;
+  if (stride < 4 || n_tiles_full / stride < 32) return false;       // shard too small for a sample to pay off
+  const int rec_per_tile = main_pl.rq ? 1 : TC_SPLIT;
+  stride = int(std::max<int64_t>(stride, (n_tiles_full * rec_per_tile + 4095) / 4096));   // at most 4096 records per query
+  const int64_t sample_rows = ((n_tiles_full + stride - 1) / stride) * tile_rows;
+  *pre = s;
+  pre->sample_stride = stride;
+  pre->pre_m = std::max(4, int(safety * double(main_pl.kp) * double(sample_rows) / double(s.n_rows) + 0.5));
+  pre->certify = false;
+  pre->ev_k0 = nullptr; pre->ev_k1 = nullptr;
+  return true;
+}
+
+// One filter launch (+ finish) over the plan of `s`; queries / state have been prepared in `scratch` already.
+inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPlan& pl, void* scratch, const CUtensorMap& map_q,
+                        std::string* err) {
   char* base = static_cast<char*>(scratch);
   float* qp = reinterpret_cast<float*>(base + pl.off_qp);
   uint32_t* tau_g = reinterpret_cast<uint32_t*>(base + pl.off_tau);
   int* flags = reinterpret_cast<int*>(base + pl.off_flags);
   int* wcnt = reinterpret_cast<int*>(base + pl.off_wcnt);
   uint2* wbuf = reinterpret_cast<uint2*>(base + pl.off_wbuf);
-
-  __nv_bfloat16* qb = s.kind == 1 ? reinterpret_cast<__nv_bfloat16*>(base + pl.off_qb) : nullptr;
-  CUtensorMap map_q;
-  if (s.kind == 0) {
-    if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(pl.n_qp) * 2 * TC_BM, uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
-  } else {
-    if (s.shadow == 1 ? !tc->ok_n : !tc->ok_b) { *err = "bf16 filter requested but the shard has no bf16 shadow"; return false; }
-    if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(pl.n_qp) * 2 * TC_BM, uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
-  }
-
-  const int n_rows_p = pl.n_qp * 2 * TC_BM;
-  const int prep_blocks = int(std::min<int64_t>((int64_t(n_rows_p) * s.pitch + 255) / 256, 4 * 148));
-  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, n_rows_p, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed,
-                                                                  (!s.tau_fixed && std::getenv("FENIX_TC_WARM")) ? 1 : 0,
-                                                                  (s.kind == 1 && s.aug) ? pl.aug_col : 0);
+  const bool pre = s.sample_stride > 1;   // threshold prepass: block maxima of a strided sample, then tau0
 
   TcParams p{};
+  p.pre_max = reinterpret_cast<float*>(base + pl.off_pre); p.pre_pitch = pl.pre_pitch;
   p.n_q = s.n_q; p.n_qt = pl.n_qt; p.n_rows = s.n_rows; p.n_tiles = pl.n_tiles; p.n_slices = pl.n_slices;
-  p.tiles_per_slice = pl.tiles_per_slice; p.n_kblocks = pl.n_kblocks; p.n_kb_data = pl.n_kb_data; p.nk_last = pl.nk_last;
+  p.tiles_per_slice = pl.tiles_per_slice; p.n_vtiles = pl.n_vtiles; p.tile_stride = pl.tile_stride;
+  p.n_kblocks = pl.n_kblocks; p.n_kb_data = pl.n_kb_data; p.nk_last = pl.nk_last;
   p.aug_line0 = pl.aug_line0;
   p.xb = s.kind == 1 ? static_cast<const unsigned char*>(s.shadow == 1 ? s.Xn : s.Xb) : nullptr;
   p.pf_tiles = 0;   // off: measured neutral where operands come from L2 (C2, C4) and 1.9x slower where HBM binds (C5)
@@ -1558,16 +1659,24 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
     p.rq_stages = rq_stages(pl.n_kblocks);
     if (const char* e = std::getenv("FENIX_RQ_STAGES")) { int f = std::atoi(e); if (f >= 2 && f <= p.rq_stages) p.rq_stages = f; }
     const uint32_t rq_smem = rq_smem_bytes(pl.n_kblocks);
-    if (epi == 0) knn_rq_filter_kernel<0><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
-    else knn_rq_filter_kernel<2><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+    if (pre) {
+      if (epi == 0) knn_rq_filter_kernel<0, 2><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+      else knn_rq_filter_kernel<2, 2><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+    } else {
+      if (epi == 0) knn_rq_filter_kernel<0, 0><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+      else knn_rq_filter_kernel<2, 0><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+    }
   } else {
 #define FX_TC_CASE(E, K, MAP)                                                       \
   if (epi == E && s.kind == K) {                                                    \
     if (dbg) {                                                                      \
-      cudaFuncSetAttribute(knn_tc_filter_kernel<E, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
-      launch(knn_tc_filter_kernel<E, K, true>, MAP);                                \
+      cudaFuncSetAttribute(knn_tc_filter_kernel<E, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
+      launch(knn_tc_filter_kernel<E, K, 1>, MAP);                                   \
+    } else if (pre && K == 1) {                                                     \
+      cudaFuncSetAttribute(knn_tc_filter_kernel<E, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
+      launch(knn_tc_filter_kernel<E, 1, 2>, MAP);                                   \
     } else {                                                                        \
-      launch(knn_tc_filter_kernel<E, K, false>, MAP);                               \
+      launch(knn_tc_filter_kernel<E, K, 0>, MAP);                                   \
     }                                                                               \
   }
   FX_TC_CASE(0, 0, tc->map_x) FX_TC_CASE(1, 0, tc->map_x) FX_TC_CASE(2, 0, tc->map_x)
@@ -1576,6 +1685,12 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
 #undef FX_TC_CASE
   }
   if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
+  if (pre) {
+    knn_tc_tau0_kernel<<<s.n_q, 256, 0, s.stream>>>(p.pre_max, pl.n_rec, s.pre_m, tau_g);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) { *err = std::string("threshold prepass launch failed: ") + cudaGetErrorString(e0); return false; }
+    return true;
+  }
 
   FinishParams f{};
   f.X = s.X; f.pitch = s.pitch; f.dim = s.dim; f.row_base = s.row_base; f.Qp = qp; f.n_q = s.n_q; f.n_qt = pl.n_qt;
@@ -1589,8 +1704,39 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   knn_tc_finish_kernel<<<s.n_q, fin_threads, fin_smem, s.stream>>>(f);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tensor-core path launch failed: ") + cudaGetErrorString(e); return false; }
-  *launched = 3;
   return true;
+}
+
+inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratch, int* launched, std::string* err) {
+  const TcPlan pl = tc_plan(st, s);
+  char* base = static_cast<char*>(scratch);
+  float* qp = reinterpret_cast<float*>(base + pl.off_qp);
+  uint32_t* tau_g = reinterpret_cast<uint32_t*>(base + pl.off_tau);
+  int* flags = reinterpret_cast<int*>(base + pl.off_flags);
+
+  __nv_bfloat16* qb = s.kind == 1 ? reinterpret_cast<__nv_bfloat16*>(base + pl.off_qb) : nullptr;
+  CUtensorMap map_q;
+  if (s.kind == 0) {
+    if (!tc_encode_2d(st, &map_q, qp, uint64_t(s.pitch), uint64_t(pl.n_qp) * 2 * TC_BM, uint64_t(s.pitch), TC_BK, TC_BM, err)) return false;
+  } else {
+    if (s.shadow == 1 ? !tc->ok_n : !tc->ok_b) { *err = "bf16 filter requested but the shard has no bf16 shadow"; return false; }
+    if (!tc_encode_2d(st, &map_q, qb, uint64_t(s.pitch_b), uint64_t(pl.n_qp) * 2 * TC_BM, uint64_t(s.pitch_b), 2 * TC_BK, TC_BM, err, true)) return false;
+  }
+
+  const int n_rows_p = pl.n_qp * 2 * TC_BM;
+  const int prep_blocks = int(std::min<int64_t>((int64_t(n_rows_p) * s.pitch + 255) / 256, 4 * 148));
+  knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, n_rows_p, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed,
+                                                                  (!s.tau_fixed && std::getenv("FENIX_TC_WARM")) ? 1 : 0,
+                                                                  (s.kind == 1 && s.aug) ? pl.aug_col : 0);
+  *launched = 3;
+  // threshold prepass over a strided sample (the padded queries and tau_g sit at the same scratch offsets in both plans)
+  TcSearch pre;
+  if (tc_prepass_config(st, s, pl, &pre)) {
+    const TcPlan ppl = tc_plan(st, pre);
+    if (!tc_run_pass(st, tc, pre, ppl, scratch, map_q, err)) return false;
+    *launched += 2;
+  }
+  return tc_run_pass(st, tc, s, pl, scratch, map_q, err);
 }
 
 }  // namespace fx

@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed
 outputs of the live reference. Bar: neighbour ids bit-exact under (distance, row) order,
 distances within 1e-5 relative (BASELINE.json north_star), tolerance written in conftest."""
+import os
+
 import numpy as np
 import pyarrow as pa
 import pyarrow.compute as pc
@@ -226,6 +228,71 @@ def test_large_property_checks(ctx):
         r1, d1 = c.search(qh[sub], metric, 10)
         r2, d2 = c.search(qh[sub], metric, 10, knn.PREC_EXACT_SCAN)
         assert np.array_equal(r1, r2) and np.array_equal(d1, d2)
+    c.close()
+
+
+@pytest.mark.parametrize("metric,dim,k", [("l2", 128, 100), ("dot", 96, 100), ("cosine", 64, 10), ("l2", 100, 10)])
+def test_resident_query_kernel_and_sample_prepass(ctx, metric, dim, k):
+    """Narrow rows + several query tiles take the resident-query kernel with thresholds from the strided sample
+    prepass: same answer as the fp64 scan, the adaptive path (prepass off) and the streaming kernel."""
+    import torch
+
+    n, nq = 400_000, 700
+    g = torch.Generator(device="cuda").manual_seed(4242 + dim)
+    x = torch.randn((n, dim), generator=g, device="cuda", dtype=torch.float32)
+    q = torch.randn((nq, dim), generator=g, device="cuda", dtype=torch.float32)
+    c = knn.Corpus(ctx, n, dim)
+    torch.cuda.synchronize()
+    c.append_device(x.data_ptr(), n)
+    c.finalize()
+    qh = q.cpu().numpy()
+    before = c.stats()
+    rows, dist = c.search(qh, metric, k)
+    after = c.stats()
+    assert after.last_path == 2
+    assert after.fallback_queries - before.fallback_queries <= 3
+    sub = np.arange(0, nq, 37)
+    rows_s, dist_s = c.search(qh[sub], metric, k, knn.PREC_EXACT_SCAN)
+    assert np.array_equal(rows[sub], rows_s) and np.array_equal(dist[sub], dist_s)
+    for env in ({"FENIX_TC_PRE": "0"}, {"FENIX_TC_NO_RQ": "1"}, {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PRE": "0"}):
+        os.environ.update(env)
+        try:
+            rows_e, dist_e = c.search(qh, metric, k)
+        finally:
+            for key in env:
+                del os.environ[key]
+        assert np.array_equal(rows, rows_e) and np.array_equal(dist, dist_e), env
+    c.close()
+
+
+def test_sample_prepass_with_an_unrepresentative_sample(ctx):
+    """Adversarial layout for the threshold prepass: every sampled tile is filled with copies of the queries, so
+    each query's sample threshold lands far above anything the rest of the shard offers and the main pass keeps
+    fewer than k candidates. The adaptive re-run (tier 0) must settle those queries exactly."""
+    import torch
+
+    n, dim, nq, k = 300_000, 64, 256, 100
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn((n, dim), generator=g, device="cuda", dtype=torch.float32)
+    q = torch.randn((nq, dim), generator=g, device="cuda", dtype=torch.float32)
+    # K' = 160 for k = 100 -> the default knobs sample every 30th tile of 128 rows (79 tiles, rank m = 16).
+    # Sampled tile j holds 3 q_i for the 128 queries of query tile j % 2: every query owns ~40 sampled blocks whose
+    # maximum is 3 |q|^2, so its sample threshold is 3 |q|^2 - and only ~40 < k rows of the shard reach it.
+    stride = 30
+    for j, t in enumerate(range(0, n // 128, stride)):
+        x[t * 128:(t + 1) * 128] = 3.0 * q[(j % 2) * 128:(j % 2) * 128 + 128]
+    c = knn.Corpus(ctx, n, dim)
+    torch.cuda.synchronize()
+    c.append_device(x.data_ptr(), n)
+    c.finalize()
+    qh = q.cpu().numpy()
+    before = c.stats()
+    rows, dist = c.search(qh, "dot", k)
+    after = c.stats()
+    assert after.refined_queries - before.refined_queries >= 64, "the planted sample should defeat most sample thresholds"
+    assert after.fallback_queries == before.fallback_queries, "the adaptive re-run should make the fp64 scan unnecessary"
+    rows_s, dist_s = c.search(qh, "dot", k, knn.PREC_EXACT_SCAN)
+    assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
     c.close()
 
 
