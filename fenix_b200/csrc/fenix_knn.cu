@@ -557,8 +557,9 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
       const int* d_flags = fx::tc_flags(&ctx->tc, s, ctx->d_tc.p);
       FX_CUDA(cudaMemcpyAsync(h_flags, d_flags, size_t(n_q) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       FX_CUDA(cudaStreamSynchronize(ctx->stream));
-      std::vector<int> bad;
-      for (int64_t i = 0; i < n_q; ++i) if (h_flags[i]) bad.push_back(int(i));
+      // flag 1: the certificate failed; flag 2: fewer than k candidates survived (a sample threshold that came out too tight)
+      std::vector<int> bad, starved;
+      for (int64_t i = 0; i < n_q; ++i) { if (h_flags[i] == 2) starved.push_back(int(i)); else if (h_flags[i]) bad.push_back(int(i)); }
       // Flagged queries are settled by up to two more filter passes over their own (small) batch:
       //  tier 0 (only when the main pass took its thresholds from the sample prepass): the adaptive search without
       //         prepass - a sample threshold that came out too tight leaves a query with fewer than k candidates,
@@ -566,7 +567,11 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
       //  tier 1: preset-threshold refinement: the admission threshold is the query's k-th distance minus the error
       //         bound and every survivor is reranked, so the result is exact.
       const bool had_prepass = fx::tc_uses_prepass(&ctx->tc, s);
-      for (int tier = had_prepass ? 0 : 1; tier <= 1 && !bad.empty() && !std::getenv("FENIX_NO_REFINE"); ++tier) {
+      if (!had_prepass) { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }
+      for (int tier = starved.empty() ? 1 : 0; tier <= 1 && !std::getenv("FENIX_NO_REFINE"); ++tier) {
+        if (tier == 0) bad.swap(starved);                                    // tier 0 takes the starved queries only ...
+        else { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }   // ... what it leaves flagged joins tier 1
+        if (bad.empty()) continue;
         const int n_f = int(bad.size());
         FX_TRY(ctx->d_qlist.ensure(size_t(n_f) * sizeof(int)));
         FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), size_t(n_f) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

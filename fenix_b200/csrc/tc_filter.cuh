@@ -1095,23 +1095,34 @@ knn_tc_finish_kernel(FinishParams p) {
       if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 0xffu], 1);
     });
     __syncthreads();
-    if (tid == 0) {
-      int remaining = s_remaining;
-      if (pass == 0) {
-        int total = 0;
-        for (int b = 0; b < 256; ++b) total += hist[b];
-        s_total = total;
+    if (warp == 0) {
+      // find the highest bin b with sum(hist[b..255]) >= remaining: each lane owns 8 bins, suffix sums across lanes
+      const int remaining = s_remaining;
+      int h[8], lane_sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; lane_sum += h[j]; }
+      int suffix = lane_sum;                                   // inclusive sum over lanes >= this one
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += up;
       }
-      if (pass == 0 && s_total <= p.kp) {
-        s_remaining = -1;  // keep everything above tg
+      const int total = __shfl_sync(0xffffffffu, suffix, 0);
+      if (pass == 0 && lane == 0) s_total = total;
+      if (pass == 0 && total <= p.kp) {
+        if (lane == 0) s_remaining = -1;                       // keep everything above tg
       } else {
-        int cum = 0, b = 255;
-        for (; b > 0; --b) {
-          if (cum + hist[b] >= remaining) break;
-          cum += hist[b];
+        const uint32_t reach = __ballot_sync(0xffffffffu, suffix >= remaining);
+        const int owner = reach ? 31 - __clz(reach) : 0;       // highest lane whose suffix reaches `remaining`
+        if (lane == owner) {
+          int cum = suffix - lane_sum, b = 8 * lane + 7;       // cum: everything in higher lanes
+          for (int j = 7; j >= 0; --j, --b) {
+            if (cum + h[j] >= remaining || b == 0) break;
+            cum += h[j];
+          }
+          s_prefix = prefix | (uint32_t(b) << shift);
+          s_remaining = remaining - cum;
         }
-        s_prefix = prefix | (uint32_t(b) << shift);
-        s_remaining = remaining - cum;
       }
     }
     __syncthreads();
@@ -1139,31 +1150,35 @@ knn_tc_finish_kernel(FinishParams p) {
   const int n_cand = n_gt + n_tie_kept;
 
   // ---- 2. exact rerank: one warp per candidate, fp64 accumulation of exact fp32 products ----
+  // Eight lanes per candidate, four candidates per warp and step: the four row loads are independent (one memory
+  // round trip per four candidates; the rows are scattered over the shard) and the fp64 reduction is three shuffle
+  // rounds instead of five (the kernel is instruction-bound: 70 % issue utilisation on C2, half of it here).
   const double qq = s_qq;
-  for (int c = warp; c < p.sort2; c += n_warps) {
-    uint64_t out_key = KEY_PAD;
-    const bool is_gt = c < n_gt;
-    const bool is_tie = !keep_all && c >= p.kp - n_tie_kept && c < p.kp;
-    if (is_gt || is_tie) {
-      const uint32_t row = cand[c];
+  {
+    const int sub = lane & 7, grp = lane >> 3;
+    const int n4 = p.pitch >> 2;
+    for (int c0 = warp * 4; c0 < p.sort2; c0 += n_warps * 4) {
+      const int c = c0 + grp;
+      const bool live = c < n_gt || (!keep_all && c >= p.kp - n_tie_kept && c < p.kp);
+      const uint32_t row = live ? cand[c] : 0u;
       const float4* xp = reinterpret_cast<const float4*>(p.X + size_t(row) * p.pitch);
       double xx = 0.0, qx = 0.0;
-      for (int j = lane; j < (p.pitch >> 2); j += 32) {
-        float4 xv = __ldg(xp + j);
-        float4 qv = *reinterpret_cast<const float4*>(qs + 4 * j);
+#pragma unroll 4
+      for (int j = sub; j < n4; j += 8) {
+        const float4 xv = live ? __ldg(xp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 qv = *reinterpret_cast<const float4*>(qs + 4 * j);
         xx = fma(double(xv.x), double(xv.x), xx); qx = fma(double(xv.x), double(qv.x), qx);
         xx = fma(double(xv.y), double(xv.y), xx); qx = fma(double(xv.y), double(qv.y), qx);
         xx = fma(double(xv.z), double(xv.z), xx); qx = fma(double(xv.z), double(qv.z), qx);
         xx = fma(double(xv.w), double(xv.w), xx); qx = fma(double(xv.w), double(qv.w), qx);
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 4; o > 0; o >>= 1) {
         xx += __shfl_xor_sync(0xffffffffu, xx, o);
         qx += __shfl_xor_sync(0xffffffffu, qx, o);
       }
-      out_key = make_key(finish_distance(p.metric, qq, xx, qx), row);
+      if (sub == 0 && c < p.sort2) keys2[c] = live ? make_key(finish_distance(p.metric, qq, xx, qx), row) : KEY_PAD;
     }
-    if (lane == 0) keys2[c] = out_key;
   }
   __syncthreads();
   // ---- 3. sort by (distance, row), output, certificate ----
@@ -1210,27 +1225,31 @@ knn_tc_finish_kernel(FinishParams p) {
         float dk = ord2f(uint32_t(keys2[p.k - 1] >> 32));
         ok = double(dk) < lb;   // NaN compares false -> flagged
       }
-      flag = ok ? 0 : 1;
+      flag = ok ? 0 : (n_cand < p.k ? 2 : 1);   // 2: fewer than k candidates at all (no k-th distance to refine from)
     }
     p.flags[q] = flag;
   }
 }
 
-// Threshold prepass, second half: one block per query picks the m-th largest of the query's n_rec (<= 4096) block
-// maxima - held in registers, bisection on the order-preserving uint encoding - and makes it the query's initial
-// threshold. The m-th largest block maximum is never above the m-th largest sample score, so it errs on the loose
-// (safe, cheap) side.
-constexpr int TAU0_PER = 16;   // records per thread: 256 threads x 16 = 4096
+// Threshold prepass, second half: a group of T threads per query (T = 32 ... 256, 16 records per thread) picks the
+// m-th largest of the query's n_rec (<= 4096) block maxima - held in registers, bisection on the order-preserving
+// uint encoding - and makes it the query's initial threshold. The m-th largest block maximum is never above the
+// m-th largest sample score, so it errs on the loose (safe, cheap) side.
+constexpr int TAU0_PER = 16;
+template <int T>
 __global__ void __launch_bounds__(256)
-knn_tc_tau0_kernel(const float* __restrict__ pre_max, int n_rec, int m, uint32_t* __restrict__ tau_g) {
+knn_tc_tau0_kernel(const float* __restrict__ pre_max, int n_q, int n_rec, int m, uint32_t* __restrict__ tau_g) {
+  constexpr int W = T / 32;                   // warps per query
   __shared__ int s_cnt[2][8];
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const float* rec = pre_max + size_t(q) * n_rec;
+  const int tid = threadIdx.x, sub = tid % T, grp = tid / T;
+  const int q = blockIdx.x * (256 / T) + grp;
+  const bool live = q < n_q;
+  const float* rec = pre_max + size_t(live ? q : 0) * n_rec;
   uint32_t o[TAU0_PER];
 #pragma unroll
   for (int i = 0; i < TAU0_PER; ++i) {
-    const int idx = i * 256 + tid;
-    o[i] = idx < n_rec ? f2ord(rec[idx]) : 0u;
+    const int idx = i * T + sub;
+    o[i] = (live && idx < n_rec) ? f2ord(rec[idx]) : 0u;
   }
   uint32_t v = 0;   // largest value with count(x >= v) >= m
   for (int bit = 31; bit >= 0; --bit) {
@@ -1239,15 +1258,17 @@ knn_tc_tau0_kernel(const float* __restrict__ pre_max, int n_rec, int m, uint32_t
 #pragma unroll
     for (int i = 0; i < TAU0_PER; ++i) c += o[i] >= cand ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
-    int* cnt = s_cnt[bit & 1];
-    if ((tid & 31) == 0) cnt[tid >> 5] = c;
-    __syncthreads();
-    int tot = 0;
+    if (W > 1) {
+      int* cnt = s_cnt[bit & 1];
+      if ((tid & 31) == 0) cnt[tid >> 5] = c;
+      __syncthreads();
+      c = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += cnt[w];
-    if (tot >= m) v = cand;
+      for (int w = 0; w < W; ++w) c += cnt[grp * W + w];
+    }
+    if (c >= m) v = cand;
   }
-  if (tid == 0) tau_g[q] = v > ORD_NEG_INF ? v : ORD_NEG_INF;
+  if (live && sub == 0) tau_g[q] = v > ORD_NEG_INF ? v : ORD_NEG_INF;
 }
 
 // Refinement of flagged queries. One block per flagged query i (original index qlist[i]): gathers the query
@@ -1686,7 +1707,10 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   }
   if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
   if (pre) {
-    knn_tc_tau0_kernel<<<s.n_q, 256, 0, s.stream>>>(p.pre_max, pl.n_rec, s.pre_m, tau_g);
+    if (pl.n_rec <= 32 * TAU0_PER) knn_tc_tau0_kernel<32><<<(s.n_q + 7) / 8, 256, 0, s.stream>>>(p.pre_max, s.n_q, pl.n_rec, s.pre_m, tau_g);
+    else if (pl.n_rec <= 64 * TAU0_PER) knn_tc_tau0_kernel<64><<<(s.n_q + 3) / 4, 256, 0, s.stream>>>(p.pre_max, s.n_q, pl.n_rec, s.pre_m, tau_g);
+    else if (pl.n_rec <= 128 * TAU0_PER) knn_tc_tau0_kernel<128><<<(s.n_q + 1) / 2, 256, 0, s.stream>>>(p.pre_max, s.n_q, pl.n_rec, s.pre_m, tau_g);
+    else knn_tc_tau0_kernel<256><<<s.n_q, 256, 0, s.stream>>>(p.pre_max, s.n_q, pl.n_rec, s.pre_m, tau_g);
     cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) { *err = std::string("threshold prepass launch failed: ") + cudaGetErrorString(e0); return false; }
     return true;
