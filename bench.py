@@ -51,6 +51,18 @@ def peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def ncu_traffic(config: str, world: int):
+    """DRAM bytes (read + write) of the dominant kernel per launch, from the committed `ncu --set full` capture of
+    this configuration on one GPU (profiles/ncu_traffic.json, written by scripts/summarise_profiles.py), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if world != 1 or not os.path.exists(path):
+        return None, "no single-GPU ncu capture for this configuration"
+    rec = json.load(open(path)).get(config)
+    if not rec:
+        return None, "no single-GPU ncu capture for this configuration"
+    return rec["dram_bytes_per_launch"], f"profiles/{rec['capture']} (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+
+
 def query_batch(cfg: dict) -> np.ndarray:
     rng = np.random.default_rng(2000 + cfg["num"])
     return rng.standard_normal((cfg["q"], cfg["d"]), dtype=np.float32)
@@ -338,7 +350,12 @@ def run_ours(args, cfg: dict) -> dict:
             peak = pk["hbm_gbs"]
             roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                         peak_source=f"{pk['_source']} copy bandwidth")
-        roof.update(kernel={0: "exact_scan_kernel", 1: "knn_tc_filter_kernel<metric, tf32>", 2: "knn_tc_filter_kernel<metric, bf16>"}[path],
+        variant = int(getattr(st1, "last_variant", 0))
+        kernel_name = {0: "exact_scan_kernel", 1: "knn_tc_filter_kernel<epilogue, tf32> (streaming)",
+                       2: "knn_rq_filter_kernel<epilogue> (resident-query, bf16)" if variant & 1
+                       else "knn_tc_filter_kernel<epilogue, bf16> (streaming)"}[path]
+        roof["traffic"], roof["traffic_source"] = ncu_traffic(args.config if not (args.rows or args.queries) else "", world)
+        roof.update(kernel=kernel_name, sample_prepass=bool(variant & 2),
                     kernel_ms=k_ms, search_device_ms=s_ms,
                     algorithmic=dict(flops=flops, bytes=bytes_alg, per="launch (one query batch against this rank's shard)"))
         out = {

@@ -547,8 +547,9 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
     std::string err;
     size_t need = fx::tc_scratch_bytes(&ctx->tc, s);
     FX_TRY(ctx->d_tc.ensure(need));
-    int launched = 0;
-    if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err)) return fail(FX_ECUDA, "fx_search: %s", err.c_str());
+    int launched = 0, variant = 0;
+    if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err, &variant)) return fail(FX_ECUDA, "fx_search: %s", err.c_str());
+    c->stats.last_variant = variant;
     ctx->launches += launched; c->stats.kernel_launches += launched;
     if (s.certify) {
       // queries whose certificate failed are recomputed by the exact scan

@@ -1731,7 +1731,8 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   return true;
 }
 
-inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratch, int* launched, std::string* err) {
+inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratch, int* launched, std::string* err,
+                      int* variant = nullptr) {
   const TcPlan pl = tc_plan(st, s);
   char* base = static_cast<char*>(scratch);
   float* qp = reinterpret_cast<float*>(base + pl.off_qp);
@@ -1755,7 +1756,9 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   *launched = 3;
   // threshold prepass over a strided sample (the padded queries and tau_g sit at the same scratch offsets in both plans)
   TcSearch pre;
-  if (tc_prepass_config(st, s, pl, &pre)) {
+  const bool with_pre = tc_prepass_config(st, s, pl, &pre);
+  if (variant) *variant = (pl.rq ? 1 : 0) | (with_pre ? 2 : 0);
+  if (with_pre) {
     const TcPlan ppl = tc_plan(st, pre);
     if (!tc_run_pass(st, tc, pre, ppl, scratch, map_q, err)) return false;
     *launched += 2;

@@ -62,7 +62,7 @@ class _FxStats(ctypes.Structure):
         ("device_bytes", ctypes.c_int64), ("searches", ctypes.c_int64), ("queries", ctypes.c_int64),
         ("fallback_queries", ctypes.c_int64), ("refined_queries", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
         ("last_search_ms", ctypes.c_double), ("last_main_kernel_ms", ctypes.c_double),
-        ("last_path", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("last_path", ctypes.c_int32), ("last_variant", ctypes.c_int32),
     ]
 
 
@@ -80,6 +80,7 @@ class Stats:
     last_search_ms: float
     last_main_kernel_ms: float
     last_path: int
+    last_variant: int = 0
 
 
 _lib_lock = threading.Lock()
@@ -264,7 +265,7 @@ class Corpus:
     def stats(self) -> Stats:
         s = _FxStats()
         _check(self._lib, self._lib.fx_get_stats(self._h, ctypes.byref(s)))
-        return Stats(**{f: getattr(s, f) for f, _ in _FxStats._fields_ if f != "reserved"})
+        return Stats(**{f: getattr(s, f) for f, _ in _FxStats._fields_})
 
     @property
     def n_rows(self) -> int:

@@ -83,7 +83,8 @@ typedef struct fx_stats {
   double last_search_ms;     /* device time of the last search (CUDA events) */
   double last_main_kernel_ms;/* device time of the dominant kernel of the last search */
   int32_t last_path;         /* 0 = exact scan, 1 = tcgen05 TF32 filter + rerank, 2 = tcgen05 bf16 filter + rerank */
-  int32_t reserved;
+  int32_t last_variant;      /* tcgen05 paths: bit 0 = resident-query kernel (narrow rows; else the streaming kernel),
+                              * bit 1 = thresholds seeded by the sample prepass */
 } fx_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
