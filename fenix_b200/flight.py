@@ -5,7 +5,8 @@ dict {coding, source, column, metric, select, filter, maxval, probes}, reads the
 `target` column of the request stream and answers with one table; `Flight.search`
 (flight.py:242-288) is byte-compatible with the reference client, so either side can be
 swapped independently. do_put / do_get / drop-table / remove are restated because the device
-shard cache must be invalidated when a table changes. IVF actions answer NotImplementedError.
+shard cache must be invalidated when a table changes. IVF actions (make-coder / make-index / drop-index) are
+served: codebook training on the host at ingest time, code assignment and probe ranking on the device.
 
 NOTE (inherited, documented in SURVEY.md §5): commands are pickles - only expose the port to
 trusted clients.
@@ -53,8 +54,9 @@ class Server(fl.FlightServerBase):
     def do_get(self, ctx, ticket):
         names = ticket.ticket.decode().split(":")
         if "coding" in self._view and "column" in self._view:
-            raise NotImplementedError("IVF index reads are outside the exact k-NN path of this build")
-        data = io.table.load(self.root, names)
+            data = io.index.load(self.root, self._view["coding"], names, self._view["column"])
+        else:
+            data = io.table.load(self.root, names)
         if "filter" in self._view:
             data = data.filter(self._view["filter"])
         if "select" in self._view:
@@ -74,12 +76,19 @@ class Server(fl.FlightServerBase):
     def do_action(self, ctx, action):
         config = pickle.loads(action.body.to_pybytes())
         kind = action.type
-        if kind in ("make-coder", "make-index"):
-            raise NotImplementedError("IVF indexes are outside the exact k-NN path of this build")
+        if kind == "make-coder":
+            io.coder.make(self.root, **config)
+        elif kind == "make-index":
+            io.index.make(self.root, **config)
         elif kind == "drop-table":
             io.table.drop(self.root, **config)
         elif kind == "drop-index":
-            pass
+            # the codebook and every sidecar written under its name (flight.py:92-100 of the reference)
+            io.coder.drop(self.root, **config)
+            for path in [*io.index.list(self.root)]:
+                parts = path.split(os.sep)
+                if len(parts) >= 3 and parts[-1] == config["name"]:
+                    io.index.drop(self.root, parts[-1], os.sep.join(parts[:-2]), parts[-2])
         elif kind == "remove":
             io.shards.invalidate(self.root)
             shutil.rmtree(self.root)

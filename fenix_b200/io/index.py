@@ -1,7 +1,6 @@
-"""Exact search orchestration: the drop-in seam `io.index.call`.
+"""Search orchestration: the drop-in seam `io.index.call`, plus the IVF sidecars (`make`, `load`, `list`, `drop`).
 
-Mirrors fenix.io.index.call (src/fenix/io/index/index.py:81-170) for the `coding is None`
-branch: same arguments, same result schema (select columns + `__DISTANCE__` typed as the
+Mirrors fenix.io.index.call (src/fenix/io/index/index.py:81-170): same arguments, same result schema (select columns + `__DISTANCE__` typed as the
 column's value type), same `maxval` edge cases (None or >= row count returns every row in
 table order with the distance attached, index.py:165), same filter-before-distance semantics
 (index.py:161). What changes is where the arithmetic runs: the per-chunk Arrow UDF ->
@@ -10,7 +9,10 @@ libfenix_knn against a device-resident shard set; only the k winning rows are ga
 host. Result rows are ordered by (distance, row position) - the reference's order among equal
 distances is unspecified ("unstable").
 
-The IVF branch (`coding`/`probes`, index.py:113-126) is out of scope and raises.
+The IVF branch (`coding` + `probes`, index.py:113-126) is the same search with one more predicate: the rows
+whose `__CODED_ID__` (sidecar written by `make`, index.py:38-66) is among the query's `probes` best composite
+codes. The codes are ranked by `io.coder.call` (codeword distances on the device), the predicate becomes the row
+mask of the masked exact search - no filtered copy of the corpus is made, unlike index.py:161.
 """
 from __future__ import annotations
 
@@ -20,7 +22,11 @@ import numpy as np
 import pyarrow as pa
 import pyarrow.compute as pc
 
+import os
+
 from .. import knn
+from . import arrow as _arrow
+from . import coder as _coder
 from . import shards as _shards
 from . import table as _table
 from .batcher import MicroBatcher
@@ -91,19 +97,17 @@ def call(
     probes: int | None = None,
     precision: int = knn.PREC_FP32,
 ) -> pa.Table:
-    if coding is not None:
-        raise NotImplementedError("IVF search (coding/probes) is outside the exact k-NN path of this build")
-    if metric is None:
-        raise AssertionError("metric is required")
-    knn.metric_code(metric)  # ValueError on unknown names, as coder.py:50
-
+    if metric is not None:
+        knn.metric_code(metric)  # ValueError on unknown names, as coder.py:50
     if isinstance(source, pa.Table):
         data = source
         shard = _shards.from_chunks(data.column(column))
         owned = True
     else:
-        data = _shards.load_table(root, source)   # raises like table.load when the file is missing
-        shard = _shards.get(root, source, column, data)
+        base = _shards.load_table(root, source)   # raises like table.load when the file is missing
+        shard = _shards.get(root, source, column, base)
+        # with a coding the table carries its `__CODED_ID__` sidecar column (index.py:93-95)
+        data = load(root, coding, source, column) if coding is not None else base
         owned = False
 
     try:
@@ -111,8 +115,31 @@ def call(
         queries = coerce_target(target, typ.list_size)
         batched = queries.shape[0] != 1 or _batched_input(target)
 
+        probe_codes = None
+        if coding is not None and probes is not None:
+            code = _coder.load(root, coding)                       # index.py:113-117
+            if metric is None:
+                metric = code["config"]["metric"]
+            probe_codes = _coder.call(queries, (root, coding), int(probes))   # (Q, probes) composite codes, best first
+        if metric is None:
+            raise AssertionError("metric is required")
+        knn.metric_code(metric)  # ValueError on unknown names, as coder.py:50
+
+        if probe_codes is not None and batched:
+            # one row mask per query: the batched wire extension answers an IVF search query by query
+            parts = []
+            for qi in range(queries.shape[0]):
+                one = call(root, coding, source, column, queries[qi], metric=metric, select=select, filter=filter,
+                           maxval=maxval, probes=probes, precision=precision)
+                parts.append(one.append_column(QUERY_COL, pa.array(np.full(one.num_rows, qi, dtype=np.int32))))
+            return pa.concat_tables(parts).combine_chunks()
+
         out_cols = [*select] if select is not None else data.column_names
         mask = _row_mask(data, column, filter) if filter is not None else None
+        if probe_codes is not None:
+            # `__CODED_ID__ isin(probe codes)` AND the caller's predicate (index.py:119-126)
+            cell = np.isin(data.column(CODE_COL).to_numpy(), probe_codes[0]).astype(np.uint8)
+            mask = cell if mask is None else (mask & cell)
         n_live = int(mask.sum()) if mask is not None else data.num_rows
 
         if not batched and (maxval is None or n_live <= maxval):
@@ -160,17 +187,49 @@ def _batched_input(target) -> bool:
     return False
 
 
-# IVF sidecar management (index.py:19-78) is not part of the exact path.
-def load(*_a, **_k):
-    raise NotImplementedError("IVF index sidecars are outside the exact k-NN path of this build")
+# ---- IVF sidecars (index.py:19-78): <root>/indexes/<source>/<column>/<coding>.arrow, one int64 column ----------
+def sidecar_path(root: str, name: str, source: str, column: str) -> str:
+    return os.path.join(root, LOCATION, source, column, name + ".arrow")
 
 
-make = load
+def load(root: str, name: str, source, column: str) -> pa.Table:
+    """The source table(s) with the `__CODED_ID__` column of coding `name` attached (index.py:19-35)."""
+    if isinstance(source, str):
+        _coder.load(root, name)
+        return _table.join(_shards.load_table(root, source), _arrow.load(sidecar_path(root, name, source, column)), axis=1)
+    if not isinstance(source, Sequence):
+        raise AssertionError("source must be a table name or a sequence of names")
+    return _table.join(*(load(root, name, one, column) for one in source))
+
+
+def make(root: str, name: str, source, column: str) -> pa.Table:
+    """Assign every row of `column` its composite code under coding `name` and write the sidecar, one record batch
+    per record batch of the source (index.py:38-66). The assignment runs on the device (`io.coder.assign`)."""
+    if isinstance(source, str):
+        _coder.load(root, name)
+        table = _shards.load_table(root, source)
+
+        def batches():
+            for chunk in table.column(column).chunks:
+                yield pa.record_batch([pa.array(_coder.assign(root, name, _shards.chunk_rows(chunk)))], names=[CODE_COL])
+
+        _arrow.make(sidecar_path(root, name, source, column),
+                    pa.RecordBatchReader.from_batches(pa.schema({CODE_COL: pa.int64()}), batches()))
+        return load(root, name, source, column)
+    if not isinstance(source, Sequence):
+        raise AssertionError("source must be a table name or a sequence of names")
+    return _table.join(*(make(root, name, one, column) for one in source))
 
 
 def list(root: str):
-    return iter(())
+    base = os.path.join(root, LOCATION)
+    for dirpath, _dirs, files in os.walk(base):
+        for f in sorted(files):
+            if f.endswith(".arrow"):
+                yield os.path.relpath(os.path.join(dirpath, f), base).removesuffix(".arrow")
 
 
 def drop(root: str, name: str, source: str, column: str) -> None:
-    return None
+    path = sidecar_path(root, name, source, column)
+    if os.path.exists(path):
+        os.unlink(path)

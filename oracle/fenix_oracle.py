@@ -6,6 +6,8 @@ A restatement (not a copy) of what the reference computes on this path, function
   from_arrow()  <- src/fenix/io/torch/torch.py:6-10        (values buffer -> (rows, D) tensor)
   call()        <- src/fenix/io/index/index.py:99-111,128-129,133-170
                    (target coercion, schema, per-chunk distance UDF, filter, select_k + take)
+  coder_call()  <- src/fenix/io/coder/coder.py:143-194     (composite IVF codes ranked by summed codeword distance)
+  ivf_call()    <- src/fenix/io/index/index.py:113-126     (`__CODED_ID__ isin(probe codes)` folded into the filter)
 
 Where the arithmetic really lives: third-party wheels absent from /root/reference -
 torch (pinned 2.1.2 in pdm.lock:1772-1773; 2.11.0 in this image) for cdist / normalize / matmul
@@ -34,6 +36,7 @@ import torch.nn.functional as F
 
 DIST_COL = "__DISTANCE__"
 ROW_COL = "__ROW__"
+CODE_COL = "__CODED_ID__"
 
 
 def _cdist_mm(u: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
@@ -115,6 +118,36 @@ def call(
     if maxval is not None and len(data) > maxval:                                       # :165
         data = data.take(pc.select_k_unstable(data, maxval, [(DIST_COL, "ascending")]))  # :166-167
     return data.combine_chunks()                                                        # :170
+
+
+def coder_call(target: torch.Tensor, tensor: torch.Tensor, metric: str, maxval: Optional[int] = None) -> torch.Tensor:
+    """coder.py:143-194 on tensors: target (T, D), codebooks (n, k, D) -> composite codes ranked by the sum of the
+    n codeword distances, best first: (T, maxval) or all (T, k^n). Composite code c uses codeword
+    (c // k^(n-1-j)) % k of codebook j (coder.py:171-181: repeat_interleave / repeat index grids)."""
+    n, k = tensor.shape[0], tensor.shape[1]
+    data = distance(target, tensor.flatten(end_dim=-2), metric).view(-1, n, k)            # :170
+    total = torch.tensor(0)
+    for j in range(n):                                                                    # :171-181
+        grid = torch.arange(0, k).repeat_interleave(k ** (n - j - 1)).repeat(k ** j)
+        total = total + data[:, j, grid]
+    if maxval is not None:
+        return torch.topk(total, maxval, largest=False).indices                           # :184
+    return torch.argsort(total, descending=False)                                         # :186
+
+
+def ivf_call(data: pa.Table, column: str, target, tensor: torch.Tensor, coding_metric: str, metric: Optional[str] = None,
+             select: Optional[Sequence[str]] = None, filter: Optional[pc.Expression] = None,
+             maxval: Optional[int] = None, probes: Optional[int] = None) -> pa.Table:
+    """index.py:81-170 with a coding: `data` already carries `__CODED_ID__` (index.load, :19-35)."""
+    typ = data.schema.field(column).type
+    scalar = _coerce_target(target, typ)
+    if probes is not None:                                                                # :113-126
+        if metric is None:
+            metric = coding_metric
+        codes = coder_call(from_arrow(pa.array([scalar])), tensor, coding_metric, probes)
+        mask = pc.field(CODE_COL).isin(pa.array(codes.reshape(-1).numpy()))
+        filter = mask if filter is None else (filter & mask)
+    return call(data, column, scalar, metric, select=select, filter=filter, maxval=maxval)
 
 
 def search_rows(data: pa.Table, column: str, target, metric: str, k: Optional[int],

@@ -15,6 +15,10 @@ from oracle import brute_force_f64, canonical, search_rows
 
 pytestmark = pytest.mark.gpu
 
+
+def client_root(served):
+    return served[3]
+
 PRECISIONS = {"fp32": knn.PREC_FP32, "scan": knn.PREC_EXACT_SCAN}
 
 
@@ -455,6 +459,58 @@ def test_index_call_matches_oracle_table(ctx, tmp_path):
     assert flipped.column("id").to_pylist() == before.column("id").to_pylist()
 
 
+IVF_CASES = sorted(f[len("ivf_"):-len(".npz")] for f in os.listdir(os.path.join(os.path.dirname(__file__), "golden")) if f.startswith("ivf_"))
+
+
+def _write_reference_coding(root, name, tensor, dim, metric, ksize, nbooks):
+    """A codebook file in the reference's own format (coder.py:120-125)."""
+    import torch
+
+    path = os.path.join(root, "codings", name + ".torch")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as f:
+        torch.save({"tensor": torch.from_numpy(tensor), "column": pa.list_(pa.float32(), dim),
+                    "config": dict(metric=metric, codebook_size=ksize, num_codebooks=nbooks, batch_size=64, num_epochs=2)}, f)
+
+
+@pytest.mark.parametrize("case", IVF_CASES)
+def test_ivf_search_matches_live_reference_outputs(built_library, case, tmp_path):
+    """SURVEY.md section 8f rank 4. Given the codebook the live reference trained (fixture), the product must rank
+    the probe codes, assign the sidecar codes and answer `index.call(coding=, probes=)` like the reference did."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ivf_{case}.npz"))
+    root, dim = str(tmp_path), g["corpus"].shape[1]
+    metric = str(g["coding_metric"])
+    fenix.io.table.make(root, "t", table_of(g["corpus"], int(g["chunk"])).to_reader())
+    _write_reference_coding(root, "cb", g["tensor"], dim, metric, int(g["codebook_size"]), int(g["num_codebooks"]))
+    try:
+        ranked = fenix.io.coder.call(g["queries"], (root, "cb"), None)
+        assert ranked.shape == g["ranked"].shape
+        top = int(g["probes"].max())
+        assert np.array_equal(ranked[:, :top], g["ranked"][:, :top])          # the cells that get probed, in order
+        assert np.array_equal(np.sort(ranked, axis=1), np.sort(g["ranked"], axis=1))
+        joined = fenix.io.index.make(root, "cb", "t", "vector")
+        assert joined.column_names == ["id", "vector", "__CODED_ID__"]
+        assert np.array_equal(joined.column("__CODED_ID__").to_numpy(), g["codes"])
+        assert [len(c) for c in joined.column("__CODED_ID__").chunks] == [len(c) for c in joined.column("id").chunks]
+        flt = golden_filter(int(g["filter_mod"]))
+        for qi, q in enumerate(g["queries"]):
+            for p in g["probes"]:
+                for m in (None, "l2", "cosine", "dot"):
+                    res = fenix.io.index.call(root, "cb", "t", "vector", q, metric=m, select=["id"], filter=flt,
+                                              maxval=int(g["k"]), probes=int(p))
+                    key = f"{m or 'default'}:{qi}:{int(p)}"
+                    assert res.column_names == ["id", "__DISTANCE__"]
+                    assert_same_neighbours(res.column("id").to_numpy(), res.column("__DISTANCE__").to_numpy(),
+                                           g[key + ":id"], g[key + ":dist"], g["corpus"], q, m or metric)
+        # default projection carries the code column, as the joined table does in the reference (index.py:128)
+        res = fenix.io.index.call(root, "cb", "t", "vector", g["queries"][0], metric=metric, maxval=3, probes=2)
+        assert res.column_names == ["id", "vector", "__CODED_ID__", "__DISTANCE__"]
+        assert set(res.column("__CODED_ID__").to_pylist()) <= set(g["ranked"][0, :2].tolist())
+    finally:
+        fenix.io.coder.drop(root, "cb")
+        fenix.io.shards.invalidate(root)
+
+
 class TestFlightDropIn:
     """The reference's own acceptance test (tests/test_flight.py:42-50, 88-114, 151-154) re-run against
     this package, plus result parity it does not check."""
@@ -474,17 +530,17 @@ class TestFlightDropIn:
         source = table_of(corpus, self.BATCH_SIZE)
         client = fenix.Flight("127.0.0.1", self.PORT)
         client.make_table("test/table", source.to_reader())
-        yield client, source, corpus
+        yield client, source, corpus, root
         client.remove()
         server.shutdown()
 
     def test_make_table_roundtrip(self, served):
-        client, source, _ = served
+        client, source, *_ = served
         assert client.read_table("test/table").read_all() == source
 
     @pytest.mark.parametrize("metric", METRICS)
     def test_search_without_index(self, served, metric):
-        client, source, corpus = served
+        client, source, corpus, *_ = served
         target = pc.random(self.VECTOR_SIZE).cast(pa.float32())
         result = client.search(target=target, source="test/table", column="vector", metric=metric, maxval=10)
         assert result.num_rows == 10
@@ -495,7 +551,7 @@ class TestFlightDropIn:
                                ref_rows, ref_dist, corpus, q, metric)
 
     def test_batched_wire_extension(self, served):
-        client, source, corpus = served
+        client, source, corpus, *_ = served
         rng = np.random.default_rng(1)
         qs = rng.random((5, self.VECTOR_SIZE), dtype=np.float32)
         out = client.search(qs, "test/table", "vector", "l2", select=["id"], maxval=3)
@@ -508,8 +564,33 @@ class TestFlightDropIn:
     def test_errors_surface_as_flight_errors(self, served):
         import pyarrow.flight as fl
 
-        client, _, _ = served
+        client, *_ = served
         with pytest.raises(fl.FlightServerError):
             client.search(np.zeros(self.VECTOR_SIZE, np.float32), "nope", "vector", "l2", maxval=3)
         with pytest.raises(AssertionError):
             client.search(np.zeros(self.VECTOR_SIZE, np.float32), "test/table", "vector", "manhattan")
+
+    def test_make_index_and_ivf_search(self, served):
+        """make_index (host k-means + device code assignment) -> search(coding=, probes=): probing every cell equals
+        the exact search, probing few cells returns exactly the best rows of those cells."""
+        client, source, corpus, *_ = served
+        config = dict(metric="l2", codebook_size=4, num_codebooks=2, batch_size=256, num_epochs=1)
+        client.make_index("cb", "test/table", "vector", config)
+        try:
+            joined = client.read_table("test/table", coding="cb", column="vector").read_all()
+            assert joined.column_names == ["id", "vector", "__CODED_ID__"]
+            codes = joined.column("__CODED_ID__").to_numpy()
+            assert codes.min() >= 0 and codes.max() < 16
+            q = corpus[123] + np.float32(0.05)
+            full = client.search(q, "test/table", "vector", "l2", coding="cb", select=["id"], maxval=10, probes=16)
+            exact = client.search(q, "test/table", "vector", "l2", select=["id"], maxval=10)
+            assert full.column("id").to_pylist() == exact.column("id").to_pylist()
+            few = client.search(q, "test/table", "vector", "l2", coding="cb", select=["id", "__CODED_ID__"], maxval=10, probes=2)
+            cells = set(few.column("__CODED_ID__").to_pylist())
+            assert 1 <= len(cells) <= 2
+            live = np.nonzero(np.isin(codes, list(cells)))[0]
+            want_rows, _ = brute_force_f64(corpus[live], q, "l2", 10)
+            assert few.column("id").to_pylist() == live[want_rows[0]].tolist()
+        finally:
+            client.drop_index("cb")
+        assert [*fenix.io.index.list(client_root(served))] == []

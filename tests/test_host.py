@@ -79,8 +79,10 @@ def test_row_mask_follows_expression():
     assert mask.tolist() == [0] * 6 + [1] * 4
 
 
-def test_ivf_branch_is_out_of_scope(tmp_path):
-    with pytest.raises(NotImplementedError):
+def test_ivf_search_needs_its_table_and_codebook(tmp_path):
+    """`coding=` loads the table, the codebook and the sidecar like index.py:93-95; missing files surface as they do
+    in the reference (FileNotFoundError), before anything touches the device."""
+    with pytest.raises(FileNotFoundError):
         fenix.io.index.call(str(tmp_path), "some-coding", "t", "vector", np.zeros(4), metric="l2", probes=4)
 
 
