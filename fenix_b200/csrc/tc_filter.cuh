@@ -50,9 +50,6 @@ constexpr int TC_SPLIT = FENIX_TC_SPLIT;
 #define FENIX_EPI_UNROLL 2                 // unroll factor of the epilogue's chunk-pair loop (1 = rolled, 2 = all four chunks)
 #endif
 constexpr int TC_EPI_UNROLL = FENIX_EPI_UNROLL;
-#ifndef FENIX_TC_PIPE
-#define FENIX_TC_PIPE 0                    // 1: software-pipelined TMEM loads in the epilogue
-#endif
 constexpr int TC_EPI_WARPS = 4 * TC_SPLIT; // 4 warps cover the 128 TMEM lanes; TC_SPLIT groups split the columns
 constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
 constexpr int TC_EPI_FIRST_WARP = 4;
@@ -1625,6 +1622,8 @@ inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan
   (void)st;
   if (s.tau_fixed || s.no_prepass || s.sample_stride > 1 || s.kind != 1 || s.dbg != nullptr) return false;
   if (main_pl.n_kblocks > 4) return false;                 // wide rows: the tensor pipe binds, thresholds are not the issue
+  if (s.epi != 2) return false;                            // a row mask (predicate / IVF cells) of unknown selectivity: the
+                                                           // sample says nothing about how many LIVE rows pass a threshold
   if (const char* e = std::getenv("FENIX_TC_PRE")) { if (std::atoi(e) == 0) return false; }
   double safety = 3.0;
   if (const char* e = std::getenv("FENIX_TC_PRE_SAFETY")) { double f = std::atof(e); if (f >= 1.0 && f <= 64.0) safety = f; }
