@@ -1634,11 +1634,15 @@ inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan
   const int64_t n_tiles_full = (s.n_rows + tile_rows - 1) / tile_rows;
   if (stride < 4 || n_tiles_full / stride < 32) return false;       // shard too small for a sample to pay off
   const int rec_per_tile = main_pl.rq ? 1 : TC_SPLIT;
-  stride = int(std::max<int64_t>(stride, (n_tiles_full * rec_per_tile + 4095) / 4096));   // at most 4096 records per query
+  // at most 4096 records per query (they are held in registers by the tau0 kernel) and 256 MB of records in all
+  const int64_t max_rec = std::min<int64_t>(4096, std::max<int64_t>(64, (int64_t(1) << 26) / std::max(s.n_q, 1)));
+  stride = int(std::max<int64_t>(stride, (n_tiles_full * rec_per_tile + max_rec - 1) / max_rec));
   const int64_t sample_rows = ((n_tiles_full + stride - 1) / stride) * tile_rows;
   *pre = s;
   pre->sample_stride = stride;
-  pre->pre_m = std::max(4, int(safety * double(main_pl.kp) * double(sample_rows) / double(s.n_rows) + 0.5));
+  const double m_exact = safety * double(main_pl.kp) * double(sample_rows) / double(s.n_rows);
+  if (m_exact < 4.0) return false;   // the sample the memory cap allows is too thin for a trustworthy rank statistic
+  pre->pre_m = int(m_exact + 0.5);
   pre->certify = false;
   pre->ev_k0 = nullptr; pre->ev_k1 = nullptr;
   return true;
