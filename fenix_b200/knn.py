@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -150,10 +151,15 @@ class Context:
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         self.device = int(device)
+        self._corpora: "weakref.WeakSet[Corpus]" = weakref.WeakSet()
         _check(self._lib, self._lib.fx_init(self.device, ctypes.byref(self._h)))
 
     def close(self) -> None:
+        """Shut the context down. Shards still alive on it are destroyed first: the C ABI requires every corpus to be
+        destroyed before its context (a corpus handle outliving fx_shutdown would point at freed state)."""
         if getattr(self, "_h", None) is not None and self._h:
+            for corpus in list(getattr(self, "_corpora", ())):
+                corpus.close()
             self._lib.fx_shutdown(self._h)
             self._h = ctypes.c_void_p()
 
@@ -181,6 +187,7 @@ class Corpus:
         self._h = ctypes.c_void_p()
         self._finalized = False
         _check(self._lib, self._lib.fx_corpus_create(ctx._h, self.capacity, self.dim, 0, self.row_base, ctypes.byref(self._h)))
+        ctx._corpora.add(self)
 
     # ---- ingest ----
     def append(self, rows: np.ndarray) -> None:
@@ -273,7 +280,8 @@ class Corpus:
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
-            self._lib.fx_corpus_destroy(self._h)
+            if self.ctx._h:   # the context destroys its shards when it is closed first
+                self._lib.fx_corpus_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self) -> None:  # pragma: no cover - best effort

@@ -269,6 +269,39 @@ def test_resident_query_kernel_and_sample_prepass(ctx, metric, dim, k):
     c.close()
 
 
+@pytest.mark.parametrize("dim", [61, 62, 64, 65, 125, 128, 189, 190, 256])
+def test_shadow_geometry_boundaries(ctx, dim):
+    """The bf16 shadow keeps -|x|^2/2 in three extra K columns: inside the last 64-column block when it has room
+    (dim % 64 <= 61), in a separate block per tile otherwise; rows of up to 3 blocks take the resident-query kernel.
+    Every metric, both kernels (a 300-query and a 40-query batch), against the fp64 scan."""
+    import torch
+
+    n, nq, k = 70_000, 300, 10
+    g = torch.Generator(device="cuda").manual_seed(1000 + dim)
+    x = torch.randn((n, dim), generator=g, device="cuda", dtype=torch.float32)
+    x *= (0.5 + torch.rand((n, 1), generator=g, device="cuda"))          # spread the norms: the L2 term matters
+    q = torch.randn((nq, dim), generator=g, device="cuda", dtype=torch.float32)
+    c = knn.Corpus(ctx, n, dim)
+    torch.cuda.synchronize()
+    c.append_device(x.data_ptr(), n)
+    c.finalize()
+    qh = q.cpu().numpy()
+    sub = np.arange(0, nq, 11)
+    for metric in ("l2", "cosine", "dot"):
+        before = c.stats()
+        rows, dist = c.search(qh, metric, k)
+        st = c.stats()
+        blocks = -(-(dim + (3 if metric == "l2" else 0)) // 64)      # 64-column k-blocks the search multiplies
+        assert st.last_path == 2 and (st.last_variant & 1) == (1 if blocks <= 3 else 0), (metric, st.last_variant)
+        assert st.fallback_queries - before.fallback_queries <= 2
+        rows_s, dist_s = c.search(qh[sub], metric, k, knn.PREC_EXACT_SCAN)
+        assert np.array_equal(rows[sub], rows_s) and np.array_equal(dist[sub], dist_s), metric
+        rows_40, dist_40 = c.search(qh[:40], metric, k)
+        assert (c.stats().last_variant & 1) == 0
+        assert np.array_equal(rows[:40], rows_40) and np.array_equal(dist[:40], dist_40), metric
+    c.close()
+
+
 def test_sample_prepass_with_an_unrepresentative_sample(ctx):
     """Adversarial layout for the threshold prepass: every sampled tile is filled with copies of the queries, so
     each query's sample threshold lands far above anything the rest of the shard offers and the main pass keeps
