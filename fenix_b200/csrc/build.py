@@ -24,7 +24,6 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "-shared",
-    *(["-DFENIX_TC_SPLIT=" + os.environ["FENIX_TC_SPLIT"]] if os.environ.get("FENIX_TC_SPLIT") else []),
     "--expt-relaxed-constexpr",
     *os.environ.get("FENIX_NVCC_EXTRA", "").split(),
 ]

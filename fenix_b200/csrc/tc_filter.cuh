@@ -1,23 +1,24 @@
-// tc_filter.cuh — the tensor-core path: tcgen05/TMEM TF32 GEMM with a fused threshold-filter
-// epilogue (no distance matrix ever reaches HBM), followed by an fp64 rerank + certificate.
+// tc_filter.cuh - the tensor-core path: tcgen05/TMEM GEMM with a fused threshold-filter epilogue (no distance
+// matrix ever reaches HBM), followed by an fp64 rerank + certificate. DESIGN.md section 4 is the narrative.
 //
-//   knn_prep_kernel      pads queries to the TMA pitch, resets per-query state
-//   knn_tc_filter_kernel warp-specialised persistent kernel, one CTA per SM:
-//                          warp 0   TMA producer  (cp.async.bulk.tensor, 128B swizzle, 4 stages)
-//                          warp 1   MMA issuer    (tcgen05.mma kind::tf32, M=128 N=256 K=8, fp32 in TMEM)
-//                          warp 2   TMEM allocator
-//                          warps 4-11 epilogue    (tcgen05.ld 32x32b -> score -> compare with a
-//                                                  per-query running threshold in a register;
-//                                                  rare survivors are appended to an L2-resident
-//                                                  candidate buffer, warp-cooperative radix select
-//                                                  tightens the threshold)
-//   knn_tc_finish_kernel one CTA per query: top-K' of the surviving candidates by approximate score,
-//                        exact (fp64-accumulated) rerank, (distance,row) sort, certificate.
+//   knn_prep_kernel        pads queries to whole tile pairs (fp32 and bf16 copies), resets per-query state
+//   knn_tc_filter_kernel   streaming kernel (any row width): persistent, one CTA per SM
+//                            warp 0     TMA producer  (cp.async.bulk.tensor, 128B swizzle, 4 stages of query + corpus blocks)
+//                            warp 1     MMA issuer    (tcgen05.mma M=128 N=256, kind::f16 on the bf16 shadow or kind::tf32
+//                                                      on the raw rows, fp32 accumulators in TMEM, double-buffered)
+//                            warp 2     TMEM allocator
+//                            warps 4-11 epilogue      (epi_tile / epi_tighten below)
+//   knn_rq_filter_kernel   resident-query kernel (narrow rows, >= 2 query tiles): two query tiles stay in shared memory,
+//                          128-row corpus blocks stream through a deep ring and feed two MMAs each (warps 1 and 3 issue)
+//   MODE 2 of both + knn_tc_tau0_kernel   threshold prepass over a strided sample (narrow rows)
+//   knn_tc_finish_kernel   one CTA per query: top-K' of the surviving candidates by approximate score, exact
+//                          (fp64-accumulated) rerank, (distance,row) sort, certificate
+//   refine_*_kernel        preset-threshold refinement of flagged queries
 //
-// Exactness argument (FX_PREC_FP32): every corpus row that is NOT a candidate has approximate
-// score s^ <= T; |s^ - s| <= E (rigorous TF32 rounding bound from |q|, max|x|, D); so its exact
-// distance is >= f(T + E). If the k-th reranked distance is strictly below that bound the top-k is
-// proven exact; otherwise the query is flagged and recomputed by the fp64 scan (exact_scan.cuh).
+// Exactness argument (FX_PREC_FP32): every corpus row that is NOT a candidate has approximate score s^ <= T;
+// |s^ - s| <= E (rigorous bf16 / TF32 rounding bound from |q|, max|x|, D); so its exact distance is >= f(T + E). If the
+// k-th reranked distance is strictly below that bound the top-k is proven exact; otherwise the query is flagged and
+// settled by the re-run / refinement tiers (fenix_knn.cu), in the last resort by the fp64 scan (exact_scan.cuh).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -39,10 +40,7 @@ constexpr int TC_BK = 32;                  // fp32 elements per k-block = 128 B 
 constexpr int TC_UMMA_K = 8;               // kind::tf32: 32 bytes of K per instruction
 constexpr int TC_STAGES = 4;
 constexpr int TC_ACC_STAGES = 2;           // 2 x 256 TMEM columns = all 512
-#ifndef FENIX_TC_SPLIT
-#define FENIX_TC_SPLIT 2                   // column split of an accumulator among epilogue warp groups (2 or 4)
-#endif
-constexpr int TC_SPLIT = FENIX_TC_SPLIT;
+constexpr int TC_SPLIT = 2;                // two epilogue warps per TMEM lane quadrant, 128 accumulator columns each
 #ifndef FENIX_TC_BACKOFF
 #define FENIX_TC_BACKOFF 1                 // 1: producer / MMA polling loops sleep between polls
 #endif
