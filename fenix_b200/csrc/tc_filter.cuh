@@ -41,9 +41,6 @@ constexpr int TC_UMMA_K = 8;               // kind::tf32: 32 bytes of K per inst
 constexpr int TC_STAGES = 4;
 constexpr int TC_ACC_STAGES = 2;           // 2 x 256 TMEM columns = all 512
 constexpr int TC_SPLIT = 2;                // two epilogue warps per TMEM lane quadrant, 128 accumulator columns each
-#ifndef FENIX_TC_BACKOFF
-#define FENIX_TC_BACKOFF 1                 // 1: producer / MMA polling loops sleep between polls
-#endif
 #ifndef FENIX_EPI_UNROLL
 #define FENIX_EPI_UNROLL 2                 // unroll factor of the epilogue's chunk-pair loop (1 = rolled, 2 = all four chunks)
 #endif
@@ -151,9 +148,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         "selp.u32 %0, 1, 0, p;\n\t"
         "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (done) break;
-#if FENIX_TC_BACKOFF
-    __nanosleep(ns);
-#endif
+    if (ns) __nanosleep(ns);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -304,6 +299,9 @@ struct TcParams {
   const unsigned char* xb; // base of the tiled bf16 shadow in use (L2 prefetch), or null
   int pf_tiles;           // L2 prefetch distance in tiles (0: off): the TMA ring only covers ~2 tiles, far less than a DRAM miss
   int rq_stages;          // resident-query kernel: depth of the corpus-block ring
+  uint32_t sleep_ns;      // producer / MMA polling loops sleep this long between polls (0: spin). Sleeping keeps their
+                          // spin loops out of the epilogue warps' issue slots where the epilogue binds (narrow rows);
+                          // where the tensor pipe binds (wide rows) a late wake-up costs ~2 % instead
   int kp;                 // K': candidates kept per (query, unit-half) selection
   int cap;                // candidate buffer capacity per epilogue thread (512 or 1024)
   const float* hx;        // [n_rows padded to 256] -0.5|x|^2
@@ -577,13 +575,13 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const int t = tv * p.tile_stride;
           if (METRIC != 2) {
             // per-column norm terms of this tile ride along, one buffer per accumulator stage
-            mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 64);
+            mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, p.sleep_ns);
             mbar_expect_tx(&norm_full[acc], TC_NORM_BYTES);
             const float* src = (METRIC == 0 ? p.hx : p.rx) + size_t(t) * TC_BN;
             bulk_load_1d(norm_smem + acc * TC_BN, src, TC_NORM_BYTES, &norm_full[acc]);
           }
           for (int kb = 0; kb < p.n_kblocks; ++kb) {
-            mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
+            mbar_wait_backoff(&empty_bar[stage], phase ^ 1, p.sleep_ns);
             mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
             unsigned char* a_dst = tiles + stage * TC_STAGE_BYTES;
             constexpr int kElemsPerBlock = KIND == 0 ? TC_BK : 2 * TC_BK;
@@ -622,7 +620,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
         const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_vtiles, t0 + p.tiles_per_slice);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, 32);
+          mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, p.sleep_ns >> 1);
           const uint32_t d_tmem = tmem_u + uint32_t(acc * TC_BN);
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
@@ -797,7 +795,7 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int qp = u % n_qp, slice = u / n_qp;
         const int t0 = slice * p.tiles_per_slice, t1 = min(n_t128, t0 + p.tiles_per_slice);
         // the unit's two query tiles (the previous unit's MMAs must have retired first)
-        mbar_wait_backoff(a_empty, a_phase ^ 1, 64);
+        mbar_wait_backoff(a_empty, a_phase ^ 1, p.sleep_ns);
         mbar_expect_tx(a_full, uint32_t(2 * p.n_kblocks) * RQ_BLOCK_BYTES);
         for (int qt = 0; qt < 2; ++qt)
           for (int kb = 0; kb < p.n_kblocks; ++kb)
@@ -807,15 +805,15 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const int t = tv * p.tile_stride;
           if (METRIC != 2) {
             // per-row terms of this tile, one buffer per accumulator stage; both query-tile groups must have left it
-            mbar_wait_backoff(&tmem_empty[acc * 2 + 0], acc_phase ^ 1, 64);
-            mbar_wait_backoff(&tmem_empty[acc * 2 + 1], acc_phase ^ 1, 64);
+            mbar_wait_backoff(&tmem_empty[acc * 2 + 0], acc_phase ^ 1, p.sleep_ns);
+            mbar_wait_backoff(&tmem_empty[acc * 2 + 1], acc_phase ^ 1, p.sleep_ns);
             mbar_expect_tx(&norm_full[acc], RQ_NORM_BYTES);
             bulk_load_1d(norm_smem + acc * RQ_BN, p.hx + size_t(t) * RQ_BN, RQ_NORM_BYTES, &norm_full[acc]);
           }
           // corpus tile t = rows [128 t, 128 t + 128) = half (t & 1) of the shadow's 256-row block t >> 1
           const int blk = t >> 1, hrow = (t & 1) * RQ_BN;
           for (int kb = 0; kb < p.n_kblocks; ++kb) {
-            mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
+            mbar_wait_backoff(&empty_bar[stage], phase ^ 1, p.sleep_ns);
             mbar_expect_tx(&full_bar[stage], RQ_BLOCK_BYTES);
             const int line = (kb < p.n_kb_data ? (blk * p.n_kb_data + kb) * TC_BN : p.aug_line0 + blk * TC_BN) + hrow;
             tma_load_2d(&map_x, &full_bar[stage], b_ring + stage * RQ_BLOCK_BYTES, 0, line);
@@ -854,7 +852,7 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_wait(a_full, a_phase);
         a_phase ^= 1;
         for (int t = t0; t < t1; ++t) {
-          mbar_wait_backoff(&tmem_empty[acc * 2 + qt], acc_phase ^ 1, 32);
+          mbar_wait_backoff(&tmem_empty[acc * 2 + qt], acc_phase ^ 1, p.sleep_ns >> 1);
           const uint32_t d_tmem = tmem_u + uint32_t((acc * 2 + qt) * RQ_BN);
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
@@ -1667,6 +1665,7 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   p.pf_tiles = 0;   // off: measured neutral where operands come from L2 (C2, C4) and 1.9x slower where HBM binds (C5)
   if (const char* e = std::getenv("FENIX_TC_PF")) p.pf_tiles = p.xb ? std::max(0, std::atoi(e)) : 0;
   p.kp = pl.kp_list; p.cap = pl.cap;
+  p.sleep_ns = pl.n_kblocks >= 6 ? 0u : 64u;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
   p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
   if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);
