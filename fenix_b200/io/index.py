@@ -39,6 +39,13 @@ QUERY_COL: str = "__QUERY__"
 LOCATION: str = "indexes"
 
 
+def _distance_array(dist: np.ndarray, value_type: pa.DataType) -> pa.Array:
+    """`__DISTANCE__` is typed like the column's values (index.py:153)."""
+    if value_type == pa.float16():
+        return pa.array(dist.astype(np.float16), type=value_type)
+    return pa.array(dist, type=value_type)
+
+
 def _is_tensor(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "numpy")
 
@@ -145,7 +152,7 @@ def call(
         if not batched and (maxval is None or n_live <= maxval):
             # every (surviving) row, table order, distance attached (index.py:162-165)
             dist = shard.distances(queries[0], metric)
-            out = data.select(out_cols).append_column(DIST_COL, pa.array(dist, type=typ.value_type))
+            out = data.select(out_cols).append_column(DIST_COL, _distance_array(dist, typ.value_type))
             if mask is not None:
                 out = out.filter(pa.array(mask.view(np.bool_)))
             return out.combine_chunks()
@@ -167,7 +174,7 @@ def call(
         keep = rows.reshape(-1) >= 0
         flat_rows = rows.reshape(-1)[keep]
         out = data.select(out_cols).take(pa.array(flat_rows, type=pa.int64()))
-        out = out.append_column(DIST_COL, pa.array(dist.reshape(-1)[keep], type=typ.value_type))
+        out = out.append_column(DIST_COL, _distance_array(dist.reshape(-1)[keep], typ.value_type))
         if batched:
             qid = np.repeat(np.arange(rows.shape[0], dtype=np.int32), rows.shape[1])[keep]
             out = out.append_column(QUERY_COL, pa.array(qid, type=pa.int32()))

@@ -48,12 +48,17 @@ def chunk_rows(chunk: pa.FixedSizeListArray) -> np.ndarray:
     typ = chunk.type
     if not pa.types.is_fixed_size_list(typ):
         raise TypeError(f"vector column must be FixedSizeList<float32>[D], got {typ}")
-    if typ.value_type != pa.float32():
-        raise NotImplementedError(f"only float32 embedding columns are device-resident (got {typ.value_type})")
     d = typ.list_size
     vals = chunk.values.to_numpy(zero_copy_only=True)
     lo = chunk.offset * d
-    return vals[lo: lo + len(chunk) * d].reshape(len(chunk), d)
+    rows = vals[lo: lo + len(chunk) * d].reshape(len(chunk), d)
+    if typ.value_type == pa.float32():
+        return rows
+    if typ.value_type in (pa.float16(), pa.float64()):
+        # shards are float32 (north_star); other float widths are converted once, at upload. The reference computes
+        # in the column's own type (index.py:133-159), so float64 columns agree to float32 rounding, not bit for bit.
+        return rows.astype(np.float32)
+    raise NotImplementedError(f"embedding columns must be float16 / float32 / float64 (got {typ.value_type})")
 
 
 @dataclass
@@ -125,8 +130,8 @@ def from_chunks(column: pa.ChunkedArray, device_ids: Optional[Sequence[int]] = N
     typ = column.type
     if not pa.types.is_fixed_size_list(typ):
         raise TypeError(f"vector column must be FixedSizeList<float32>[D], got {typ}")
-    if typ.value_type != pa.float32():
-        raise NotImplementedError(f"only float32 embedding columns are device-resident (got {typ.value_type})")
+    if typ.value_type not in (pa.float16(), pa.float32(), pa.float64()):
+        raise NotImplementedError(f"embedding columns must be float16 / float32 / float64 (got {typ.value_type})")
     dim, n = typ.list_size, len(column)
     devs = list(device_ids) if device_ids is not None else devices()
     world = max(1, min(len(devs), max(n, 1)))

@@ -333,6 +333,37 @@ def test_sample_prepass_with_an_unrepresentative_sample(ctx):
     c.close()
 
 
+@pytest.mark.parametrize("value_type", ["float64", "float16"])
+def test_other_float_widths_of_the_vector_column(built_library, value_type, tmp_path):
+    """float64 / float16 embedding columns: converted to float32 shards at upload, `__DISTANCE__` typed like the
+    column (index.py:153). float64: against the oracle (which, like the reference, computes in float64) at the
+    parity bar; float16 (the reference's CPU path has no half cdist): against the fp64 adjudicator."""
+    rng = np.random.default_rng(17)
+    n, d, k = 6000, 48, 10
+    corpus = rng.standard_normal((n, d)).astype(value_type)
+    queries = rng.standard_normal((5, d)).astype(value_type)
+    vec = pa.FixedSizeListArray.from_arrays(pa.array(corpus.reshape(-1)), d)
+    table = pa.table({"id": pa.array(np.arange(n, dtype=np.int64)), "vector": vec})
+    root = str(tmp_path)
+    fenix.io.table.make(root, "t", table.to_reader())
+    try:
+        for metric in ("l2", "cosine", "dot"):
+            for q in queries:
+                res = fenix.io.index.call(root, None, "t", "vector", q, metric=metric, select=["id"], maxval=k)
+                assert res.schema.field("__DISTANCE__").type == vec.type.value_type
+                got_rows, got_dist = res.column("id").to_numpy(), res.column("__DISTANCE__").to_numpy().astype(np.float64)
+                if value_type == "float64":
+                    ref_rows, ref_dist = search_rows(table, "vector", q, metric, k)
+                    assert_same_neighbours(got_rows, got_dist.astype(np.float32), ref_rows, ref_dist.astype(np.float32),
+                                           corpus.astype(np.float32), q.astype(np.float32), metric)
+                else:
+                    want_rows, want_dist = brute_force_f64(corpus.astype(np.float32), q.astype(np.float32), metric, k)
+                    assert np.array_equal(got_rows, want_rows[0])
+                    assert np.allclose(got_dist, want_dist[0], rtol=2e-3, atol=2e-3)   # the column type rounds the answer
+    finally:
+        fenix.io.shards.invalidate(root)
+
+
 def test_tensor_core_path_runs_and_certifies(ctx):
     """fp32 mode must take the tcgen05 path on ordinary data (no silent fallback to the scan) and the
     certificate must hold for (nearly) every query; tf32 mode reports its recall."""

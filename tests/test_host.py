@@ -51,8 +51,19 @@ def test_chunk_rows_is_zero_copy_and_honours_offset():
     assert not view.flags.owndata
     sl = arr.slice(3, 4)
     assert np.array_equal(shards.chunk_rows(sl), corpus[3:7])
+
+
+def test_chunk_rows_converts_other_float_widths():
+    """float16 / float64 columns become float32 rows at upload (one conversion per table version); anything else
+    is refused."""
+    for typ, npt in ((pa.float64(), np.float64), (pa.float16(), np.float16)):
+        x = np.arange(12, dtype=npt).reshape(3, 4)
+        arr = pa.FixedSizeListArray.from_arrays(pa.array(x.reshape(-1), type=typ), 4)
+        rows = shards.chunk_rows(arr.slice(1))
+        assert rows.dtype == np.float32 and np.array_equal(rows, x[1:].astype(np.float32))
+    ints = pa.FixedSizeListArray.from_arrays(pa.array(np.arange(8, dtype=np.int32)), 4)
     with pytest.raises(NotImplementedError):
-        shards.chunk_rows(pa.FixedSizeListArray.from_arrays(pa.array(np.zeros(8)), 4))  # float64 column
+        shards.chunk_rows(ints)
 
 
 def test_coerce_target_forms():
