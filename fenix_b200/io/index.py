@@ -46,6 +46,30 @@ def _distance_array(dist: np.ndarray, value_type: pa.DataType) -> pa.Array:
     return pa.array(dist, type=value_type)
 
 
+def take_rows(data: pa.Table, rows: np.ndarray) -> pa.Table:
+    """`data.take(rows)` (index.py:166) for a FEW rows of a table with MANY chunks. pyarrow's Table.take concatenates
+    the chunks of a nested column first: 4.7 ms per query for the 10 winning rows of a 100k x 128 table in 100
+    record batches (the vector column is gathered by default), against 0.1 ms for the search itself. Nested / variable
+    width columns are therefore gathered row by row (bisection to the chunk, one-row slices, one concatenation);
+    primitive columns keep the library routine, which is cheap for them."""
+    rows = np.asarray(rows, dtype=np.int64)
+    if data.num_rows == 0 or len(rows) > 256 or len(rows) * 8 > data.num_rows:
+        return data.take(pa.array(rows, type=pa.int64()))
+    index = pa.array(rows, type=pa.int64())
+    columns = []
+    for col in data.columns:
+        if pa.types.is_primitive(col.type) or col.num_chunks <= 4:
+            columns.append(col.take(index))
+            continue
+        chunks = col.chunks
+        bounds = np.cumsum([0] + [len(c) for c in chunks])
+        which = np.searchsorted(bounds, rows, side="right") - 1
+        local = rows - bounds[which]
+        columns.append(pa.concat_arrays([chunks[c].slice(int(i), 1) for c, i in zip(which, local)])
+                       if len(rows) else pa.array([], type=col.type))
+    return pa.Table.from_arrays(columns, schema=data.schema)
+
+
 def _is_tensor(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "numpy")
 
@@ -173,7 +197,7 @@ def call(
 
         keep = rows.reshape(-1) >= 0
         flat_rows = rows.reshape(-1)[keep]
-        out = data.select(out_cols).take(pa.array(flat_rows, type=pa.int64()))
+        out = take_rows(data.select(out_cols), flat_rows)
         out = out.append_column(DIST_COL, _distance_array(dist.reshape(-1)[keep], typ.value_type))
         if batched:
             qid = np.repeat(np.arange(rows.shape[0], dtype=np.int32), rows.shape[1])[keep]

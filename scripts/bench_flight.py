@@ -40,6 +40,8 @@ ours = {}
 def ours_single(i):
     ours[i] = client.search(queries[i], "c1", "vector", "l2", select=["id"], maxval=K)
 run("fenix_b200 Flight, 1 query per RPC (GPU)", NQ, ours_single)
+run("fenix_b200 Flight, 1 query per RPC, default select (the 10 winning vectors are gathered and returned)", NQ,
+    lambda i: client.search(queries[i], "c1", "vector", "l2", maxval=K))
 client.search(queries, "c1", "vector", "l2", select=["id"], maxval=K)   # warm-up (scratch growth for a 1000-query batch)
 t0 = time.perf_counter()
 for _ in range(5):

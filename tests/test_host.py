@@ -83,6 +83,19 @@ def test_coerce_target_forms():
         ix.coerce_target(np.ones(5), 6)
 
 
+def test_take_rows_equals_table_take():
+    rng = np.random.default_rng(0)
+    corpus = rng.standard_normal((1000, 6), dtype=np.float32)
+    t = table_of(corpus, 64)
+    for rows in ([5, 999, 0, 64, 63, 128, 5], [], [7], list(range(990, 1000))):
+        rows = np.array(rows, dtype=np.int64)
+        got = ix.take_rows(t, rows)
+        assert got.schema == t.schema
+        assert got.combine_chunks() == t.take(pa.array(rows, type=pa.int64())).combine_chunks()
+    big = rng.integers(0, 1000, 500)          # many rows: falls back to Table.take
+    assert ix.take_rows(t, big).combine_chunks() == t.take(pa.array(big)).combine_chunks()
+
+
 def test_row_mask_follows_expression():
     corpus = np.zeros((10, 4), dtype=np.float32)
     t = table_of(corpus, 4)
