@@ -302,6 +302,37 @@ def test_shadow_geometry_boundaries(ctx, dim):
     c.close()
 
 
+@pytest.mark.parametrize("nq,k", [(129, 1), (257, 256), (300, 37)])
+def test_resident_query_kernel_edges(ctx, nq, k):
+    """Query counts that leave a tile (almost) empty, k = 1 and a large k, and a row mask (the resident-query
+    kernel's additive-term variant; masked searches take no prepass) - all against the fp64 scan."""
+    import torch
+
+    n, dim = 120_000, 96
+    g = torch.Generator(device="cuda").manual_seed(5 + nq)
+    x = torch.randn((n, dim), generator=g, device="cuda", dtype=torch.float32)
+    q = torch.randn((nq, dim), generator=g, device="cuda", dtype=torch.float32)
+    c = knn.Corpus(ctx, n, dim)
+    torch.cuda.synchronize()
+    c.append_device(x.data_ptr(), n)
+    c.finalize()
+    qh = q.cpu().numpy()
+    mask = (np.random.default_rng(nq).random(n) < 0.4).astype(np.uint8)
+    sub = np.unique(np.concatenate([np.arange(0, nq, 17), [nq - 1]]))
+    for metric in ("l2", "cosine", "dot"):
+        rows, dist = c.search(qh, metric, k)
+        # the prepass needs >= 32 sampled tiles at a stride of ~3 K' / 16: k = 256 is too large for this shard
+        assert c.stats().last_variant == (3 if k <= 37 else 1), "resident-query kernel expected"
+        rows_s, dist_s = c.search(qh[sub], metric, k, knn.PREC_EXACT_SCAN)
+        assert np.array_equal(rows[sub], rows_s) and np.array_equal(dist[sub], dist_s), metric
+        rows_m, dist_m = c.search(qh, metric, k, knn.PREC_FP32, row_mask=mask)
+        assert c.stats().last_variant == 1, "masked: resident-query kernel, no prepass"
+        assert mask[rows_m].all()
+        rows_ms, dist_ms = c.search(qh[sub], metric, k, knn.PREC_EXACT_SCAN, row_mask=mask)
+        assert np.array_equal(rows_m[sub], rows_ms) and np.array_equal(dist_m[sub], dist_ms), metric
+    c.close()
+
+
 def test_sample_prepass_with_an_unrepresentative_sample(ctx):
     """Adversarial layout for the threshold prepass: every sampled tile is filled with copies of the queries, so
     each query's sample threshold lands far above anything the rest of the shard offers and the main pass keeps
