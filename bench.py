@@ -240,7 +240,7 @@ def run_ours(args, cfg: dict) -> dict:
 
     from fenix_b200 import knn
     from fenix_b200.csrc.build import build as build_lib
-    from fenix_b200.dist import ShardedSearcher, shard_bounds
+    from fenix_b200.dist import ReplicaSearcher, ShardedSearcher, shard_bounds
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -263,11 +263,16 @@ def run_ours(args, cfg: dict) -> dict:
         torch.cuda.synchronize(device)
 
     ctx = knn.Context(local)
-    lo, hi = shard_bounds(cfg["n"], world, rank)
+    # N > 1: row-shard the corpus, or - small corpora with big batches - replicate it and split the query batch
+    par = args.parallelism
+    if par == "auto":
+        par = "queries" if 8.0 * cfg["n"] * cfg["d"] <= 8e9 and cfg["q"] // max(world, 1) >= 256 else "rows"
+    by_queries = par == "queries" and world > 1
+    lo, hi = (0, cfg["n"]) if by_queries else shard_bounds(cfg["n"], world, rank)
     t_build = time.perf_counter()
     corpus = build_shard(cfg, ctx, lo, hi, device)
     t_build = time.perf_counter() - t_build
-    searcher = ShardedSearcher(corpus)
+    searcher = ReplicaSearcher(corpus) if by_queries else ShardedSearcher(corpus)
     metric, k, n_q, d = knn.metric_code(cfg["metric"]), cfg["k"], cfg["q"], cfg["d"]
     prec = {"fp32": knn.PREC_FP32, "tf32": knn.PREC_TF32, "scan": knn.PREC_EXACT_SCAN}[args.precision]
 
@@ -296,7 +301,7 @@ def run_ours(args, cfg: dict) -> dict:
     elapsed = time.perf_counter() - t0
     st1 = corpus.stats()
     clocks = sampler.stop() if rank == 0 else None
-    launches = st1.kernel_launches - st0.kernel_launches + (args.steps if world > 1 else 0)
+    launches = st1.kernel_launches - st0.kernel_launches + (args.steps if world > 1 and not by_queries else 0)   # + merge kernels
     fallback = st1.fallback_queries - st0.fallback_queries
     refined = st1.refined_queries - st0.refined_queries
 
@@ -345,10 +350,11 @@ def run_ours(args, cfg: dict) -> dict:
     if rank == 0:
         pk = peaks()
         n_shard = hi - lo
-        flops = 2.0 * n_q * n_shard * d
+        n_q_rank = -(-n_q // world) if by_queries else n_q     # queries one launch of this rank answers
+        flops = 2.0 * n_q_rank * n_shard * d
         elem = 2.0 if path == 2 else 4.0     # the bf16 filter streams the bf16 shadow, otherwise the fp32 rows
-        bytes_alg = elem * n_shard * d + 4.0 * n_q * d + 12.0 * n_q * k
-        tensor_bound = path >= 1 and n_q >= (420 if path == 2 else 210)
+        bytes_alg = elem * n_shard * d + 4.0 * n_q_rank * d + 12.0 * n_q_rank * k
+        tensor_bound = path >= 1 and n_q_rank >= (420 if path == 2 else 210)
         if tensor_bound:
             achieved = flops / (k_ms * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
@@ -378,7 +384,7 @@ def run_ours(args, cfg: dict) -> dict:
             "dtype": "f32" if args.precision != "tf32" else "tf32", "data": "synthetic",
             "config": {
                 "workload": f"{args.config}: {cfg['label']}", "n_rows": cfg["n"], "dim": d, "metric": cfg["metric"], "k": k,
-                "queries_per_step": n_q, "precision_mode": args.precision, "parallelism": f"row-shard x{world}",
+                "queries_per_step": n_q, "precision_mode": args.precision, "parallelism": (f"replicated corpus, query batch split x{world}" if by_queries else f"row-shard x{world}"),
                 "l2_policy": "corpus shard is larger than L2 (126 MB), no flush needed" if 4.0 * n_shard * d > 2.5e8
                 else "corpus shard fits in L2: steady-state (warm L2) timing",
                 "path": {0: "fp64 exact scan (CUDA cores)", 1: "tcgen05 TF32 filter + fp64 rerank + certificate",
@@ -387,7 +393,7 @@ def run_ours(args, cfg: dict) -> dict:
             },
             "clocks": clocks,
             "e2e": {"value": n_q / (e2e_elapsed / args.steps), "unit": "queries/s",
-                    "api": "fx_search (C ABI, pinned host buffers)" if world == 1 else "fenix_b200.dist.ShardedSearcher.search_host",
+                    "api": "fx_search (C ABI, pinned host buffers)" if world == 1 else f"fenix_b200.dist.{type(searcher).__name__}.search_host",
                     "h2d_bytes_per_step": int(h_q.numel() * 4) * world, "d2h_bytes_per_step": int(n_q * k * 12),
                     "ms_per_step": e2e_elapsed / args.steps * 1e3},
             "gpu_launches": int(launches),
@@ -436,6 +442,9 @@ def main() -> None:
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "scan"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "rows", "queries"],
+                    help="N > 1: row-shard the corpus, or replicate it and split the query batch (auto: replicate when the "
+                         "corpus and its shadows take <= 8 GB and every rank still gets >= 256 queries)")
     ap.add_argument("--rows", type=int, default=0, help="tuning only: override the corpus row count of the config")
     ap.add_argument("--queries", type=int, default=0, help="tuning only: override the query batch of the config")
     args = ap.parse_args()

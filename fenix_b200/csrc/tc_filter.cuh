@@ -1724,7 +1724,8 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim, s.kind); f.c_add = tc_c_add(s.dim, s.kind == 1 && s.aug); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
   const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + size_t(FIN_POOL) * 8 + 16;
   // many short lists per query (small batches split over all SMs): more warps sweep them in parallel
-  const int fin_threads = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices > 32 ? 1024 : 256;
+  int fin_threads = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices > 32 ? 1024 : 256;
+  if (const char* e = std::getenv("FENIX_FIN_THREADS")) { int f = std::atoi(e); if (f == 128 || f == 256 || f == 512 || f == 1024) fin_threads = f; }
   knn_tc_finish_kernel<<<s.n_q, fin_threads, fin_smem, s.stream>>>(f);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tensor-core path launch failed: ") + cudaGetErrorString(e); return false; }

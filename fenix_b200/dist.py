@@ -1,4 +1,11 @@
-"""Row-sharded multi-GPU search: one process per GPU (torch.distributed), one exchange step.
+"""Multi-GPU search: one process per GPU (torch.distributed), one exchange step. Two partitionings:
+
+* `ShardedSearcher` - the corpus is ROW-sharded (the default; large corpora): described below;
+* `ReplicaSearcher` - the corpus is REPLICATED and the QUERY batch is split (small corpora / huge batches, SURVEY.md
+  section 8e "query-sharding"): each rank answers its contiguous slice of the batch against the whole corpus and the
+  slices are all-gathered; nothing to merge.
+
+Row-sharded search:
 
 New relative to the reference (it has no parallelism): rank r owns the
 contiguous rows [r*ceil(N/W), min(N,(r+1)*ceil(N/W))) so that global row = base + local row and
@@ -79,6 +86,58 @@ class ShardedSearcher:
     def search_host(self, h_queries: torch.Tensor, metric: int, k: int, precision: int = knn.PREC_FP32,
                     h_rows: Optional[torch.Tensor] = None, h_dist: Optional[torch.Tensor] = None):
         """End-to-end form: pinned host queries in, pinned host results out (H2D/D2H included)."""
+        d_q = h_queries.to(self.device, non_blocking=True)
+        rows, dist = self.search_device(d_q, metric, k, precision)
+        if h_rows is None:
+            return rows.cpu(), dist.cpu()
+        h_rows.copy_(rows, non_blocking=True)
+        h_dist.copy_(dist, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h_rows, h_dist
+
+
+def gather_slices(rows: torch.Tensor, dist: torch.Tensor, n_q: int, group=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """All-gather per-rank result slices ([per, k] each, `per` = ceil(n_q / W), short slices padded) into the
+    results of the whole batch, [n_q, k], in query order."""
+    world = td.get_world_size(group)
+    packed = pack_candidates(rows, dist)                                  # [2, per, k]
+    out = torch.empty((world * 2, *packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    td.all_gather_into_tensor(out, packed, group=group)
+    g_rows, g_dist = unpack_candidates(out.view(world, *packed.shape))    # [W, per, k]
+    k = rows.shape[1]
+    return g_rows.reshape(-1, k)[:n_q].contiguous(), g_dist.reshape(-1, k)[:n_q].contiguous()
+
+
+class ReplicaSearcher:
+    """Replicated corpus, query batch split over the ranks. All ranks must call `search` together with the SAME
+    batch; every rank returns the results of the whole batch."""
+
+    def __init__(self, corpus: knn.Corpus, group=None) -> None:
+        self.corpus = corpus
+        self.group = group
+        self.world = td.get_world_size(group) if td.is_initialized() else 1
+        self.rank = td.get_rank(group) if td.is_initialized() else 0
+        self.device = torch.device("cuda", corpus.ctx.device)
+        self.merge_launches = 0
+
+    def search_device(self, d_queries: torch.Tensor, metric: int, k: int,
+                      precision: int = knn.PREC_FP32) -> tuple[torch.Tensor, torch.Tensor]:
+        n_q = d_queries.shape[0]
+        per = -(-n_q // self.world)
+        lo, hi = shard_bounds(n_q, self.world, self.rank)
+        rows = torch.full((per, k), -1, dtype=torch.int64, device=self.device)
+        dist = torch.full((per, k), float("inf"), dtype=torch.float32, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        if hi > lo:
+            mine = d_queries[lo:hi].contiguous()
+            torch.cuda.current_stream(self.device).synchronize()
+            self.corpus.search_device(mine.data_ptr(), hi - lo, metric, k, precision, rows.data_ptr(), dist.data_ptr())
+        if self.world == 1:
+            return rows[:n_q], dist[:n_q]
+        return gather_slices(rows, dist, n_q, self.group)
+
+    def search_host(self, h_queries: torch.Tensor, metric: int, k: int, precision: int = knn.PREC_FP32,
+                    h_rows: Optional[torch.Tensor] = None, h_dist: Optional[torch.Tensor] = None):
         d_q = h_queries.to(self.device, non_blocking=True)
         rows, dist = self.search_device(d_q, metric, k, precision)
         if h_rows is None:

@@ -76,3 +76,35 @@ def test_two_rank_gloo_gather_and_merge():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _replica_worker(rank, world, port, out):
+    from oracle import brute_force_f64
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        corpus = rng.standard_normal((500, 8), dtype=np.float32)
+        queries = rng.standard_normal((7, 8), dtype=np.float32)      # 7 queries over 2 ranks: slices of 4 and 3
+        k = 5
+        per = -(-len(queries) // world)
+        lo, hi = fdist.shard_bounds(len(queries), world, rank)
+        rows = np.full((per, k), -1, dtype=np.int64)
+        dist = np.full((per, k), np.inf, dtype=np.float32)
+        rows[: hi - lo], dist[: hi - lo] = brute_force_f64(corpus, queries[lo:hi], "dot", k)
+        g_rows, g_dist = fdist.gather_slices(torch.from_numpy(rows), torch.from_numpy(dist), len(queries))
+        want_rows, want_dist = brute_force_f64(corpus, queries, "dot", k)
+        assert np.array_equal(g_rows.numpy(), want_rows) and np.array_equal(g_dist.numpy(), want_dist)
+        out[rank] = True
+    finally:
+        td.destroy_process_group()
+
+
+def test_two_rank_gloo_query_sharded_gather():
+    """Replicated corpus, split query batch: the gathered slices are the whole batch in query order."""
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_replica_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
