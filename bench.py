@@ -312,7 +312,10 @@ def run_ours(args, cfg: dict) -> dict:
         if world == 1:
             corpus.search_raw(h_q.data_ptr(), n_q, metric, k, prec, h_rows.data_ptr(), h_dist.data_ptr())
         else:
-            searcher.search_host(h_q, metric, k, prec, h_rows, h_dist)
+            if by_queries:   # each rank uploads its slice of the batch; the gathered result is read back on rank 0
+                searcher.search_host(h_q, metric, k, prec, h_rows, h_dist, result_rank=0)
+            else:
+                searcher.search_host(h_q, metric, k, prec, h_rows, h_dist)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -394,7 +397,7 @@ def run_ours(args, cfg: dict) -> dict:
             "clocks": clocks,
             "e2e": {"value": n_q / (e2e_elapsed / args.steps), "unit": "queries/s",
                     "api": "fx_search (C ABI, pinned host buffers)" if world == 1 else f"fenix_b200.dist.{type(searcher).__name__}.search_host",
-                    "h2d_bytes_per_step": int(h_q.numel() * 4) * world, "d2h_bytes_per_step": int(n_q * k * 12),
+                    "h2d_bytes_per_step": int(h_q.numel() * 4) * (1 if by_queries else world), "d2h_bytes_per_step": int(n_q * k * 12),
                     "ms_per_step": e2e_elapsed / args.steps * 1e3},
             "gpu_launches": int(launches),
             "roofline": roof,

@@ -122,24 +122,35 @@ class ReplicaSearcher:
 
     def search_device(self, d_queries: torch.Tensor, metric: int, k: int,
                       precision: int = knn.PREC_FP32) -> tuple[torch.Tensor, torch.Tensor]:
+        """d_queries: the WHOLE batch, float32 [Q, D] on this rank's GPU. Returns the results of the whole batch."""
         n_q = d_queries.shape[0]
-        per = -(-n_q // self.world)
         lo, hi = shard_bounds(n_q, self.world, self.rank)
+        return self._search_slice(d_queries[lo:hi].contiguous() if hi > lo else None, n_q, metric, k, precision)
+
+    def _search_slice(self, d_slice: Optional[torch.Tensor], n_q: int, metric: int, k: int, precision: int):
+        """Search this rank's slice (already on the device, or None when the slice is empty) and gather the batch."""
+        per = -(-n_q // self.world)
         rows = torch.full((per, k), -1, dtype=torch.int64, device=self.device)
         dist = torch.full((per, k), float("inf"), dtype=torch.float32, device=self.device)
         torch.cuda.current_stream(self.device).synchronize()
-        if hi > lo:
-            mine = d_queries[lo:hi].contiguous()
-            torch.cuda.current_stream(self.device).synchronize()
-            self.corpus.search_device(mine.data_ptr(), hi - lo, metric, k, precision, rows.data_ptr(), dist.data_ptr())
+        if d_slice is not None and d_slice.shape[0] > 0:
+            self.corpus.search_device(d_slice.data_ptr(), d_slice.shape[0], metric, k, precision, rows.data_ptr(), dist.data_ptr())
         if self.world == 1:
             return rows[:n_q], dist[:n_q]
         return gather_slices(rows, dist, n_q, self.group)
 
     def search_host(self, h_queries: torch.Tensor, metric: int, k: int, precision: int = knn.PREC_FP32,
-                    h_rows: Optional[torch.Tensor] = None, h_dist: Optional[torch.Tensor] = None):
-        d_q = h_queries.to(self.device, non_blocking=True)
-        rows, dist = self.search_device(d_q, metric, k, precision)
+                    h_rows: Optional[torch.Tensor] = None, h_dist: Optional[torch.Tensor] = None,
+                    result_rank: Optional[int] = None):
+        """End-to-end form: only this rank's slice of the (pinned) host batch is uploaded; the gathered results are
+        copied back to the host on every rank, or on `result_rank` alone."""
+        n_q = h_queries.shape[0]
+        lo, hi = shard_bounds(n_q, self.world, self.rank)
+        d_slice = h_queries[lo:hi].to(self.device, non_blocking=True) if hi > lo else None
+        rows, dist = self._search_slice(d_slice, n_q, metric, k, precision)
+        if result_rank is not None and self.rank != result_rank:
+            torch.cuda.current_stream(self.device).synchronize()
+            return None, None
         if h_rows is None:
             return rows.cpu(), dist.cpu()
         h_rows.copy_(rows, non_blocking=True)
