@@ -22,7 +22,7 @@ class _Request:
 
     def __init__(self, query: np.ndarray) -> None:
         self.query = query
-        self.done = threading.Event()
+        self.done = None        # an Event, created by a follower (under the batcher's lock) before it waits
         self.result = None
         self.error = None
 
@@ -53,6 +53,8 @@ class MicroBatcher:
             if leader:
                 group = self._pending[key] = []
             group.append(req)
+            if not leader:
+                req.done = threading.Event()
             lonely = self._inflight == 1
         try:
             if not leader:
@@ -79,7 +81,8 @@ class MicroBatcher:
                         self.batches += 1
                         self.requests += len(batch)
                     for r in batch:
-                        r.done.set()
+                        if r.done is not None:
+                            r.done.set()
         finally:
             with self._lock:
                 self._inflight -= 1

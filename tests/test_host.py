@@ -89,11 +89,13 @@ def test_take_rows_equals_table_take():
     t = table_of(corpus, 64)
     for rows in ([5, 999, 0, 64, 63, 128, 5], [], [7], list(range(990, 1000))):
         rows = np.array(rows, dtype=np.int64)
-        got = ix.take_rows(t, rows)
-        assert got.schema == t.schema
-        assert got.combine_chunks() == t.take(pa.array(rows, type=pa.int64())).combine_chunks()
+        for cols in (["id", "vector"], ["vector"], ["id"]):
+            got = ix.take_rows(t, cols, rows)
+            want = t.select(cols).take(pa.array(rows, type=pa.int64()))
+            assert got.schema == want.schema
+            assert got.combine_chunks() == want.combine_chunks()
     big = rng.integers(0, 1000, 500)          # many rows: falls back to Table.take
-    assert ix.take_rows(t, big).combine_chunks() == t.take(pa.array(big)).combine_chunks()
+    assert ix.take_rows(t, ["id", "vector"], big).combine_chunks() == t.take(pa.array(big)).combine_chunks()
 
 
 def test_row_mask_follows_expression():
