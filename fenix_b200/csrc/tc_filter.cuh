@@ -1617,14 +1617,20 @@ inline double tc_c_err(int dim, int kind = 0) {
 inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan& main_pl, TcSearch* pre) {
   (void)st;
   if (s.tau_fixed || s.no_prepass || s.sample_stride > 1 || s.kind != 1 || s.dbg != nullptr) return false;
-  if (main_pl.n_kblocks > 4) return false;                 // wide rows: the tensor pipe binds, thresholds are not the issue
+  // Wide rows: with a large batch the tensor pipe binds and the sample's cost (1/stride of the scan) eats what the
+  // tighter thresholds save (C3: neutral). Small batches are HBM-bound with a lightly loaded tensor pipe, and there
+  // the epilogue's hit path and the finish kernel's candidate volume show: C5 batch 64 +18 %, batch 8 +6 %.
+  const bool wide = main_pl.n_kblocks > 4;
+  if (wide && main_pl.n_qt > 3 && !std::getenv("FENIX_TC_PRE_WIDE")) return false;
   if (s.epi != 2) return false;                            // a row mask (predicate / IVF cells) of unknown selectivity: the
                                                            // sample says nothing about how many LIVE rows pass a threshold
   if (const char* e = std::getenv("FENIX_TC_PRE")) { if (std::atoi(e) == 0) return false; }
   double safety = 3.0;
   if (const char* e = std::getenv("FENIX_TC_PRE_SAFETY")) { double f = std::atof(e); if (f >= 1.0 && f <= 64.0) safety = f; }
   const int tile_rows = main_pl.rq ? RQ_BN : TC_BN;
-  double target_m = 16.0;
+  // rank m of the sample statistic: P(threshold too tight for k rows) = P(Gamma(m) < m k / (safety K')). Wide rows pay
+  // for every sampled tile, so they take the thinner sample when k is small against K' (k = 10: m = 6, P ~ 1e-6)
+  double target_m = (wide && double(s.k) <= 0.06 * safety * double(main_pl.kp)) ? 6.0 : 16.0;
   if (const char* e = std::getenv("FENIX_TC_PRE_M")) { double f = std::atof(e); if (f >= 2.0 && f <= 256.0) target_m = f; }
   int stride = int(double(main_pl.kp) * safety / target_m);         // S = N / stride, m = safety K' S / N
   const int64_t n_tiles_full = (s.n_rows + tile_rows - 1) / tile_rows;
