@@ -92,6 +92,8 @@ typedef struct fx_stats {
 /* Bind a context to CUDA device `device`. Replaces nothing in the reference (it never
  * touches a device); one context per process-visible GPU. */
 int fx_init(int device, fx_ctx** out);
+/* Destroy every corpus created on `ctx` (fx_corpus_destroy) BEFORE shutting the context down: a corpus handle that
+ * outlives its context points at freed state. */
 int fx_shutdown(fx_ctx* ctx);
 
 /* Create an empty shard able to hold `capacity_rows` vectors of width `dim`.
@@ -114,6 +116,7 @@ int fx_corpus_append_device(fx_corpus* c, const void* device_rows, int64_t n_row
  * cdist / F.normalize redo on every call in the reference, coder.py:40,44). */
 int fx_corpus_finalize(fx_corpus* c);
 
+/* Frees the shard (rows, norms, bf16 shadows). Must precede fx_shutdown of its context. */
 int fx_corpus_destroy(fx_corpus* c);
 
 /* ---- search ---------------------------------------------------------------------------- */
