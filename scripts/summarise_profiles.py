@@ -31,8 +31,8 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 CAPTURES = {
     "r55_prof_c3.ncu-rep": ("r01_ncu_full_c3_main", "c3", "python bench.py --steps 3 --warmup 3 --no-cpu-baseline; main filter launch"),
     "r55_prof_c4s.ncu-rep": ("r01_ncu_full_c4s_rq_main", "c4s", "python bench.py --config c4s ...; resident-query filter, main pass"),
-    "r53_prof_c2_rq.ncu-rep": ("r01_ncu_full_c2_rq_main", "c2", "python bench.py --config c2 ...; resident-query filter, main pass"),
-    "r53_prof_c2_finish.ncu-rep": ("r01_ncu_full_c2_finish", None, "python bench.py --config c2 ...; finish kernel of the main pass (before the 8-lane rerank)"),
+    "r77_prof_c2_rq.ncu-rep": ("r01_ncu_full_c2_rq_main", "c2", "python bench.py --config c2 ...; resident-query filter, main pass"),
+    "r77_prof_c2_finish.ncu-rep": ("r01_ncu_full_c2_finish", None, "python bench.py --config c2 ...; finish kernel of the main pass"),
     "r55_prof_c5_8.ncu-rep": ("r01_ncu_full_c5_8", "c5_8", "python bench.py --config c5_8 ...; streaming filter, batch 8"),
 }
 
