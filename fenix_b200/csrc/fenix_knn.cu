@@ -1,8 +1,8 @@
 // fenix_knn.cu — C ABI of libfenix_knn.so (declared in include/fenix_knn.h).
 //
 // Host side of the B200 exact k-NN path: device shard ownership, pinned staging, kernel
-// dispatch and the certificate/fallback logic. Kernels live in exact_scan.cuh (fp64 CUDA-core
-// scan, merges, row norms) and tc_filter.cuh (tcgen05/TMEM TF32 filter + rerank).
+// dispatch and the certificate / refinement tiers. Kernels live in exact_scan.cuh (fp64 CUDA-core
+// scan, merges, row norms) and tc_filter.cuh (tcgen05/TMEM filter kernels, prepass, finish + rerank).
 #include <cuda.h>
 #include <cuda_runtime.h>
 

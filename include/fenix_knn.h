@@ -49,11 +49,11 @@ extern "C" {
 #define FX_METRIC_IP 2     /* "dot", "inner_product" */
 
 /* precision modes of fx_search
- *   FP32: exact. A TF32 tensor-core pass filters candidates under a rigorous error bound,
- *         survivors are re-ranked with fp64-accumulated arithmetic, the result is certified
- *         (or recomputed by the exact scan kernel when the certificate fails).
- *         The filter runs on a bf16 shadow copy of the shard (2x MMA rate, built at finalize when
- *         D >= 256 or FENIX_BF16_SHADOW=1) or, without one, on the fp32 rows read as TF32.
+ *   FP32: exact. A tensor-core pass (tcgen05) filters candidates under a rigorous error bound, survivors are
+ *         re-ranked with fp64-accumulated arithmetic, the result is certified; queries whose certificate fails are
+ *         settled by a re-run / preset-threshold refinement pass, in the last resort by the exact scan kernel.
+ *         The filter runs on a bf16 shadow copy of the shard (built at finalize when HBM allows; FENIX_BF16_SHADOW=0
+ *         disables it) or, without one, on the fp32 rows read as TF32.
  *   TF32 / BF16: the same tensor-core pass (TF32 over the fp32 rows / bf16 over the shadow) without
  *         slack or certificate; distances of the returned rows are still exact, membership is
  *         approximate (recall reported by bench.py). BF16 needs the shadow (FX_ESTATE otherwise).
