@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: epi_sweep3.sh "<bench args>" "ENV=1 ENV2=2" ...   ("-" = no env)
+# tuning sweep over env knobs / bench configs; usage: scripts/sweep.sh "<bench args>" "ENV=1 ENV2=2" ...   ("-" = no env)
 BARGS=$1; shift
 for e in "$@"; do
   [ "$e" = "-" ] && e="X=0"
