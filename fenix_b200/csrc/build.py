@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "-shared",
     "--expt-relaxed-constexpr",
+    "-ldl",
     *os.environ.get("FENIX_NVCC_EXTRA", "").split(),
 ]
 

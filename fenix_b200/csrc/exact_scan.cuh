@@ -32,6 +32,8 @@ __device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, int n) {
 //   double  qs[QB][dimp]      queries widened to fp64 (dimp = pitch)
 //   double  qq[QB]            squared query norms
 //   u64     tau[QB]           current admission key per query
+//   u64     floor[QB]         keys at or below it are not admitted (large-k searches run in passes of <= 2048 neighbours:
+//                             pass p takes the smallest keys ABOVE the last key of pass p - 1); 0 = no floor
 //   u64     buf[QB][BUF]      candidate keys
 //   int     cnt[QB]
 struct ScanParams {
@@ -48,6 +50,7 @@ struct ScanParams {
   int k;                   // 0 => distance-column mode
   int buf;                 // BUF: power of two >= k + SCAN_THREADS
   int qb;                  // queries per block (<= SCAN_MAX_QB)
+  const uint64_t* floor;   // optional [n_list]: admission floor per list slot (multi-pass large-k search)
   uint64_t* partial;       // [n_list][gridDim.x][k] sorted keys per (query, row block)
   float* dist_out;         // [n_list][n_rows] (distance-column mode)
 };
@@ -59,7 +62,8 @@ exact_scan_kernel(ScanParams p) {
   double* qs = reinterpret_cast<double*>(smem_raw);
   double* qq = qs + size_t(QB) * p.pitch;
   uint64_t* tau = reinterpret_cast<uint64_t*>(qq + QB);
-  uint64_t* buf = tau + QB;
+  uint64_t* flo = tau + QB;
+  uint64_t* buf = flo + QB;
   int* cnt = reinterpret_cast<int*>(buf + size_t(QB) * p.buf);
 
   const int g0 = blockIdx.y * QB;                       // first list slot of this group
@@ -75,7 +79,10 @@ exact_scan_kernel(ScanParams p) {
     }
     qs[i] = v;
   }
-  if (threadIdx.x < QB) { cnt[threadIdx.x] = 0; tau[threadIdx.x] = KEY_PAD; }
+  if (threadIdx.x < QB) {
+    cnt[threadIdx.x] = 0; tau[threadIdx.x] = KEY_PAD;
+    flo[threadIdx.x] = (p.floor != nullptr && int(threadIdx.x) < nq_here) ? p.floor[g0 + threadIdx.x] : 0ull;
+  }
   __syncthreads();
   if (threadIdx.x < QB) {
     double s = 0.0;
@@ -120,7 +127,7 @@ exact_scan_kernel(ScanParams p) {
             p.dist_out[size_t(g0 + q) * p.n_rows + r] = d;
           } else {
             uint64_t key = make_key(d, uint32_t(r));
-            if (key < tau[q]) {
+            if (key < tau[q] && key > flo[q]) {
               int pos = atomicAdd(&cnt[q], 1);
               buf[size_t(q) * p.buf + pos] = key;
             }
@@ -169,7 +176,8 @@ exact_scan_kernel(ScanParams p) {
 __global__ void __launch_bounds__(256)
 merge_keys_kernel(const uint64_t* __restrict__ lists, int W, int k, int n_sort,
                   const int* __restrict__ q_list, int64_t row_base,
-                  int64_t* __restrict__ out_rows, float* __restrict__ out_dist) {
+                  int64_t* __restrict__ out_rows, float* __restrict__ out_dist,
+                  int out_stride, int out_off, uint64_t* __restrict__ floor_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
   const int slot = blockIdx.x;
@@ -179,19 +187,21 @@ merge_keys_kernel(const uint64_t* __restrict__ lists, int W, int k, int n_sort,
   __syncthreads();
   block_bitonic_sort(keys, n_sort);
   const int qi = q_list ? q_list[slot] : slot;
+  // out_stride / out_off: the k results land in columns [out_off, out_off + k) of rows of out_stride entries
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     uint64_t key = keys[i];
     bool pad = key == KEY_PAD;
-    out_rows[size_t(qi) * k + i] = pad ? int64_t(-1) : row_base + int64_t(key & 0xffffffffull);
-    out_dist[size_t(qi) * k + i] = pad ? __int_as_float(0x7f800000) : ord2f(uint32_t(key >> 32));
+    out_rows[size_t(qi) * out_stride + out_off + i] = pad ? int64_t(-1) : row_base + int64_t(key & 0xffffffffull);
+    out_dist[size_t(qi) * out_stride + out_off + i] = pad ? __int_as_float(0x7f800000) : ord2f(uint32_t(key >> 32));
   }
+  if (floor_out != nullptr && threadIdx.x == 0) floor_out[slot] = keys[k - 1];   // next pass starts above this key
 }
 
 // Merge n_lists per-shard (row:int64, dist:f32) result lists into the global top-k.
 // One block per query; bitonic sort on (ord(dist), row) pairs held in shared memory.
 __global__ void __launch_bounds__(256)
 merge_pairs_kernel(const int64_t* __restrict__ rows, const float* __restrict__ dist,
-                   int n_lists, int64_t n_q, int k, int n_sort,
+                   int n_lists, int64_t n_q, int k, int n_sort, int64_t rows_stride_bytes, int64_t dist_stride_bytes,
                    int64_t* __restrict__ out_rows, float* __restrict__ out_dist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int64_t* srow = reinterpret_cast<int64_t*>(smem_raw);
@@ -201,10 +211,13 @@ merge_pairs_kernel(const int64_t* __restrict__ rows, const float* __restrict__ d
   for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
     if (i < total) {
       int l = i / k, j = i - l * k;
-      size_t off = (size_t(l) * n_q + q) * k + j;
-      int64_t r = rows[off];
+      // list l: rows at `rows` + l * rows_stride bytes, distances at `dist` + l * dist_stride bytes, each [n_q][k]
+      // (list-major arrays: strides n_q*k*8 and n_q*k*4; exchange slots of a sharded search: both = the slot size)
+      const size_t off = size_t(q) * k + j;
+      const int64_t r = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(rows) + size_t(l) * rows_stride_bytes)[off];
+      const float d = reinterpret_cast<const float*>(reinterpret_cast<const char*>(dist) + size_t(l) * dist_stride_bytes)[off];
       srow[i] = r < 0 ? INT64_MAX : r;
-      sord[i] = r < 0 ? 0xffffffffu : f2ord(dist[off]);
+      sord[i] = r < 0 ? 0xffffffffu : f2ord(d);
     } else {
       srow[i] = INT64_MAX; sord[i] = 0xffffffffu;
     }
@@ -229,6 +242,42 @@ merge_pairs_kernel(const int64_t* __restrict__ rows, const float* __restrict__ d
     bool pad = r == INT64_MAX;
     out_rows[q * k + i] = pad ? int64_t(-1) : r;
     out_dist[q * k + i] = pad ? __int_as_float(0x7f800000) : ord2f(sord[i]);
+  }
+}
+
+// The same merge without a shared-memory limit (lists * k > 8192): every list is sorted by (distance, row) and keys are
+// unique, so an entry's global rank is its own position plus, for every other list, the number of entries below it
+// (binary search). One thread per entry; entries ranked < k are written straight to their output slot.
+__global__ void __launch_bounds__(256)
+merge_rank_kernel(const int64_t* __restrict__ rows, const float* __restrict__ dist,
+                  int n_lists, int64_t n_q, int k, int64_t rows_stride_bytes, int64_t dist_stride_bytes,
+                  int64_t* __restrict__ out_rows, float* __restrict__ out_dist) {
+  const int64_t q = blockIdx.x;
+  auto list_rows = [&](int l) { return reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(rows) + size_t(l) * rows_stride_bytes) + size_t(q) * k; };
+  auto list_dist = [&](int l) { return reinterpret_cast<const float*>(reinterpret_cast<const char*>(dist) + size_t(l) * dist_stride_bytes) + size_t(q) * k; };
+  auto key_of = [&](int l, int j, uint32_t& o, int64_t& r) {
+    r = list_rows(l)[j];
+    if (r < 0) { r = INT64_MAX; o = 0xffffffffu; } else o = f2ord(list_dist(l)[j]);
+  };
+  const int total = n_lists * k;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) { out_rows[q * k + i] = -1; out_dist[q * k + i] = __int_as_float(0x7f800000); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int l = i / k, j = i - l * k;
+    uint32_t o; int64_t r; key_of(l, j, o, r);
+    if (r == INT64_MAX) continue;   // pad
+    int rank = j;
+    for (int m = 0; m < n_lists && rank < k; ++m) {
+      if (m == l) continue;
+      int lo = 0, hi = k;            // entries of list m strictly below (o, r)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        uint32_t om; int64_t rm; key_of(m, mid, om, rm);
+        if (om < o || (om == o && rm < r)) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) { out_rows[q * k + rank] = r; out_dist[q * k + rank] = ord2f(o); }
   }
 }
 

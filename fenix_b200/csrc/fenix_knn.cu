@@ -6,15 +6,21 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/fenix_knn.h"
@@ -93,11 +99,14 @@ struct fx_ctx {
   cudaStream_t upload = nullptr;   // H2D of corpus chunks
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   std::mutex mu;                   // one search at a time per device context
-  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref, d_maskn;
+  cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;   // exchange (all-gather + merge) of a sharded search
+  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref, d_maskn, d_floor, d_xchg, d_hdr;
   HostBuf h_q, h_rows, h_dist, h_flags;
+  int* h_word = nullptr;           // pinned: [0] flagged-query count of the last main pass, [1..] gathered per-rank counts
   int64_t launches = 0;
-  fx::TcState tc;                  // driver entry points / kernel attributes of the TC path
+  fx::TcState tc;                  // driver entry points / kernel attributes / tuning knobs of the TC path
 };
+constexpr int H_WORDS = 64;
 
 constexpr size_t RING_BYTES = size_t(32) << 20;
 
@@ -126,6 +135,40 @@ static int bind(fx_ctx* ctx) {
   FX_CUDA(cudaSetDevice(ctx->device));
   return FX_OK;
 }
+
+// ----------------------------------------------------------------------------------------
+// live-handle registry: a corpus handle is checked (and leased) before it is dereferenced, so a call that races with
+// fx_corpus_destroy of the same shard fails with FX_EINVAL - or finishes first - instead of running on freed memory.
+// fx_corpus_destroy retires the handle, then waits for the leases already out.
+// ----------------------------------------------------------------------------------------
+struct HandleState { int users = 0; bool doomed = false; };
+static std::mutex g_reg_mu;
+static std::condition_variable g_reg_cv;
+static std::unordered_map<const fx_corpus*, HandleState> g_live;
+
+struct Lease {
+  const fx_corpus* c;
+  bool ok = false;
+  explicit Lease(const fx_corpus* c_) : c(c_) {
+    if (!c) return;
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    auto it = g_live.find(c);
+    if (it == g_live.end() || it->second.doomed) return;
+    it->second.users++;
+    ok = true;
+  }
+  ~Lease() {
+    if (!ok) return;
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    auto it = g_live.find(c);
+    if (it != g_live.end() && --it->second.users == 0 && it->second.doomed) g_reg_cv.notify_all();
+  }
+  Lease(const Lease&) = delete;
+  Lease& operator=(const Lease&) = delete;
+};
+#define FX_LEASE(c, who)                                                                             \
+  Lease _lease(c);                                                                                   \
+  if (!_lease.ok) return fail(FX_EINVAL, "%s: %s", who, (c) ? "not a live corpus handle (destroyed?)" : "corpus is NULL")
 
 // ----------------------------------------------------------------------------------------
 // lifetime
@@ -165,6 +208,10 @@ extern "C" int fx_init(int device, fx_ctx** out) {
   FX_CUDA(cudaEventCreate(&ctx->ev_stop));
   FX_CUDA(cudaEventCreate(&ctx->ev_k0));
   FX_CUDA(cudaEventCreate(&ctx->ev_k1));
+  FX_CUDA(cudaEventCreate(&ctx->ev_x0));
+  FX_CUDA(cudaEventCreate(&ctx->ev_x1));
+  FX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_word), H_WORDS * sizeof(int)));
+  std::memset(ctx->h_word, 0, H_WORDS * sizeof(int));
   FX_CUDA(cudaFuncSetAttribute(fx::exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -186,9 +233,12 @@ extern "C" int fx_shutdown(fx_ctx* ctx) {
   cudaStreamSynchronize(ctx->upload);
   ctx->d_q.release(); ctx->d_rows.release(); ctx->d_dist.release(); ctx->d_mask.release();
   ctx->d_partial.release(); ctx->d_qlist.release(); ctx->d_tc.release(); ctx->d_ref.release(); ctx->d_maskn.release();
+  ctx->d_floor.release(); ctx->d_xchg.release(); ctx->d_hdr.release();
   ctx->h_q.release(); ctx->h_rows.release(); ctx->h_dist.release(); ctx->h_flags.release();
+  if (ctx->h_word) cudaFreeHost(ctx->h_word);
   cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_stop);
   cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
+  cudaEventDestroy(ctx->ev_x0); cudaEventDestroy(ctx->ev_x1);
   cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->upload);
   delete ctx;
   return FX_OK;
@@ -230,7 +280,18 @@ extern "C" int fx_corpus_create(fx_ctx* ctx, int64_t capacity_rows, int32_t dim,
   FX_CUDA(cudaMemsetAsync(c->rx, 0, norm_alloc * sizeof(float), ctx->upload));
   c->stats.dim = dim; c->stats.pitch = c->pitch;
   c->stats.device_bytes = int64_t(rows_alloc * (c->pitch + 2) * sizeof(float));
+  {
+    std::lock_guard<std::mutex> reg(g_reg_mu);
+    g_live[c] = HandleState{};
+  }
   *out = c;
+  return FX_OK;
+}
+
+extern "C" int fx_set_option(fx_ctx* ctx, const char* name, const char* value) {
+  if (!ctx || !name) return fail(FX_EINVAL, "fx_set_option: NULL argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (!fx::tc_set_knob(&ctx->tc.knobs, name, value)) return fail(FX_EINVAL, "fx_set_option: unknown option '%s'", name);
   return FX_OK;
 }
 
@@ -245,7 +306,7 @@ static int ensure_ring(fx_corpus* c) {
 }
 
 static int append_impl(fx_corpus* c, const void* rows, int64_t n_rows, bool on_device) {
-  if (!c) return fail(FX_EINVAL, "fx_corpus_append: corpus is NULL");
+  FX_LEASE(c, "fx_corpus_append");
   if (n_rows < 0) return fail(FX_EINVAL, "fx_corpus_append: negative row count");
   if (n_rows == 0) return FX_OK;
   if (!rows) return fail(FX_EINVAL, "fx_corpus_append: rows is NULL");
@@ -290,7 +351,7 @@ extern "C" int fx_corpus_append_device(fx_corpus* c, const void* device_rows, in
 }
 
 extern "C" int fx_corpus_finalize(fx_corpus* c) {
-  if (!c) return fail(FX_EINVAL, "fx_corpus_finalize: corpus is NULL");
+  FX_LEASE(c, "fx_corpus_finalize");
   fx_ctx* ctx = c->ctx;
   std::lock_guard<std::mutex> lock(ctx->mu);
   if (c->finalized) return FX_OK;
@@ -358,6 +419,15 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
 
 extern "C" int fx_corpus_destroy(fx_corpus* c) {
   if (!c) return fail(FX_EINVAL, "fx_corpus_destroy: corpus is NULL");
+  {
+    // retire the handle (new calls on it fail), then wait for the calls already inside the library
+    std::unique_lock<std::mutex> reg(g_reg_mu);
+    auto it = g_live.find(c);
+    if (it == g_live.end() || it->second.doomed) return fail(FX_EINVAL, "fx_corpus_destroy: not a live corpus handle (destroyed twice?)");
+    it->second.doomed = true;
+    g_reg_cv.wait(reg, [&] { return g_live[c].users == 0; });
+    g_live.erase(c);
+  }
   fx_ctx* ctx = c->ctx;
   std::lock_guard<std::mutex> lock(ctx->mu);
   cudaSetDevice(ctx->device);
@@ -377,7 +447,8 @@ extern "C" int fx_corpus_destroy(fx_corpus* c) {
 }
 
 extern "C" int fx_get_stats(fx_corpus* c, fx_stats* out) {
-  if (!c || !out) return fail(FX_EINVAL, "fx_get_stats: NULL argument");
+  if (!out) return fail(FX_EINVAL, "fx_get_stats: NULL argument");
+  FX_LEASE(c, "fx_get_stats");
   std::lock_guard<std::mutex> lock(c->ctx->mu);
   c->stats.n_rows = c->n;
   *out = c->stats;
@@ -388,15 +459,18 @@ extern "C" int fx_get_stats(fx_corpus* c, fx_stats* out) {
 // exact scan dispatch
 // ----------------------------------------------------------------------------------------
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+constexpr int SCAN_K_PASS = 2048;   // neighbours one pass of the scan selects (shared-memory candidate buffers)
 
-// Runs the fp64 scan for `n_list` queries (all of them when d_qlist == null) and writes the
-// (row, distance) top-k of each into the output slots of the listed queries.
-static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_qlist, int n_list,
-                          int metric, int k, const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist) {
+// One pass of the fp64 scan for `n_list` queries (all of them when d_qlist == null): the k smallest (distance, row)
+// keys ABOVE each query's floor key (d_floor, optional) land in columns [out_off, out_off + k) of the listed
+// queries' output rows (out_stride entries per query); the last key becomes the next floor (floor_out, optional).
+static int run_scan_pass(fx_corpus* c, const float* d_q, int n_q, const int* d_qlist, int n_list, int metric, int k,
+                         const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist, int out_stride, int out_off,
+                         uint64_t* d_floor) {
   fx_ctx* ctx = c->ctx;
   if (n_list == 0) return FX_OK;
   const int buf = next_pow2(k + fx::SCAN_THREADS);
-  const size_t per_q = size_t(c->pitch) * 8 + 8 + 8 + size_t(buf) * 8 + 4;
+  const size_t per_q = size_t(c->pitch) * 8 + 8 + 8 + 8 + size_t(buf) * 8 + 4;
   const size_t smem_limit = 200 * 1024;
   int qb = int(std::min<size_t>(fx::SCAN_MAX_QB, smem_limit / per_q));
   if (qb < 1) return fail(FX_EUNSUP, "exact scan: dim %d with k %d needs %zu B of shared memory per query", c->dim, k, per_q);
@@ -411,7 +485,8 @@ static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_
     while (done < n_list) {
       int take = std::min(n_list - done, 65535 * qb);
       if (d_qlist) {
-        FX_TRY(run_exact_scan(c, d_q, n_q, d_qlist + done, take, metric, k, d_mask, d_out_rows, d_out_dist));
+        FX_TRY(run_scan_pass(c, d_q, n_q, d_qlist + done, take, metric, k, d_mask, d_out_rows, d_out_dist, out_stride, out_off,
+                             d_floor ? d_floor + done : nullptr));
       } else {
         // build an explicit list for the slab
         std::vector<int> idx(take);
@@ -419,7 +494,8 @@ static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_
         DevBuf tmp;
         FX_TRY(tmp.ensure(size_t(take) * sizeof(int)));
         FX_CUDA(cudaMemcpyAsync(tmp.p, idx.data(), size_t(take) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        int r = run_exact_scan(c, d_q, n_q, static_cast<int*>(tmp.p), take, metric, k, d_mask, d_out_rows, d_out_dist);
+        int r = run_scan_pass(c, d_q, n_q, static_cast<int*>(tmp.p), take, metric, k, d_mask, d_out_rows, d_out_dist, out_stride,
+                              out_off, d_floor ? d_floor + done : nullptr);
         cudaStreamSynchronize(ctx->stream);
         tmp.release();
         FX_TRY(r);
@@ -432,15 +508,32 @@ static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_
   fx::ScanParams p{};
   p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.Q = d_q; p.n_q = n_q;
   p.metric = metric; p.mask = d_mask; p.q_list = d_qlist; p.n_list = n_list; p.k = k; p.buf = buf; p.qb = qb;
+  p.floor = d_floor;
   p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.dist_out = nullptr;
   const size_t smem = per_q * qb + 16;
   fx::exact_scan_kernel<<<dim3(W, groups), fx::SCAN_THREADS, smem, ctx->stream>>>(p);
   FX_CUDA(cudaGetLastError());
   const int n_sort = next_pow2(std::max(W * k, 2));
   fx::merge_keys_kernel<<<n_list, 256, size_t(n_sort) * 8, ctx->stream>>>(
-      p.partial, W, k, n_sort, d_qlist, c->row_base, d_out_rows, d_out_dist);
+      p.partial, W, k, n_sort, d_qlist, c->row_base, d_out_rows, d_out_dist, out_stride, out_off, d_floor);
   FX_CUDA(cudaGetLastError());
   ctx->launches += 2; c->stats.kernel_launches += 2;
+  return FX_OK;
+}
+
+// The fp64 scan for any k: passes of at most SCAN_K_PASS neighbours, each admitting only keys above the last
+// (distance, row) key of the one before ((distance, row) keys are unique, so the passes partition the order).
+static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_qlist, int n_list,
+                          int metric, int k, const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist) {
+  fx_ctx* ctx = c->ctx;
+  if (k <= SCAN_K_PASS) return run_scan_pass(c, d_q, n_q, d_qlist, n_list, metric, k, d_mask, d_out_rows, d_out_dist, k, 0, nullptr);
+  FX_TRY(ctx->d_floor.ensure(size_t(n_list) * sizeof(uint64_t)));
+  FX_CUDA(cudaMemsetAsync(ctx->d_floor.p, 0, size_t(n_list) * sizeof(uint64_t), ctx->stream));
+  for (int done = 0; done < k; done += SCAN_K_PASS) {
+    const int kp = std::min(SCAN_K_PASS, k - done);
+    FX_TRY(run_scan_pass(c, d_q, n_q, d_qlist, n_list, metric, kp, d_mask, d_out_rows, d_out_dist, k, done,
+                         static_cast<uint64_t*>(ctx->d_floor.p)));
+  }
   return FX_OK;
 }
 
@@ -452,7 +545,7 @@ static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_
 static bool ensure_norm_shadow(fx_corpus* c) {
   fx_ctx* ctx = c->ctx;
   if (c->tc.ok_n) return true;
-  if (c->xn_failed || !c->tc.ok_b || std::getenv("FENIX_NO_NORM_SHADOW")) return false;
+  if (c->xn_failed || !c->tc.ok_b || ctx->tc.knobs.no_norm_shadow) return false;
   const int n_kb = fx::shadow_geom(c->dim).n_kb_data;
   const int64_t n_tiles = (c->n + fx::TC_BN - 1) / fx::TC_BN;
   const size_t shadow_bytes = size_t(n_tiles) * n_kb * fx::TC_BN * 64 * 2;
@@ -506,25 +599,43 @@ static int configure_filter(fx_corpus* c, int metric, int kind, const uint8_t* d
 }
 
 static int check_search_args(fx_corpus* c, const void* q, int64_t n_q, int metric, int k, int precision,
-                             const void* out_rows, const void* out_dist) {
-  if (!c) return fail(FX_EINVAL, "fx_search: corpus is NULL");
+                             const void* out_rows, const void* out_dist, bool outs_required = true) {
   if (!c->finalized) return fail(FX_ESTATE, "fx_search: corpus is not finalized");
   if (n_q < 0) return fail(FX_EINVAL, "fx_search: negative query count");
-  if (n_q > 0 && (!q || !out_rows || !out_dist)) return fail(FX_EINVAL, "fx_search: NULL buffer");
+  if (n_q > 0 && (!q || (outs_required && (!out_rows || !out_dist)))) return fail(FX_EINVAL, "fx_search: NULL buffer");
+  if ((out_rows == nullptr) != (out_dist == nullptr)) return fail(FX_EINVAL, "fx_search: out_rows and out_dist must both be given, or neither");
   if (n_q > int64_t(1) << 24) return fail(FX_EUNSUP, "fx_search: at most 2^24 queries per call");
   if (metric < 0 || metric > 2) return fail(FX_EINVAL, "fx_search: unknown metric %d", metric);
   if (k < 1) return fail(FX_EINVAL, "fx_search: k must be >= 1 (got %d)", k);
-  if (k > 2048) return fail(FX_EUNSUP, "fx_search: k = %d exceeds the supported maximum of 2048", k);
+  if (n_q * int64_t(k) > (int64_t(1) << 33)) return fail(FX_EUNSUP, "fx_search: n_q * k = %lld results exceed 2^33", (long long)(n_q * int64_t(k)));
   if (precision != FX_PREC_FP32 && precision != FX_PREC_TF32 && precision != FX_PREC_BF16 && precision != FX_PREC_EXACT_SCAN)
     return fail(FX_EINVAL, "fx_search: unknown precision mode %d", precision);
   return FX_OK;
 }
 
-static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int metric, int k, int precision,
-                                const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist) {
+// A search runs in two phases so that callers can queue whatever follows (result copies, the all-gather and merge of
+// a sharded search) behind the kernels WITHOUT a host synchronisation in between:
+//   search_enqueue  launches prep / prepass / filter / finish (or the scan) on the context's stream and queues the copy
+//                   of the "flagged queries" counter into pinned memory;
+//   search_settle   after the caller's ONE synchronisation: nothing to do when no certificate failed (the common
+//                   case); otherwise the re-run / refinement / scan tiers repair the flagged queries' results in place
+//                   and the caller repeats its copies.
+struct SearchRun {
+  bool tc = false;            // the tensor-core path ran (flags are meaningful)
+  int path = 0;               // 0 exact scan, 1 tensor-core TF32 filter, 2 tensor-core bf16 filter
+  fx::TcSearch s{};
+  fx::TcLaunch L{};
+  const float* d_q = nullptr; int64_t n_q = 0; int metric = 0, k = 0;
+  const uint8_t* d_mask = nullptr; int64_t* d_out_rows = nullptr; float* d_out_dist = nullptr;
+};
+
+static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metric, int k, int precision,
+                          const uint8_t* d_mask, int64_t* d_out_rows, float* d_out_dist, SearchRun* run) {
   fx_ctx* ctx = c->ctx;
+  run->tc = false; run->path = 0; run->d_q = d_q; run->n_q = n_q; run->metric = metric; run->k = k;
+  run->d_mask = d_mask; run->d_out_rows = d_out_rows; run->d_out_dist = d_out_dist;
+  ctx->h_word[0] = 0;
   FX_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
-  int path = 0;   // 0 exact scan, 1 tensor-core TF32 filter, 2 tensor-core bf16 filter
   const bool want_tc = precision != FX_PREC_EXACT_SCAN &&
                        fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q));
   if (c->n == 0) {
@@ -532,133 +643,159 @@ static int search_device_locked(fx_corpus* c, const float* d_q, int64_t n_q, int
     fx::fill_pad_kernel<<<int(std::min<int64_t>((n_q * k + 255) / 256, 65535)), 256, 0, ctx->stream>>>(d_out_rows, d_out_dist, n_q * k);
     FX_CUDA(cudaGetLastError());
     ctx->launches++; c->stats.kernel_launches++;
+    FX_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    FX_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
   } else if (want_tc) {
-    path = 1;
-    fx::TcSearch s{};
+    fx::TcSearch& s = run->s;
+    s = fx::TcSearch{};
     s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
     s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = d_q; s.n_q = int(n_q); s.metric = metric; s.k = k;
     s.certify = precision == FX_PREC_FP32; s.out_rows = d_out_rows; s.out_dist = d_out_dist;
     s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.dbg = nullptr; s.tau_fixed = nullptr;
     // operand kind of the filter: exact mode takes the bf16 shadow when the shard has one
-    const int kind = (precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && c->tc.ok_b && !std::getenv("FENIX_FP32_FILTER_TF32"))) ? 1 : 0;
-    path = 1 + kind;
+    const int kind = (precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && c->tc.ok_b && !ctx->tc.knobs.fp32_filter_tf32)) ? 1 : 0;
     if (kind == 1 && !c->tc.ok_b) return fail(FX_ESTATE, "fx_search: FX_PREC_BF16 needs the bf16 shadow (FENIX_BF16_SHADOW=1 at finalize)");
     FX_TRY(configure_filter(c, metric, kind, d_mask, &s));
+    run->L = fx::tc_prepare(&ctx->tc, s);
+    FX_TRY(ctx->d_tc.ensure(run->L.scratch_bytes));
     std::string err;
-    size_t need = fx::tc_scratch_bytes(&ctx->tc, s);
-    FX_TRY(ctx->d_tc.ensure(need));
     int launched = 0, variant = 0;
-    if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err, &variant)) return fail(FX_ECUDA, "fx_search: %s", err.c_str());
+    if (!fx::tc_search(&ctx->tc, &c->tc, s, run->L, ctx->d_tc.p, &launched, &err, &variant)) return fail(FX_ECUDA, "fx_search: %s", err.c_str());
+    run->tc = true; run->path = 1 + kind;
     c->stats.last_variant = variant;
     ctx->launches += launched; c->stats.kernel_launches += launched;
-    if (s.certify) {
-      // queries whose certificate failed are recomputed by the exact scan
-      FX_TRY(ctx->h_flags.ensure(size_t(n_q) * sizeof(int)));
-      int* h_flags = static_cast<int*>(ctx->h_flags.p);
-      const int* d_flags = fx::tc_flags(&ctx->tc, s, ctx->d_tc.p);
-      FX_CUDA(cudaMemcpyAsync(h_flags, d_flags, size_t(n_q) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      FX_CUDA(cudaStreamSynchronize(ctx->stream));
-      // flag 1: the certificate failed; flag 2: fewer than k candidates survived (a sample threshold that came out too tight)
-      std::vector<int> bad, starved;
-      for (int64_t i = 0; i < n_q; ++i) { if (h_flags[i] == 2) starved.push_back(int(i)); else if (h_flags[i]) bad.push_back(int(i)); }
-      // Flagged queries are settled by up to two more filter passes over their own (small) batch:
-      //  tier 0 (only when the main pass took its thresholds from the sample prepass): the adaptive search without
-      //         prepass - a sample threshold that came out too tight leaves a query with fewer than k candidates,
-      //         and then there is no k-th distance to refine from;
-      //  tier 1: preset-threshold refinement: the admission threshold is the query's k-th distance minus the error
-      //         bound and every survivor is reranked, so the result is exact.
-      const bool had_prepass = fx::tc_uses_prepass(&ctx->tc, s);
-      if (!had_prepass) { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }
-      for (int tier = starved.empty() ? 1 : 0; tier <= 1 && !std::getenv("FENIX_NO_REFINE"); ++tier) {
-        if (tier == 0) bad.swap(starved);                                    // tier 0 takes the starved queries only ...
-        else { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }   // ... what it leaves flagged joins tier 1
-        if (bad.empty()) continue;
-        const int n_f = int(bad.size());
-        FX_TRY(ctx->d_qlist.ensure(size_t(n_f) * sizeof(int)));
-        FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), size_t(n_f) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        size_t off = 0;
-        auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-        const size_t o_q = take(size_t(n_f) * c->dim * 4), o_tau = take(size_t(n_f) * 4);
-        const size_t o_rows = take(size_t(n_f) * k * 8), o_dist = take(size_t(n_f) * k * 4);
-        FX_TRY(ctx->d_ref.ensure(off));
-        char* rb = static_cast<char*>(ctx->d_ref.p);
-        float* q_r = reinterpret_cast<float*>(rb + o_q);
-        uint32_t* tau_fixed = reinterpret_cast<uint32_t*>(rb + o_tau);
-        int64_t* rows2 = reinterpret_cast<int64_t*>(rb + o_rows);
-        float* dist2 = reinterpret_cast<float*>(rb + o_dist);
-        // gathers the flagged queries (and derives the preset thresholds tier 1 uses)
-        fx::refine_prep_kernel<<<n_f, 128, 0, ctx->stream>>>(d_q, static_cast<const int*>(ctx->d_qlist.p), c->dim, metric, k,
-                                                            d_out_dist, c->max_norm, fx::tc_c_err(c->dim, s.kind),
-                                                            fx::tc_c_add(c->dim, s.kind == 1 && s.aug), q_r, tau_fixed);
-        FX_CUDA(cudaGetLastError());
-        fx::TcSearch s2 = s;
-        s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.certify = true;
-        s2.tau_fixed = tier == 1 ? tau_fixed : nullptr; s2.no_prepass = 1;
-        s2.ev_k0 = nullptr; s2.ev_k1 = nullptr;   // keep the timing of the main pass
-        FX_TRY(ctx->d_tc.ensure(fx::tc_scratch_bytes(&ctx->tc, s2)));
-        int launched2 = 0;
-        if (!fx::tc_search(&ctx->tc, &c->tc, s2, ctx->d_tc.p, &launched2, &err)) return fail(FX_ECUDA, "fx_search (refine): %s", err.c_str());
-        const int* d_flags2 = fx::tc_flags(&ctx->tc, s2, ctx->d_tc.p);
-        // tier 0 results replace the first pass's in any case (they hold k real neighbours for tier 1 to refine from);
-        // tier 1 results only where their certificate holds
-        fx::refine_scatter_kernel<<<std::min((n_f * k + 255) / 256, 1024), 256, 0, ctx->stream>>>(
-            static_cast<const int*>(ctx->d_qlist.p), tier == 1 ? d_flags2 : nullptr, n_f, k, rows2, dist2, d_out_rows, d_out_dist);
-        FX_CUDA(cudaGetLastError());
-        ctx->launches += launched2 + 2; c->stats.kernel_launches += launched2 + 2;
-        FX_CUDA(cudaMemcpyAsync(h_flags, d_flags2, size_t(n_f) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        FX_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (std::getenv("FENIX_DEBUG_REFINE")) {
-          std::vector<uint32_t> tf(n_f); std::vector<float> d2(size_t(n_f) * k); std::vector<int64_t> r2(size_t(n_f) * k);
-          cudaMemcpy(tf.data(), tau_fixed, size_t(n_f) * 4, cudaMemcpyDeviceToHost);
-          cudaMemcpy(d2.data(), dist2, size_t(n_f) * k * 4, cudaMemcpyDeviceToHost);
-          cudaMemcpy(r2.data(), rows2, size_t(n_f) * k * 8, cudaMemcpyDeviceToHost);
-          for (int i = 0; i < std::min(n_f, 4); ++i)
-            fprintf(stderr, "[refine tier %d] q=%d tau=%g flag=%d rows %lld %lld .. %lld dist %g .. %g\n", tier, bad[i], fx::ord2f(tf[i]), h_flags[i],
-                    (long long)r2[size_t(i) * k], (long long)r2[size_t(i) * k + 1], (long long)r2[size_t(i) * k + k - 1],
-                    d2[size_t(i) * k], d2[size_t(i) * k + k - 1]);
-        }
-        std::vector<int> still;
-        for (int i = 0; i < n_f; ++i) if (h_flags[i]) still.push_back(bad[i]);
-        c->stats.refined_queries += int64_t(n_f - int(still.size()));
-        bad.swap(still);
-      }
-      if (!bad.empty()) {
-        // tier 2: the certificate-free fp64 scan
-        FX_TRY(ctx->d_qlist.ensure(bad.size() * sizeof(int)));
-        FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), bad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        FX_TRY(run_exact_scan(c, d_q, int(n_q), static_cast<int*>(ctx->d_qlist.p), int(bad.size()), metric, k,
-                              d_mask, d_out_rows, d_out_dist));
-        FX_CUDA(cudaStreamSynchronize(ctx->stream));  // `bad` must outlive the H2D copy
-        c->stats.fallback_queries += int64_t(bad.size());
-      }
-    }
+    if (s.certify) FX_CUDA(cudaMemcpyAsync(ctx->h_word, fx::tc_flag_count(ctx->d_tc.p), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   } else {
     FX_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
     FX_TRY(run_exact_scan(c, d_q, int(n_q), nullptr, int(n_q), metric, k, d_mask, d_out_rows, d_out_dist));
     FX_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
   }
   FX_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+  return FX_OK;
+}
+
+// Precondition: the stream has been synchronised since search_enqueue. *changed: results were rewritten.
+static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
+  fx_ctx* ctx = c->ctx;
+  *changed = false;
+  if (!run->tc || !run->s.certify || ctx->h_word[0] == 0) return FX_OK;
+  *changed = true;
+  const fx::TcSearch& s = run->s;
+  const int64_t n_q = run->n_q;
+  const int k = run->k, metric = run->metric;
+  const float* d_q = run->d_q;
+  int64_t* d_out_rows = run->d_out_rows; float* d_out_dist = run->d_out_dist;
+  std::string err;
+  // queries whose certificate failed: flag 1; fewer than k candidates survived (a sample threshold that came out too tight): flag 2
+  FX_TRY(ctx->h_flags.ensure(size_t(n_q) * sizeof(int)));
+  int* h_flags = static_cast<int*>(ctx->h_flags.p);
+  const int* d_flags = fx::tc_flags(run->L, ctx->d_tc.p);
+  FX_CUDA(cudaMemcpyAsync(h_flags, d_flags, size_t(n_q) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> bad, starved;
+  for (int64_t i = 0; i < n_q; ++i) { if (h_flags[i] == 2) starved.push_back(int(i)); else if (h_flags[i]) bad.push_back(int(i)); }
+  // Flagged queries are settled by up to two more filter passes over their own (small) batch:
+  //  tier 0 (only when the main pass took its thresholds from the sample prepass): the adaptive search without
+  //         prepass - a sample threshold that came out too tight leaves a query with fewer than k candidates,
+  //         and then there is no k-th distance to refine from;
+  //  tier 1: preset-threshold refinement: the admission threshold is the query's k-th distance minus the error
+  //         bound and every survivor is reranked, so the result is exact.
+  if (!run->L.with_pre) { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }
+  for (int tier = starved.empty() ? 1 : 0; tier <= 1 && !ctx->tc.knobs.no_refine; ++tier) {
+    if (tier == 0) bad.swap(starved);                                    // tier 0 takes the starved queries only ...
+    else { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }   // ... what it leaves flagged joins tier 1
+    if (bad.empty()) continue;
+    const int n_f = int(bad.size());
+    FX_TRY(ctx->d_qlist.ensure(size_t(n_f) * sizeof(int)));
+    FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), size_t(n_f) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t o_q = take(size_t(n_f) * c->dim * 4), o_tau = take(size_t(n_f) * 4);
+    const size_t o_rows = take(size_t(n_f) * k * 8), o_dist = take(size_t(n_f) * k * 4);
+    FX_TRY(ctx->d_ref.ensure(off));
+    char* rb = static_cast<char*>(ctx->d_ref.p);
+    float* q_r = reinterpret_cast<float*>(rb + o_q);
+    uint32_t* tau_fixed = reinterpret_cast<uint32_t*>(rb + o_tau);
+    int64_t* rows2 = reinterpret_cast<int64_t*>(rb + o_rows);
+    float* dist2 = reinterpret_cast<float*>(rb + o_dist);
+    // gathers the flagged queries (and derives the preset thresholds tier 1 uses)
+    fx::refine_prep_kernel<<<n_f, 128, 0, ctx->stream>>>(d_q, static_cast<const int*>(ctx->d_qlist.p), c->dim, metric, k,
+                                                        d_out_dist, c->max_norm, fx::tc_c_err(c->dim, s.kind),
+                                                        fx::tc_c_add(c->dim, s.kind == 1 && s.aug), q_r, tau_fixed);
+    FX_CUDA(cudaGetLastError());
+    fx::TcSearch s2 = s;
+    s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.certify = true;
+    s2.tau_fixed = tier == 1 ? tau_fixed : nullptr; s2.no_prepass = 1;
+    s2.ev_k0 = nullptr; s2.ev_k1 = nullptr;   // keep the timing of the main pass
+    const fx::TcLaunch L2 = fx::tc_prepare(&ctx->tc, s2);
+    FX_TRY(ctx->d_tc.ensure(L2.scratch_bytes));
+    int launched2 = 0;
+    if (!fx::tc_search(&ctx->tc, &c->tc, s2, L2, ctx->d_tc.p, &launched2, &err)) return fail(FX_ECUDA, "fx_search (refine): %s", err.c_str());
+    const int* d_flags2 = fx::tc_flags(L2, ctx->d_tc.p);
+    // tier 0 results replace the first pass's in any case (they hold k real neighbours for tier 1 to refine from);
+    // tier 1 results only where their certificate holds
+    fx::refine_scatter_kernel<<<std::min((n_f * k + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+        static_cast<const int*>(ctx->d_qlist.p), tier == 1 ? d_flags2 : nullptr, n_f, k, rows2, dist2, d_out_rows, d_out_dist);
+    FX_CUDA(cudaGetLastError());
+    ctx->launches += launched2 + 2; c->stats.kernel_launches += launched2 + 2;
+    FX_CUDA(cudaMemcpyAsync(h_flags, d_flags2, size_t(n_f) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FX_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> still;
+    for (int i = 0; i < n_f; ++i) if (h_flags[i]) still.push_back(bad[i]);
+    c->stats.refined_queries += int64_t(n_f - int(still.size()));
+    bad.swap(still);
+  }
+  if (!bad.empty()) {
+    // tier 2: the certificate-free fp64 scan
+    FX_TRY(ctx->d_qlist.ensure(bad.size() * sizeof(int)));
+    FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), bad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    FX_TRY(run_exact_scan(c, d_q, int(n_q), static_cast<int*>(ctx->d_qlist.p), int(bad.size()), metric, k,
+                          run->d_mask, d_out_rows, d_out_dist));
+    FX_CUDA(cudaStreamSynchronize(ctx->stream));  // `bad` must outlive the H2D copy
+    c->stats.fallback_queries += int64_t(bad.size());
+  }
+  FX_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));   // the search now ends here
+  return FX_OK;
+}
+
+// After the final synchronisation of a search: device times from the events, counters.
+static void search_account(fx_corpus* c, const SearchRun& run) {
+  fx_ctx* ctx = c->ctx;
   float ms = 0.f, kms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
-  if (c->n > 0) cudaEventElapsedTime(&kms, ctx->ev_k0, ctx->ev_k1);
-  c->stats.last_search_ms = ms; c->stats.last_main_kernel_ms = kms; c->stats.last_path = path;
-  c->stats.searches++; c->stats.queries += n_q;
-  return FX_OK;
+  cudaEventElapsedTime(&kms, ctx->ev_k0, ctx->ev_k1);
+  c->stats.last_search_ms = ms; c->stats.last_main_kernel_ms = kms; c->stats.last_path = run.path;
+  c->stats.searches++; c->stats.queries += run.n_q;
 }
 
 extern "C" int fx_search_device(fx_corpus* c, const float* d_queries, int64_t n_q, int32_t metric, int32_t k,
                                 int32_t precision, const uint8_t* d_row_mask, int64_t* d_out_rows, float* d_out_dist) {
+  FX_LEASE(c, "fx_search_device");
   FX_TRY(check_search_args(c, d_queries, n_q, metric, k, precision, d_out_rows, d_out_dist));
   if (n_q == 0) return FX_OK;
   fx_ctx* ctx = c->ctx;
   std::lock_guard<std::mutex> lock(ctx->mu);
   FX_TRY(bind(ctx));
-  return search_device_locked(c, d_queries, n_q, metric, k, precision, d_row_mask, d_out_rows, d_out_dist);
+  SearchRun run;
+  FX_TRY(search_enqueue(c, d_queries, n_q, metric, k, precision, d_row_mask, d_out_rows, d_out_dist, &run));
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  bool changed = false;
+  FX_TRY(search_settle(c, &run, &changed));
+  if (changed) FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  search_account(c, run);
+  return FX_OK;
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return pinned;
 }
 
 extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, int32_t k,
                          int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist) {
+  FX_LEASE(c, "fx_search");
   FX_TRY(check_search_args(c, queries, n_q, metric, k, precision, out_rows, out_dist));
   if (n_q == 0) return FX_OK;
   fx_ctx* ctx = c->ctx;
@@ -670,11 +807,8 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
   FX_TRY(ctx->d_rows.ensure(r_bytes));
   FX_TRY(ctx->d_dist.ensure(d_bytes));
   // queries: direct DMA when the caller's buffer is pinned, otherwise through pinned staging
-  cudaPointerAttributes attr{};
-  bool pinned = cudaPointerGetAttributes(&attr, queries) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  cudaGetLastError();
   const void* q_src = queries;
-  if (!pinned) {
+  if (!is_pinned(queries)) {
     FX_TRY(ctx->h_q.ensure(q_bytes));
     std::memcpy(ctx->h_q.p, queries, q_bytes);
     q_src = ctx->h_q.p;
@@ -686,31 +820,37 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
     FX_CUDA(cudaMemcpyAsync(ctx->d_mask.p, row_mask, size_t(c->n), cudaMemcpyHostToDevice, ctx->stream));
     d_mask = static_cast<const uint8_t*>(ctx->d_mask.p);
   }
-  FX_TRY(search_device_locked(c, static_cast<const float*>(ctx->d_q.p), n_q, metric, k, precision, d_mask,
-                              static_cast<int64_t*>(ctx->d_rows.p), static_cast<float*>(ctx->d_dist.p)));
-  // results: straight into the caller's buffers when pinned, else via pinned staging
-  bool out_pinned = cudaPointerGetAttributes(&attr, out_rows) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  bool outd_pinned = cudaPointerGetAttributes(&attr, out_dist) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  if (out_pinned && outd_pinned) {
-    FX_CUDA(cudaMemcpyAsync(out_rows, ctx->d_rows.p, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    FX_CUDA(cudaMemcpyAsync(out_dist, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    FX_CUDA(cudaStreamSynchronize(ctx->stream));
-  } else {
+  SearchRun run;
+  FX_TRY(search_enqueue(c, static_cast<const float*>(ctx->d_q.p), n_q, metric, k, precision, d_mask,
+                        static_cast<int64_t*>(ctx->d_rows.p), static_cast<float*>(ctx->d_dist.p), &run));
+  // results: straight into the caller's buffers when pinned, else via pinned staging. The copies are queued behind the
+  // kernels; the one synchronisation below covers the flagged-query counter too.
+  const bool direct = is_pinned(out_rows) && is_pinned(out_dist);
+  void* dst_rows = out_rows; void* dst_dist = out_dist;
+  if (!direct) {
     FX_TRY(ctx->h_rows.ensure(r_bytes));
     FX_TRY(ctx->h_dist.ensure(d_bytes));
-    FX_CUDA(cudaMemcpyAsync(ctx->h_rows.p, ctx->d_rows.p, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    FX_CUDA(cudaMemcpyAsync(ctx->h_dist.p, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    dst_rows = ctx->h_rows.p; dst_dist = ctx->h_dist.p;
+  }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    FX_CUDA(cudaMemcpyAsync(dst_rows, ctx->d_rows.p, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FX_CUDA(cudaMemcpyAsync(dst_dist, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     FX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (attempt == 1) break;
+    bool changed = false;
+    FX_TRY(search_settle(c, &run, &changed));
+    if (!changed) break;
+  }
+  if (!direct) {
     std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
     std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
   }
+  search_account(c, run);
   return FX_OK;
 }
 
 extern "C" int fx_distances(fx_corpus* c, const float* query, int32_t metric, float* out_dist) {
-  if (!c) return fail(FX_EINVAL, "fx_distances: corpus is NULL");
+  FX_LEASE(c, "fx_distances");
   if (!c->finalized) return fail(FX_ESTATE, "fx_distances: corpus is not finalized");
   if (metric < 0 || metric > 2) return fail(FX_EINVAL, "fx_distances: unknown metric %d", metric);
   if (c->n == 0) return FX_OK;
@@ -722,11 +862,12 @@ extern "C" int fx_distances(fx_corpus* c, const float* query, int32_t metric, fl
   FX_TRY(ctx->d_q.ensure(q_bytes));
   FX_TRY(ctx->d_dist.ensure(d_bytes));
   FX_CUDA(cudaMemcpyAsync(ctx->d_q.p, query, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  const size_t per_q = size_t(c->pitch) * 8 + 8 + 8 + 2 * 8 + 4;
+  const size_t per_q = size_t(c->pitch) * 8 + 8 + 8 + 8 + 2 * 8 + 4;
   if (per_q > 200 * 1024) return fail(FX_EUNSUP, "fx_distances: dim %d too large", c->dim);
   fx::ScanParams p{};
   p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.Q = static_cast<const float*>(ctx->d_q.p);
   p.n_q = 1; p.metric = metric; p.mask = nullptr; p.q_list = nullptr; p.n_list = 1; p.k = 0; p.buf = 2; p.qb = 1;
+  p.floor = nullptr;
   p.partial = nullptr; p.dist_out = static_cast<float*>(ctx->d_dist.p);
   const int64_t tiles = (c->n + fx::SCAN_THREADS - 1) / fx::SCAN_THREADS;
   int W = int(std::min<int64_t>(tiles, int64_t(ctx->sm_count) * 8));
@@ -741,7 +882,8 @@ extern "C" int fx_distances(fx_corpus* c, const float* query, int32_t metric, fl
 }
 
 extern "C" int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, float* out_scores) {
-  if (!c || !queries || !out_scores) return fail(FX_EINVAL, "fx_debug_scores: NULL argument");
+  if (!queries || !out_scores) return fail(FX_EINVAL, "fx_debug_scores: NULL argument");
+  FX_LEASE(c, "fx_debug_scores");
   if (!c->finalized) return fail(FX_ESTATE, "fx_debug_scores: corpus is not finalized");
   if (n_q < 1 || metric < 0 || metric > 2) return fail(FX_EINVAL, "fx_debug_scores: bad arguments");
   fx_ctx* ctx = c->ctx;
@@ -762,12 +904,34 @@ extern "C" int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, 
   s.metric = metric; s.k = 10; s.certify = false; s.out_rows = static_cast<int64_t*>(ctx->d_rows.p);
   s.out_dist = static_cast<float*>(ctx->d_dist.p); s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1;
   s.dbg = d_dbg; s.tau_fixed = nullptr;
-  FX_TRY(configure_filter(c, metric, (std::getenv("FENIX_DEBUG_BF16") && c->tc.ok_b) ? 1 : 0, nullptr, &s));
-  FX_TRY(ctx->d_tc.ensure(fx::tc_scratch_bytes(&ctx->tc, s)));
+  FX_TRY(configure_filter(c, metric, (ctx->tc.knobs.debug_bf16 && c->tc.ok_b) ? 1 : 0, nullptr, &s));
+  const fx::TcLaunch L = fx::tc_prepare(&ctx->tc, s);
+  FX_TRY(ctx->d_tc.ensure(L.scratch_bytes));
   std::string err; int launched = 0;
-  if (!fx::tc_search(&ctx->tc, &c->tc, s, ctx->d_tc.p, &launched, &err)) return fail(FX_ECUDA, "fx_debug_scores: %s", err.c_str());
+  if (!fx::tc_search(&ctx->tc, &c->tc, s, L, ctx->d_tc.p, &launched, &err)) return fail(FX_ECUDA, "fx_debug_scores: %s", err.c_str());
   FX_CUDA(cudaMemcpyAsync(out_scores, d_dbg, 128 * 256 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FX_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// merge of per-shard lists
+// ----------------------------------------------------------------------------------------
+// Lists are [n_q][k] each (rows int64, distances f32), sorted by (distance, row), pads last; list l sits
+// l * rows_stride / l * dist_stride bytes into the two arrays.
+static int enqueue_merge(fx_ctx* ctx, const int64_t* d_rows, const float* d_dist, int n_lists, int64_t n_q, int k,
+                         int64_t rows_stride, int64_t dist_stride, int64_t* d_out_rows, float* d_out_dist) {
+  const int64_t total = int64_t(n_lists) * k;
+  if (total <= 8192) {
+    const int n_sort = next_pow2(std::max(int(total), 2));
+    fx::merge_pairs_kernel<<<unsigned(n_q), 256, size_t(n_sort) * 12, ctx->stream>>>(
+        d_rows, d_dist, n_lists, n_q, k, n_sort, rows_stride, dist_stride, d_out_rows, d_out_dist);
+  } else {
+    fx::merge_rank_kernel<<<unsigned(n_q), 256, 0, ctx->stream>>>(d_rows, d_dist, n_lists, n_q, k, rows_stride, dist_stride,
+                                                                 d_out_rows, d_out_dist);
+  }
+  FX_CUDA(cudaGetLastError());
+  ctx->launches++;
   return FX_OK;
 }
 
@@ -777,17 +941,393 @@ extern "C" int fx_merge_topk(fx_ctx* ctx, const int64_t* d_rows, const float* d_
   if (n_lists < 1 || n_q < 0 || k < 1) return fail(FX_EINVAL, "fx_merge_topk: bad sizes (lists=%d, n_q=%lld, k=%d)", n_lists, (long long)n_q, k);
   if (n_q == 0) return FX_OK;
   if (!d_rows || !d_dist || !d_out_rows || !d_out_dist) return fail(FX_EINVAL, "fx_merge_topk: NULL buffer");
-  const int n_sort = next_pow2(std::max(n_lists * k, 2));
-  if (size_t(n_sort) * 12 > 128 * 1024) return fail(FX_EUNSUP, "fx_merge_topk: lists*k = %d exceeds 8192", n_lists * k);
   std::lock_guard<std::mutex> lock(ctx->mu);
   FX_TRY(bind(ctx));
-  for (int64_t q0 = 0; q0 < n_q; q0 += 1 << 30) {  // grid.x is effectively unbounded for our sizes
-    fx::merge_pairs_kernel<<<unsigned(n_q), 256, size_t(n_sort) * 12, ctx->stream>>>(
-        d_rows, d_dist, n_lists, n_q, k, n_sort, d_out_rows, d_out_dist);
-    break;
-  }
-  FX_CUDA(cudaGetLastError());
-  ctx->launches++;
+  // list-major inputs: list l starts l * n_q * k entries into each array
+  FX_TRY(enqueue_merge(ctx, d_rows, d_dist, n_lists, n_q, k, n_q * int64_t(k) * 8, n_q * int64_t(k) * 4, d_out_rows, d_out_dist));
   FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FX_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// multi-GPU: NCCL communicator owned by the library, sharded search with one host synchronisation
+// ----------------------------------------------------------------------------------------
+// NCCL comes from the process (torch ships libnccl.so.2; the Python binding pre-loads it for a bare server): nothing
+// links against it and the header is not needed - the few entry points used here have had a stable ABI since NCCL 2.0.
+namespace {
+typedef struct ncclComm* ncclComm_t;
+struct ncclUniqueId { char internal[128]; };
+static_assert(sizeof(ncclUniqueId) == FX_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+constexpr int kNcclInt8 = 0;   // ncclInt8 / ncclChar
+
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string error;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* name = std::getenv("FENIX_NCCL_LIB");
+    api.handle = dlopen(name && *name ? name : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) {
+      const char* why = dlerror();
+      api.error = std::string("cannot load NCCL (") + (why ? why : "?") + "); set FENIX_NCCL_LIB to the path of libnccl.so.2";
+      return;
+    }
+    auto sym = [&](const char* s) { void* p = dlsym(api.handle, s); if (!p && api.error.empty()) api.error = std::string("NCCL symbol missing: ") + s; return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  });
+  return &api;
+}
+}  // namespace
+
+#define FX_NCCL(expr)                                                                             \
+  do {                                                                                            \
+    int _r = (expr);                                                                              \
+    if (_r != 0) return fail(FX_ECUDA, "%s failed: %s", #expr, nccl_api()->GetErrorString ? nccl_api()->GetErrorString(_r) : "?"); \
+  } while (0)
+
+struct fx_comm {
+  fx_ctx* ctx = nullptr;
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+};
+
+static int nccl_ready() {
+  NcclApi* api = nccl_api();
+  if (!api->error.empty() || !api->handle) return fail(FX_EUNSUP, "multi-GPU search: %s", api->error.c_str());
+  return FX_OK;
+}
+
+extern "C" int fx_comm_unique_id(void* out_id) {
+  if (!out_id) return fail(FX_EINVAL, "fx_comm_unique_id: NULL argument");
+  FX_TRY(nccl_ready());
+  ncclUniqueId id;
+  FX_NCCL(nccl_api()->GetUniqueId(&id));
+  std::memcpy(out_id, &id, sizeof id);
+  return FX_OK;
+}
+
+extern "C" int fx_comm_init_rank(fx_ctx* ctx, const void* id, int32_t world, int32_t rank, fx_comm** out) {
+  if (!ctx || !id || !out) return fail(FX_EINVAL, "fx_comm_init_rank: NULL argument");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return fail(FX_EINVAL, "fx_comm_init_rank: bad rank %d of %d", rank, world);
+  if (world + 1 > H_WORDS) return fail(FX_EUNSUP, "fx_comm_init_rank: at most %d ranks", H_WORDS - 1);
+  FX_TRY(nccl_ready());
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof uid);
+  fx_comm* cm = new (std::nothrow) fx_comm();
+  if (!cm) return fail(FX_ENOMEM, "fx_comm_init_rank: out of host memory");
+  cm->ctx = ctx; cm->world = world; cm->rank = rank;
+  int r = nccl_api()->CommInitRank(&cm->comm, world, uid, rank);
+  if (r != 0) { delete cm; return fail(FX_ECUDA, "ncclCommInitRank failed: %s", nccl_api()->GetErrorString(r)); }
+  *out = cm;
+  return FX_OK;
+}
+
+extern "C" int fx_comm_destroy(fx_comm* cm) {
+  if (!cm) return fail(FX_EINVAL, "fx_comm_destroy: comm is NULL");
+  {
+    std::lock_guard<std::mutex> lock(cm->ctx->mu);
+    cudaSetDevice(cm->ctx->device);
+    cudaStreamSynchronize(cm->ctx->stream);
+    if (cm->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(cm->comm);
+  }
+  delete cm;
+  return FX_OK;
+}
+
+// Per-rank body of a sharded search (ctx->mu held, device bound). Collective: every rank of the communicator runs it
+// with the same (n_q, metric, k, precision). `queries`: host (whole batch; this rank uploads its slice) or device
+// (whole batch). Outputs host, device or null.
+static int sharded_search_locked(fx_corpus* c, fx_comm* cm, const float* queries, bool q_on_device, int64_t n_q, int metric,
+                                 int k, int precision, const uint8_t* row_mask, bool mask_on_device, int64_t* out_rows,
+                                 float* out_dist, bool out_on_device) {
+  fx_ctx* ctx = c->ctx;
+  NcclApi* api = nccl_api();
+  const int W = cm->world, rank = cm->rank;
+  const int64_t per = (n_q + W - 1) / W;                    // queries per rank slice (the last slices may be short / empty)
+  const size_t row_bytes = size_t(c->dim) * sizeof(float);
+  // ---- queries: upload 1/W of the batch, all-gather the slices over NVLink ----
+  const float* d_q = queries;
+  if (!q_on_device) {
+    FX_TRY(ctx->d_q.ensure(size_t(per) * W * row_bytes));
+    char* qall = static_cast<char*>(ctx->d_q.p);
+    const int64_t lo = std::min<int64_t>(n_q, rank * per), hi = std::min<int64_t>(n_q, lo + per);
+    if (hi > lo) {
+      const char* src = reinterpret_cast<const char*>(queries) + size_t(lo) * row_bytes;
+      const size_t bytes = size_t(hi - lo) * row_bytes;
+      if (!is_pinned(queries)) {
+        FX_TRY(ctx->h_q.ensure(bytes));
+        std::memcpy(ctx->h_q.p, src, bytes);
+        src = static_cast<const char*>(ctx->h_q.p);
+      }
+      FX_CUDA(cudaMemcpyAsync(qall + size_t(lo) * row_bytes, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (W > 1) FX_NCCL(api->AllGather(qall + size_t(rank) * per * row_bytes, qall, size_t(per) * row_bytes, kNcclInt8, cm->comm, ctx->stream));
+    d_q = reinterpret_cast<const float*>(qall);
+  }
+  const uint8_t* d_mask = nullptr;
+  if (row_mask && c->n > 0) {
+    if (mask_on_device) d_mask = row_mask;
+    else {
+      FX_TRY(ctx->d_mask.ensure(size_t(c->n)));
+      FX_CUDA(cudaMemcpyAsync(ctx->d_mask.p, row_mask, size_t(c->n), cudaMemcpyHostToDevice, ctx->stream));
+      d_mask = static_cast<const uint8_t*>(ctx->d_mask.p);
+    }
+  }
+  // ---- exchange buffer: W slots of [rows n_q*k int64][distances n_q*k f32][header 16 B]; the shard search writes
+  // this rank's slot in place and the all-gather is in place too ----
+  const size_t nk = size_t(n_q) * k;
+  const size_t hdr_off = (nk * 12 + 15) & ~size_t(15), slot = hdr_off + 16;
+  FX_TRY(ctx->d_xchg.ensure(slot * W));
+  char* xb = static_cast<char*>(ctx->d_xchg.p);
+  char* mine = xb + slot * rank;
+  int64_t* my_rows = reinterpret_cast<int64_t*>(mine);
+  float* my_dist = reinterpret_cast<float*>(mine + nk * 8);
+  const bool want_out = out_rows != nullptr;
+  int64_t* d_res_rows = nullptr; float* d_res_dist = nullptr;
+  if (want_out) {
+    if (out_on_device) { d_res_rows = out_rows; d_res_dist = out_dist; }
+    else {
+      FX_TRY(ctx->d_rows.ensure(nk * 8));
+      FX_TRY(ctx->d_dist.ensure(nk * 4));
+      d_res_rows = static_cast<int64_t*>(ctx->d_rows.p); d_res_dist = static_cast<float*>(ctx->d_dist.p);
+    }
+  }
+  const bool direct = want_out && !out_on_device && is_pinned(out_rows) && is_pinned(out_dist);
+  void* h_rows = out_rows; void* h_dist = out_dist;
+  if (want_out && !out_on_device && !direct) {
+    FX_TRY(ctx->h_rows.ensure(nk * 8));
+    FX_TRY(ctx->h_dist.ensure(nk * 4));
+    h_rows = ctx->h_rows.p; h_dist = ctx->h_dist.p;
+  }
+
+  SearchRun run;
+  FX_TRY(search_enqueue(c, d_q, n_q, metric, k, precision, d_mask, my_rows, my_dist, &run));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // header word 0: queries of this shard whose result is not final yet (first exchange only)
+    if (attempt == 0 && run.tc && run.s.certify)
+      FX_CUDA(cudaMemcpyAsync(mine + hdr_off, fx::tc_flag_count(ctx->d_tc.p), sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+      FX_CUDA(cudaMemsetAsync(mine + hdr_off, 0, 16, ctx->stream));
+    FX_CUDA(cudaEventRecord(ctx->ev_x0, ctx->stream));
+    if (W > 1) FX_NCCL(api->AllGather(mine, xb, slot, kNcclInt8, cm->comm, ctx->stream));
+    if (want_out) {
+      FX_TRY(enqueue_merge(ctx, reinterpret_cast<const int64_t*>(xb), reinterpret_cast<const float*>(xb + nk * 8), W, n_q, k,
+                           int64_t(slot), int64_t(slot), d_res_rows, d_res_dist));
+    }
+    FX_CUDA(cudaEventRecord(ctx->ev_x1, ctx->stream));
+    if (want_out && !out_on_device) {
+      FX_CUDA(cudaMemcpyAsync(h_rows, d_res_rows, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      FX_CUDA(cudaMemcpyAsync(h_dist, d_res_dist, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    // every rank's header word, strided out of the gathered slots -> pinned h_word[1 .. W]
+    FX_CUDA(cudaMemcpy2DAsync(ctx->h_word + 1, sizeof(int), xb + hdr_off, slot, sizeof(int), size_t(W), cudaMemcpyDeviceToHost, ctx->stream));
+    FX_CUDA(cudaStreamSynchronize(ctx->stream));   // the ONE synchronisation of the common path
+    if (attempt == 1) break;
+    bool any = false;
+    for (int r = 0; r < W; ++r) any = any || ctx->h_word[1 + r] != 0;
+    if (!any) break;
+    // some shard's certificate failed for some query: those ranks repair their lists, then EVERY rank repeats the exchange
+    bool changed = false;
+    FX_TRY(search_settle(c, &run, &changed));
+  }
+  if (want_out && !out_on_device && !direct) {
+    std::memcpy(out_rows, ctx->h_rows.p, nk * 8);
+    std::memcpy(out_dist, ctx->h_dist.p, nk * 4);
+  }
+  search_account(c, run);
+  float xms = 0.f;
+  cudaEventElapsedTime(&xms, ctx->ev_x0, ctx->ev_x1);
+  c->stats.last_exchange_ms = xms;
+  return FX_OK;
+}
+
+extern "C" int fx_search_sharded(fx_corpus* c, fx_comm* cm, const float* queries, int64_t n_q, int32_t metric, int32_t k,
+                                 int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist) {
+  if (!cm) return fail(FX_EINVAL, "fx_search_sharded: comm is NULL");
+  FX_LEASE(c, "fx_search_sharded");
+  FX_TRY(check_search_args(c, queries, n_q, metric, k, precision, out_rows, out_dist, false));
+  if (cm->ctx != c->ctx) return fail(FX_EINVAL, "fx_search_sharded: corpus and communicator live on different contexts");
+  if (n_q == 0) return FX_OK;
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  return sharded_search_locked(c, cm, queries, false, n_q, metric, k, precision, row_mask, false, out_rows, out_dist, false);
+}
+
+extern "C" int fx_search_sharded_device(fx_corpus* c, fx_comm* cm, const float* d_queries, int64_t n_q, int32_t metric,
+                                        int32_t k, int32_t precision, const uint8_t* d_row_mask, int64_t* d_out_rows,
+                                        float* d_out_dist) {
+  if (!cm) return fail(FX_EINVAL, "fx_search_sharded_device: comm is NULL");
+  FX_LEASE(c, "fx_search_sharded_device");
+  FX_TRY(check_search_args(c, d_queries, n_q, metric, k, precision, d_out_rows, d_out_dist, false));
+  if (cm->ctx != c->ctx) return fail(FX_EINVAL, "fx_search_sharded_device: corpus and communicator live on different contexts");
+  if (n_q == 0) return FX_OK;
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  return sharded_search_locked(c, cm, d_queries, true, n_q, metric, k, precision, d_row_mask, true, d_out_rows, d_out_dist, true);
+}
+
+// ----------------------------------------------------------------------------------------
+// one process, several devices: a context, a communicator and a worker thread per device
+// ----------------------------------------------------------------------------------------
+struct GroupJob {
+  fx_corpus* const* shards = nullptr;
+  const float* queries = nullptr; int64_t n_q = 0; int metric = 0, k = 0, precision = 0;
+  const uint8_t* row_mask = nullptr; int64_t* out_rows = nullptr; float* out_dist = nullptr;
+};
+
+struct fx_group {
+  int n = 0;
+  std::vector<fx_ctx*> ctxs;
+  std::vector<fx_comm*> comms;
+  std::vector<std::thread> workers;
+  std::mutex search_mu;            // collective searches on a group serialise
+  std::mutex mu;                   // job hand-off
+  std::condition_variable cv_go, cv_done;
+  uint64_t generation = 0;
+  int pending = 0;
+  bool quit = false;
+  GroupJob job;
+  std::vector<int> rc;
+  std::vector<std::string> err;
+};
+
+static void group_worker(fx_group* g, int i) {
+  uint64_t seen = 0;
+  cudaSetDevice(g->ctxs[i]->device);
+  for (;;) {
+    GroupJob job;
+    {
+      std::unique_lock<std::mutex> lock(g->mu);
+      g->cv_go.wait(lock, [&] { return g->quit || g->generation != seen; });
+      if (g->quit) return;
+      seen = g->generation;
+      job = g->job;
+    }
+    fx_corpus* c = job.shards[i];
+    const uint8_t* mask = job.row_mask ? job.row_mask + (c->row_base - job.shards[0]->row_base) : nullptr;
+    int rc = fx_search_sharded(c, g->comms[i], job.queries, job.n_q, job.metric, job.k, job.precision, mask,
+                               i == 0 ? job.out_rows : nullptr, i == 0 ? job.out_dist : nullptr);
+    {
+      std::lock_guard<std::mutex> lock(g->mu);
+      g->rc[i] = rc;
+      if (rc != FX_OK) g->err[i] = g_last_error;   // thread-local of the worker: hand it to the caller
+      if (--g->pending == 0) g->cv_done.notify_all();
+    }
+  }
+}
+
+extern "C" int fx_group_create(const int32_t* devices, int32_t n_devices, fx_group** out) {
+  if (!devices || !out) return fail(FX_EINVAL, "fx_group_create: NULL argument");
+  *out = nullptr;
+  if (n_devices < 1 || n_devices + 1 > H_WORDS) return fail(FX_EINVAL, "fx_group_create: bad device count %d", n_devices);
+  for (int i = 0; i < n_devices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return fail(FX_EINVAL, "fx_group_create: device %d listed twice", devices[i]);
+  fx_group* g = new (std::nothrow) fx_group();
+  if (!g) return fail(FX_ENOMEM, "fx_group_create: out of host memory");
+  g->n = n_devices;
+  auto cleanup = [&]() {
+    for (fx_comm* cm : g->comms) if (cm) { if (cm->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(cm->comm); delete cm; }
+    for (fx_ctx* c : g->ctxs) if (c) fx_shutdown(c);
+    delete g;
+  };
+  for (int i = 0; i < n_devices; ++i) {
+    fx_ctx* ctx = nullptr;
+    int r = fx_init(devices[i], &ctx);
+    if (r != FX_OK) { cleanup(); return r; }
+    g->ctxs.push_back(ctx);
+  }
+  if (n_devices > 1) {
+    int r = nccl_ready();
+    if (r != FX_OK) { cleanup(); return r; }
+    std::vector<ncclComm_t> comms(n_devices, nullptr);
+    std::vector<int> devs(devices, devices + n_devices);
+    int nr = nccl_api()->CommInitAll(comms.data(), n_devices, devs.data());
+    if (nr != 0) { cleanup(); return fail(FX_ECUDA, "ncclCommInitAll failed: %s", nccl_api()->GetErrorString(nr)); }
+    for (int i = 0; i < n_devices; ++i) {
+      fx_comm* cm = new fx_comm();
+      cm->ctx = g->ctxs[i]; cm->comm = comms[i]; cm->world = n_devices; cm->rank = i;
+      g->comms.push_back(cm);
+    }
+    g->rc.assign(n_devices, FX_OK);
+    g->err.assign(n_devices, std::string());
+    for (int i = 0; i < n_devices; ++i) g->workers.emplace_back(group_worker, g, i);
+  }
+  *out = g;
+  return FX_OK;
+}
+
+extern "C" int fx_group_size(fx_group* g) { return g ? g->n : fail(FX_EINVAL, "fx_group_size: group is NULL"); }
+extern "C" fx_ctx* fx_group_ctx(fx_group* g, int32_t i) {
+  if (!g || i < 0 || i >= g->n) { fail(FX_EINVAL, "fx_group_ctx: bad argument"); return nullptr; }
+  return g->ctxs[i];
+}
+
+extern "C" int fx_group_search(fx_group* g, fx_corpus* const* shards, const float* queries, int64_t n_q, int32_t metric,
+                               int32_t k, int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist) {
+  if (!g || !shards) return fail(FX_EINVAL, "fx_group_search: NULL argument");
+  if (n_q > 0 && (!queries || !out_rows || !out_dist)) return fail(FX_EINVAL, "fx_group_search: NULL buffer");
+  if (n_q == 0) return FX_OK;
+  std::vector<std::unique_ptr<Lease>> leases;
+  for (int i = 0; i < g->n; ++i) {
+    leases.emplace_back(new Lease(shards[i]));
+    if (!leases.back()->ok) return fail(FX_EINVAL, "fx_group_search: shard %d is not a live corpus handle", i);
+    if (shards[i]->ctx != g->ctxs[i]) return fail(FX_EINVAL, "fx_group_search: shard %d does not live on fx_group_ctx(g, %d)", i, i);
+    if (i > 0 && shards[i]->row_base != shards[i - 1]->row_base + shards[i - 1]->n)
+      return fail(FX_EINVAL, "fx_group_search: shards must hold contiguous row ranges in order (shard %d starts at %lld, expected %lld)",
+                  i, (long long)shards[i]->row_base, (long long)(shards[i - 1]->row_base + shards[i - 1]->n));
+  }
+  if (g->n == 1) return fx_search(shards[0], queries, n_q, metric, k, precision, row_mask, out_rows, out_dist);
+  std::lock_guard<std::mutex> serial(g->search_mu);
+  {
+    std::lock_guard<std::mutex> lock(g->mu);
+    g->job = GroupJob{shards, queries, n_q, metric, k, precision, row_mask, out_rows, out_dist};
+    g->pending = g->n;
+    g->generation++;
+  }
+  g->cv_go.notify_all();
+  {
+    std::unique_lock<std::mutex> lock(g->mu);
+    g->cv_done.wait(lock, [&] { return g->pending == 0; });
+  }
+  for (int i = 0; i < g->n; ++i)
+    if (g->rc[i] != FX_OK) return fail(g->rc[i], "fx_group_search (device %d): %s", g->ctxs[i]->device, g->err[i].c_str());
+  return FX_OK;
+}
+
+extern "C" int fx_group_destroy(fx_group* g) {
+  if (!g) return fail(FX_EINVAL, "fx_group_destroy: group is NULL");
+  {
+    std::lock_guard<std::mutex> serial(g->search_mu);
+    {
+      std::lock_guard<std::mutex> lock(g->mu);
+      g->quit = true;
+    }
+    g->cv_go.notify_all();
+    for (std::thread& t : g->workers) t.join();
+  }
+  for (fx_comm* cm : g->comms) fx_comm_destroy(cm);
+  for (fx_ctx* c : g->ctxs) fx_shutdown(c);
+  delete g;
   return FX_OK;
 }

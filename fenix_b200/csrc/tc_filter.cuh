@@ -56,7 +56,13 @@ constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_NORM_BYTES = TC_BN * 4;        // per accumulator stage
 constexpr uint32_t TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES +
-                                   TC_ACC_STAGES * TC_NORM_BYTES + 256 /*barriers*/;
+                                   TC_ACC_STAGES * TC_NORM_BYTES + 512 /*barriers*/;
+constexpr int TC2_STAGES = 6;               // CTA-pair kernel: stages of (query k-block, HALF a corpus k-block), 32 KB each
+constexpr uint32_t TC2_B_BYTES = TC_B_BYTES / 2;
+constexpr uint32_t TC2_STAGE_BYTES = TC_A_BYTES + TC2_B_BYTES;
+constexpr uint32_t TC2_SMEM_BYTES = 1024 /*align slack*/ + TC2_STAGES * TC2_STAGE_BYTES +
+                                    TC_ACC_STAGES * TC_NORM_BYTES + 512 /*barriers*/;
+constexpr size_t TC_HDR_BYTES = 256;        // scratch header (word 0: flagged-query counter of the last finish launch)
 constexpr int TC_MAX_WAVES = 4;            // units per CTA at most (bounds the candidate-buffer scratch)
 constexpr uint32_t ORD_NEG_INF = 0x007fffffu;  // f2ord(-inf)
 
@@ -80,9 +86,73 @@ inline ShadowGeom shadow_geom(int dim) {
   return g;
 }
 
+// Tuning knobs. Read from the environment ONCE per context (fx_init) - the search path never calls getenv - and
+// settable per context afterwards through fx_set_option (same names).
+struct TcKnobs {
+  int kp = 0;              // FENIX_TC_KP          force K' (candidates reranked per query)
+  int fullk = 0;           // FENIX_TC_FULLK       multiply the zero padding of the last k-block too
+  int no_rq = 0;           // FENIX_TC_NO_RQ       never take the resident-query kernel
+  int slices = 0;          // FENIX_TC_SLICES      force the corpus slice count
+  int order = -1;          // FENIX_TC_ORDER       unit order of the one-CTA streaming kernel (1 = query-tile major)
+  int kp_list = 0;         // FENIX_TC_KP_LIST     candidates each (query, list) keeps at a selection
+  int pre_wide = 0;        // FENIX_TC_PRE_WIDE    sample prepass also for wide rows at large batches
+  int pre = -1;            // FENIX_TC_PRE         0: no sample prepass
+  double pre_safety = 0.0; // FENIX_TC_PRE_SAFETY
+  double pre_m = 0.0;      // FENIX_TC_PRE_M
+  int pf = 0;              // FENIX_TC_PF          L2 prefetch distance in tiles
+  int rq_stages = 0;       // FENIX_RQ_STAGES
+  int fin_threads = 0;     // FENIX_FIN_THREADS
+  int warm = 0;            // FENIX_TC_WARM        keep thresholds of the previous search (experiments only)
+  int pair = -1;           // FENIX_TC_PAIR        CTA-pair streaming kernel: 0 never, 1 whenever possible, -1 auto
+  int fp32_filter_tf32 = 0;// FENIX_FP32_FILTER_TF32  exact mode filters with TF32 over the fp32 rows even when a shadow exists
+  int no_refine = 0;       // FENIX_NO_REFINE      flagged queries go straight to the fp64 scan
+  int no_norm_shadow = 0;  // FENIX_NO_NORM_SHADOW cosine keeps the plain shadow + multiplicative epilogue
+  int debug_bf16 = 0;      // FENIX_DEBUG_BF16     fx_debug_scores dumps the bf16 filter's scores
+};
+// name = the environment variable's name; value = its text, or null to restore the default. False: unknown name.
+inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
+  const std::string n(name ? name : "");
+  const TcKnobs d{};
+  auto as_int = [&](int dflt) { return value ? std::atoi(value) : dflt; };
+  auto as_flag = [&]() { return (value && std::atoi(value) != 0) ? 1 : 0; };   // switches: a non-zero integer sets them
+  auto as_dbl = [&]() { return value ? std::atof(value) : 0.0; };
+  if (n == "FENIX_TC_KP") k->kp = as_int(d.kp);
+  else if (n == "FENIX_TC_FULLK") k->fullk = as_flag();
+  else if (n == "FENIX_TC_NO_RQ") k->no_rq = as_flag();
+  else if (n == "FENIX_TC_SLICES") k->slices = as_int(d.slices);
+  else if (n == "FENIX_TC_ORDER") k->order = as_int(d.order);
+  else if (n == "FENIX_TC_KP_LIST") k->kp_list = as_int(d.kp_list);
+  else if (n == "FENIX_TC_PRE_WIDE") k->pre_wide = as_flag();
+  else if (n == "FENIX_TC_PRE") k->pre = as_int(d.pre);
+  else if (n == "FENIX_TC_PRE_SAFETY") k->pre_safety = as_dbl();
+  else if (n == "FENIX_TC_PRE_M") k->pre_m = as_dbl();
+  else if (n == "FENIX_TC_PF") k->pf = as_int(d.pf);
+  else if (n == "FENIX_RQ_STAGES") k->rq_stages = as_int(d.rq_stages);
+  else if (n == "FENIX_FIN_THREADS") k->fin_threads = as_int(d.fin_threads);
+  else if (n == "FENIX_TC_WARM") k->warm = as_flag();
+  else if (n == "FENIX_TC_PAIR") k->pair = as_int(d.pair);
+  else if (n == "FENIX_FP32_FILTER_TF32") k->fp32_filter_tf32 = as_flag();
+  else if (n == "FENIX_NO_REFINE") k->no_refine = as_flag();
+  else if (n == "FENIX_NO_NORM_SHADOW") k->no_norm_shadow = as_flag();
+  else if (n == "FENIX_DEBUG_BF16") k->debug_bf16 = as_flag();
+  else return false;
+  return true;
+}
+inline void tc_knobs_from_env(TcKnobs* k) {
+  static const char* const names[] = {
+      "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
+      "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
+      "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
+      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16"};
+  for (const char* name : names) {
+    if (const char* v = std::getenv(name)) tc_set_knob(k, name, v);
+  }
+}
+
 struct TcState {
   int sm_count = 0;
   void* encode = nullptr;  // cuTensorMapEncodeTiled
+  TcKnobs knobs;
 };
 struct TcCorpus {
   CUtensorMap map_x;       // [n_rows][pitch] fp32, box 32 x 256, 128B swizzle
@@ -212,6 +282,54 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on one TPC share the B operand of a 256-row MMA ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on an mbarrier that may live in the peer
+// CTA of the pair (the leader's "stage full" barrier)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows from each CTA] * B[N/2 rows from each CTA]^T, issued by one thread of the leader
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive (once the pair's previously issued MMAs have completed) on the mbarrier at this offset in BOTH CTAs.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(uint16_t(3)) : "memory");
 }
 
 // K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart).
@@ -401,15 +519,25 @@ __device__ __noinline__ uint32_t warp_select_compact(uint2* buf, int cnt, int kp
 //    passing quads and, per quad in the union, re-reads those four columns from TMEM (tcgen05.ld.x4 takes a runtime
 //    column address, registers cannot be indexed) and appends what passes: one compact loop instead of 32 unrolled
 //    append sites per chunk. Columns past the shard's last row are rejected here, so the scan needs no tail handling.
-template <int METRIC, int MODE>   // MODE 0: filter, 1: filter + raw score dump (diagnostics), 2: threshold prepass (block maximum only)
+// PAIR (CTA-pair kernel): the accumulator is handed back to the LEADER's MMA warp (release_leader: shared::cluster
+// address of its barrier) and, separately, the norm buffer to this CTA's own producer (norm_release).
+template <int METRIC, int MODE, int PAIR = 0>   // MODE 0: filter, 1: filter + raw score dump (diagnostics), 2: threshold prepass (block maximum only)
 __device__ __forceinline__ void epi_tile(uint32_t t_acc, int ncols, const float* nrm, int col0, float tau, uint2* buf,
-                                         uint32_t& wn, uint64_t* release_bar, uint32_t lane, float* dbg_row, float* pre_out) {
+                                         uint32_t& wn, uint64_t* release_bar, uint32_t release_leader, uint64_t* norm_release,
+                                         uint32_t lane, float* dbg_row, float* pre_out) {
   constexpr bool DBG = MODE == 1;
   float blk_max = -INFINITY;
   auto release = [&]() {
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(release_bar);
+    if (lane == 0) {
+      if (PAIR) {
+        mbar_arrive_cluster(release_leader);
+        if (METRIC != 2) mbar_arrive(norm_release);
+      } else {
+        mbar_arrive(release_bar);
+      }
+    }
   };
   auto scan = [&](uint32_t (&v)[TC_CW], int c) {
     if (METRIC != 2) {
@@ -524,100 +652,137 @@ __device__ __forceinline__ void epi_tighten(const TcParams& p, bool active, int 
 // ---------------------------------------------------------------------------------------------
 // KIND 0: fp32 operands read as TF32 (k-block = 32 elements, UMMA K = 8)
 // KIND 1: bf16 operands          (k-block = 64 elements, UMMA K = 16); both are 128 B rows / 32 B per MMA
-template <int METRIC, int KIND, int MODE>
+// PAIR 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, bf16 shadow only). The pair computes a 256-query x 256-row
+//         tile per MMA: each CTA stages ITS query tile (A, 16 KB per k-block) and HALF of the corpus block (B, 128 of
+//         the 256 rows, 16 KB); the tensor cores of both SMs read both halves. Per SM and k-block that is 32 KB of
+//         L2 -> SM operand traffic instead of 48 KB, at the same tensor work (measured on C3, one CTA per tile:
+//         742.8 GB per launch = 96 B/clk/SM at the full tensor rate, more than the fabric delivers once the power cap
+//         lifts). The leader (cluster rank 0) issues every MMA; "stage full" lives in the leader (both CTAs' TMA
+//         loads count their bytes there), "stage empty" / "accumulator full" are multicast to both CTAs by
+//         tcgen05.commit, "accumulator empty" collects the epilogue warps of both CTAs in the leader.
+//         Units: (query-tile pair) x (corpus slice); CTA r of the pair owns query tile 2*qp + r and keeps the
+//         candidate lists of "CTA unit" slice * (2 n_qp) + 2 qp + r, the layout the finish kernel reads.
+template <int METRIC, int KIND, int MODE, int PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcParams p) {
+  static_assert(!PAIR || KIND == 1, "CTA pairs stream the bf16 shadow");
+  constexpr int STAGES = PAIR ? TC2_STAGES : TC_STAGES;
+  constexpr uint32_t B_BYTES = PAIR ? TC2_B_BYTES : TC_B_BYTES;
+  constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment for the 128B-swizzled operand tiles
+  // 1024-byte alignment for the 128B-swizzled operand tiles (the offset is the same in both CTAs of a pair:
+  // the dynamic shared memory window starts at the same offset in every CTA of a kernel)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* tiles = smem;
-  float* norm_smem = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_ACC_STAGES * TC_NORM_BYTES);
-  uint64_t* full_bar = bars;                         // [TC_STAGES]   TMA -> MMA
-  uint64_t* empty_bar = bars + TC_STAGES;            // [TC_STAGES]   MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * TC_STAGES;        // [2]           MMA -> epilogue
-  uint64_t* tmem_empty = tmem_full + TC_ACC_STAGES;  // [2]           epilogue -> MMA / TMA(norms)
+  float* norm_smem = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + TC_ACC_STAGES * TC_NORM_BYTES);
+  uint64_t* full_bar = bars;                         // [STAGES]      TMA -> MMA          (PAIR: the leader's is used)
+  uint64_t* empty_bar = bars + STAGES;               // [STAGES]      MMA -> TMA          (PAIR: multicast to both CTAs)
+  uint64_t* tmem_full = bars + 2 * STAGES;           // [2]           MMA -> epilogue     (PAIR: multicast to both CTAs)
+  uint64_t* tmem_empty = tmem_full + TC_ACC_STAGES;  // [2]           epilogue -> MMA     (PAIR: both CTAs' warps, in the leader)
   uint64_t* norm_full = tmem_empty + TC_ACC_STAGES;  // [2]           TMA(norms) -> epilogue
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + TC_ACC_STAGES);
+  uint64_t* norm_empty = norm_full + TC_ACC_STAGES;  // [2]           epilogue -> TMA(norms) (PAIR only; otherwise tmem_empty serves)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_empty + TC_ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader
+  const int cid = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);   // persistent worker index (cluster / CTA)
+  const int n_workers = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_q);
     prefetch_tmap(&map_x);
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < TC_ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], TC_EPI_WARPS);
+      mbar_init(&tmem_empty[i], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);
       mbar_init(&norm_full[i], 1);
+      mbar_init(&norm_empty[i], TC_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  if (warp == 2) { if (PAIR) tmem_alloc_pair(tmem_ptr, 512); else tmem_alloc(tmem_ptr, 512); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();    // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_units = p.n_slices * p.n_qt;
+  const int n_qp = (p.n_qt + 1) >> 1;
+  const int n_units = PAIR ? p.n_slices * n_qp : p.n_slices * p.n_qt;
   const int n_rows_i = int(p.n_rows);   // < 2^31 (tc_supported)
+  // worker unit u -> (query tile of THIS CTA, corpus slice, index of this CTA's candidate-list block)
+  auto decode = [&](int u, int& qt, int& slice, int& cu) {
+    if (PAIR) { const int qp = u % n_qp; slice = u / n_qp; qt = 2 * qp + int(rank); cu = slice * (2 * n_qp) + qt; }
+    else { qt = p.qt_major ? u / p.n_slices : u % p.n_qt; slice = p.qt_major ? u % p.n_slices : u / p.n_qt; cu = u; }
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int qt = p.qt_major ? u / p.n_slices : u % p.n_qt, slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
+      const uint32_t full_leader = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0u;   // the leader's full_bar[0]
+      for (int u = cid; u < n_units; u += n_workers) {
+        int qt, slice, cu; decode(u, qt, slice, cu);
         const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_vtiles, t0 + p.tiles_per_slice);
         for (int tv = t0; tv < t1; ++tv) {
           const int t = tv * p.tile_stride;
           if (METRIC != 2) {
             // per-column norm terms of this tile ride along, one buffer per accumulator stage
-            mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, p.sleep_ns);
+            mbar_wait_backoff(PAIR ? &norm_empty[acc] : &tmem_empty[acc], acc_phase ^ 1, p.sleep_ns);
             mbar_expect_tx(&norm_full[acc], TC_NORM_BYTES);
             const float* src = (METRIC == 0 ? p.hx : p.rx) + size_t(t) * TC_BN;
             bulk_load_1d(norm_smem + acc * TC_BN, src, TC_NORM_BYTES, &norm_full[acc]);
           }
           for (int kb = 0; kb < p.n_kblocks; ++kb) {
             mbar_wait_backoff(&empty_bar[stage], phase ^ 1, p.sleep_ns);
-            mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-            unsigned char* a_dst = tiles + stage * TC_STAGE_BYTES;
+            unsigned char* a_dst = tiles + stage * STAGE_BYTES;
             constexpr int kElemsPerBlock = KIND == 0 ? TC_BK : 2 * TC_BK;
-            tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * kElemsPerBlock, qt * TC_BM);
-            if (KIND == 0) tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * kElemsPerBlock, t * TC_BN);
-            else {
-              tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0,                   // tiled shadow: one contiguous 32 KB block
-                          kb < p.n_kb_data ? (t * p.n_kb_data + kb) * TC_BN : p.aug_line0 + t * TC_BN);
+            // tiled shadow: one contiguous block of 256 (PAIR: this CTA's 128) rows x 128 B
+            const int line = kb < p.n_kb_data ? (t * p.n_kb_data + kb) * TC_BN : p.aug_line0 + t * TC_BN;
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);    // both CTAs' query + corpus blocks
+              const uint32_t bar = full_leader + uint32_t(stage) * 8u;
+              tma_load_2d_pair(&map_q, bar, a_dst, kb * kElemsPerBlock, qt * TC_BM);
+              tma_load_2d_pair(&map_x, bar, a_dst + TC_A_BYTES, 0, line + int(rank) * (TC_BN / 2));
+            } else {
+              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+              tma_load_2d(&map_q, &full_bar[stage], a_dst, kb * kElemsPerBlock, qt * TC_BM);
+              if (KIND == 0) tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, kb * kElemsPerBlock, t * TC_BN);
+              else {
+                tma_load_2d(&map_x, &full_bar[stage], a_dst + TC_A_BYTES, 0, line);
 #ifndef FENIX_NO_PFCODE
-              if (p.pf_tiles > 0 && tv + p.pf_tiles < t1) {
-                const int tp = (tv + p.pf_tiles) * p.tile_stride;
-                const int64_t line = kb < p.n_kb_data ? (int64_t(tp) * p.n_kb_data + kb) * TC_BN : int64_t(p.aug_line0) + int64_t(tp) * TC_BN;
-                prefetch_l2(p.xb + line * 128, TC_B_BYTES);
-              }
+                if (p.pf_tiles > 0 && tv + p.pf_tiles < t1) {
+                  const int tp = (tv + p.pf_tiles) * p.tile_stride;
+                  const int64_t linep = kb < p.n_kb_data ? (int64_t(tp) * p.n_kb_data + kb) * TC_BN : int64_t(p.aug_line0) + int64_t(tp) * TC_BN;
+                  prefetch_l2(p.xb + linep * 128, TC_B_BYTES);
+                }
 #endif
+              }
             }
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (PAIR: the leader CTA issues for both) =====================
     // The whole warp runs the loop (warp-uniform control flow keeps descriptors and addresses in uniform registers;
     // under `if (lane == 0)` the compiler wraps every MMA in a register-broadcast loop), one elected lane issues.
     {
-      constexpr uint32_t idesc = KIND == 0 ? make_idesc_tf32(TC_BM, TC_BN) : make_idesc_bf16(TC_BM, TC_BN);
+      constexpr uint32_t idesc = KIND == 0 ? make_idesc_tf32(TC_BM, TC_BN)
+                                           : make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, TC_BN);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t desc0 = make_smem_desc(0);
       const uint32_t tiles_lo = smem_u32(tiles) >> 4;
       const int n_kb = p.n_kblocks, n_kb_data = p.n_kb_data, nk_last = p.nk_last;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
+      for (int u = cid; u < n_units; u += n_workers) {
+        int qt, slice, cu; decode(u, qt, slice, cu);
         const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_vtiles, t0 + p.tiles_per_slice);
         for (int t = t0; t < t1; ++t) {
           mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1, p.sleep_ns >> 1);
@@ -625,27 +790,36 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint64_t a_desc = desc0 | uint64_t(tiles_lo + uint32_t(stage) * (TC_STAGE_BYTES >> 4));
+            const uint64_t a_desc = desc0 | uint64_t(tiles_lo + uint32_t(stage) * (STAGE_BYTES >> 4));
             const uint64_t b_desc = a_desc + (TC_A_BYTES >> 4);
             const int nk = kb < n_kb_data - 1 ? TC_BK / TC_UMMA_K : (kb == n_kb_data - 1 ? nk_last : 1);
             if (elect_one()) {
               // advance 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-              if (KIND == 0) {
-                umma_tf32(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
-                if (nk > 1) umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                if (nk > 2) umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                if (nk > 3) umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              if (PAIR) {
+                umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                if (nk > 1) umma_bf16_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                if (nk > 2) umma_bf16_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                if (nk > 3) umma_bf16_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                umma_commit_pair(&empty_bar[stage]);                       // frees the stage in BOTH CTAs
+                if (kb == n_kb - 1) umma_commit_pair(&tmem_full[acc]);     // accumulators ready in both CTAs
               } else {
-                umma_bf16(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
-                if (nk > 1) umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                if (nk > 2) umma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                if (nk > 3) umma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                if (KIND == 0) {
+                  umma_tf32(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                  if (nk > 1) umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                  if (nk > 2) umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                  if (nk > 3) umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                } else {
+                  umma_bf16(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                  if (nk > 1) umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                  if (nk > 2) umma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                  if (nk > 3) umma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                }
+                umma_commit(&empty_bar[stage]);                       // frees the smem stage once these MMAs retire
+                if (kb == n_kb - 1) umma_commit(&tmem_full[acc]);     // accumulator ready for the epilogue
               }
-              umma_commit(&empty_bar[stage]);                       // frees the smem stage once these MMAs retire
-              if (kb == n_kb - 1) umma_commit(&tmem_full[acc]);     // accumulator ready for the epilogue
             }
             __syncwarp();
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
@@ -659,17 +833,19 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int row_in_tile = lane_grp * 32 + int(lane);
     const int slot = half * TC_BM + row_in_tile; // candidate buffer of this thread
     const uint32_t t_lane = tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(half * TC_HALF_COLS);
+    // PAIR: the accumulator goes back to the leader's MMA warp (arrive in the leader), the norm buffer to this CTA's producer
+    const uint32_t tmem_empty_leader = PAIR ? mapa_u32(smem_u32(tmem_empty), 0) : 0u;
     int acc = 0; uint32_t acc_phase = 0;
 
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int qt = p.qt_major ? u / p.n_slices : u % p.n_qt, slice = p.qt_major ? u % p.n_slices : u / p.n_qt;
+    for (int u = cid; u < n_units; u += n_workers) {
+      int qt, slice, cu; decode(u, qt, slice, cu);
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.n_vtiles, t0 + p.tiles_per_slice);
       // tile row j = lane_grp*32 + lane holds query qt*128 + lane*4 + lane_grp (see knn_prep_kernel): a small
       // batch is spread over all four lane groups, i.e. over all epilogue warps and SM sub-partitions
       const int q = qt * TC_BM + int(lane) * 4 + lane_grp;
       const bool active = q < p.n_q;
       const bool any_active = __any_sync(0xffffffffu, active);
-      uint2* buf = p.wbuf + (size_t(u) * TC_SLOTS + slot) * p.cap;
+      uint2* buf = p.wbuf + (size_t(cu) * TC_SLOTS + slot) * p.cap;
       uint32_t wn = 0;   // entries in the buffer
       float tau = active ? -INFINITY : INFINITY;   // lanes past the last query never admit anything
       if (p.fixed && active) tau = ord2f(p.tau_g[q]);
@@ -695,22 +871,23 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         if (MODE == 1) { if (u == 0 && tv == t0) dbg_row = p.dbg + (int(lane) * 4 + lane_grp) * TC_BN + half * TC_HALF_COLS; }
         float* pre_out = nullptr;
         if (MODE == 2) { if (active) pre_out = p.pre_max + size_t(q) * p.pre_pitch + (tv * TC_SPLIT + half); }
-        epi_tile<METRIC, MODE>(t_lane + uint32_t(acc * TC_BN), any_active ? ncols : 0, nrm, col0, tau, buf, wn,
-                               &tmem_empty[acc], lane, dbg_row, pre_out);
+        epi_tile<METRIC, MODE, PAIR>(t_lane + uint32_t(acc * TC_BN), any_active ? ncols : 0, nrm, col0, tau, buf, wn,
+                                     &tmem_empty[acc], tmem_empty_leader + uint32_t(acc) * 8u, &norm_empty[acc], lane, dbg_row, pre_out);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         if (MODE != 2) epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
       }
 
       // end of unit: the finish kernel reads the buffer in place
-      if (MODE != 2) p.wcnt[size_t(u) * TC_SLOTS + slot] = active ? int(wn) : 0;
+      if (MODE != 2) p.wcnt[size_t(cu) * TC_SLOTS + slot] = active ? int(wn) : 0;
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair's MMAs / barrier signals may still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -912,7 +1089,7 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         float* pre_out = nullptr;
         if (MODE == 2) { if (active) pre_out = p.pre_max + size_t(q) * p.pre_pitch + tv; }
         epi_tile<METRIC, MODE>(t_lane + uint32_t(acc * 2 * RQ_BN), any_active ? ncols : 0,
-                               norm_smem + acc * RQ_BN, col0, tau, buf, wn, &tmem_empty[acc * 2 + qt_l], lane, nullptr, pre_out);
+                               norm_smem + acc * RQ_BN, col0, tau, buf, wn, &tmem_empty[acc * 2 + qt_l], 0u, nullptr, lane, nullptr, pre_out);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         if (MODE != 2) epi_tighten(p, active, q, buf, wn, wn_trig, tau, lane);
       }
@@ -934,7 +1111,8 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int n_rows_p, int dim, int pitch, float* __restrict__ Qp,
                                 uint32_t* __restrict__ tau_g, int* __restrict__ flags,
                                 __nv_bfloat16* __restrict__ Qb, int pitch_b,
-                                const uint32_t* __restrict__ tau_fixed, int keep_tau, int aug_col) {
+                                const uint32_t* __restrict__ tau_fixed, int keep_tau, int aug_col, int* __restrict__ n_flagged) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_flagged = 0;
   // Rows are written in TILE order: row qt*128 + j holds query qt*128 + (j % 32) * 4 + j / 32 (zeros past the last
   // query), so that consecutive queries land in different TMEM lane groups.
   // n_rows_p: rows of the padded query matrices (whole tile pairs)
@@ -973,6 +1151,7 @@ struct FinishParams {
   const uint32_t* tau_g; const uint2* wbuf; const int* wcnt; int qt_major; int rq; int n_qp;
   int* flags; int certify; float max_norm; double c_err; double c_add;
   int64_t* out_rows; float* out_dist;
+  int* n_flagged;   // counts the queries this launch flags (read back by the host together with the results)
 };
 
 // One CTA per query. The query's candidates live in 2 * n_slices buffers (one per unit-half).
@@ -1221,6 +1400,7 @@ knn_tc_finish_kernel(FinishParams p) {
       flag = ok ? 0 : (n_cand < p.k ? 2 : 1);   // 2: fewer than k candidates at all (no k-th distance to refine from)
     }
     p.flags[q] = flag;
+    if (flag) atomicAdd(p.n_flagged, 1);
   }
 }
 
@@ -1413,12 +1593,20 @@ inline bool tc_init(TcState* st, int sm_count, std::string* err) {
     return false;
   }
   st->encode = fn;
-  cudaError_t a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_tc_filter_kernel<2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  tc_knobs_from_env(&st->knobs);
+  cudaError_t a = cudaSuccess;
+  auto attr = [&](auto kernel, uint32_t bytes) {
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  };
+  attr(knn_tc_filter_kernel<0, 0, 0, 0>, TC_SMEM_BYTES); attr(knn_tc_filter_kernel<1, 0, 0, 0>, TC_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<2, 0, 0, 0>, TC_SMEM_BYTES); attr(knn_tc_filter_kernel<0, 1, 0, 0>, TC_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<1, 1, 0, 0>, TC_SMEM_BYTES); attr(knn_tc_filter_kernel<2, 1, 0, 0>, TC_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<0, 1, 2, 0>, TC_SMEM_BYTES); attr(knn_tc_filter_kernel<1, 1, 2, 0>, TC_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<2, 1, 2, 0>, TC_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<0, 1, 0, 1>, TC2_SMEM_BYTES); attr(knn_tc_filter_kernel<1, 1, 0, 1>, TC2_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<2, 1, 0, 1>, TC2_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<0, 1, 2, 1>, TC2_SMEM_BYTES); attr(knn_tc_filter_kernel<1, 1, 2, 1>, TC2_SMEM_BYTES);
+  attr(knn_tc_filter_kernel<2, 1, 2, 1>, TC2_SMEM_BYTES);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
   if (a == cudaSuccess) a = cudaFuncSetAttribute(knn_rq_filter_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_MAX);
@@ -1475,6 +1663,8 @@ struct TcPlan {
   int n_vtiles, tile_stride;
   int qt_major;
   int rq;        // 1: resident-query kernel (units = query pairs x slices of 128-row tiles, one list per unit and query)
+  int pair;      // 1: CTA-pair streaming kernel (units = query pairs x slices; candidate lists per CTA as in the one-CTA kernel)
+  int n_qt_lists;// query tiles the candidate-list layout is indexed with (2 n_qp for the pair kernel, else n_qt)
   int n_qp;      // query pairs
   int kp_list;   // candidates each (query, list) keeps at a selection (<= kp)
   size_t off_qp, off_qb, off_tau, off_flags, off_wcnt, off_wbuf, off_pre, total;
@@ -1488,7 +1678,8 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.kp = s.tau_fixed ? 1024 : tc_kp(s.k, s.certify, s.kind);   // refinement reranks every survivor (up to 1024)
   const bool pre = s.sample_stride > 1;                          // threshold prepass over a strided sample
   if (pre) pl.kp = 32;   // unused by the prepass kernels (no candidate lists); keeps the slice heuristics below sane
-  if (!s.tau_fixed && s.certify && !pre) { if (const char* e = std::getenv("FENIX_TC_KP")) { int f = std::atoi(e); if (f >= s.k && f <= 512) pl.kp = (f + 31) & ~31; } }
+  const TcKnobs& kn = st->knobs;
+  if (!s.tau_fixed && s.certify && !pre && kn.kp >= s.k && kn.kp <= 512) pl.kp = (kn.kp + 31) & ~31;
   pl.cap = tc_cap(pl.kp);
   // MMA instructions per tile: 32 B of K each (8 fp32 / 16 bf16 elements); only columns that hold data
   pl.aug_line0 = 0; pl.aug_col = 0;
@@ -1505,23 +1696,26 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     pl.aug_line0 = pl.n_tiles * g.n_kb_data * TC_BN;
     pl.aug_col = g.aug_col;
   }
-  if (std::getenv("FENIX_TC_FULLK")) pl.nk_last = TC_BK / TC_UMMA_K;   // tuning knob: multiply the zero padding too
+  if (kn.fullk) pl.nk_last = TC_BK / TC_UMMA_K;   // tuning knob: multiply the zero padding too
   // narrow rows and at least two query tiles: the resident-query kernel (operand traffic, not the tensor pipe, binds
   // the streaming kernel there); its tiles are 128 corpus rows, its units pair two query tiles
-  pl.rq = (s.kind == 1 && pl.n_kblocks <= RQ_MAX_KB && pl.n_qt >= 2 && s.epi != 1 && s.dbg == nullptr &&
-           !std::getenv("FENIX_TC_NO_RQ")) ? 1 : 0;
+  pl.rq = (s.kind == 1 && pl.n_kblocks <= RQ_MAX_KB && pl.n_qt >= 2 && s.epi != 1 && s.dbg == nullptr && !kn.no_rq) ? 1 : 0;
   pl.n_qp = (pl.n_qt + 1) / 2;
+  // wider rows and at least two query tiles: CTA pairs (cta_group::2) over the bf16 shadow - each SM stages half of
+  // every corpus block, two thirds of the one-CTA kernel's L2 -> SM operand traffic at the same tensor work
+  pl.pair = (!pl.rq && s.kind == 1 && pl.n_qt >= 2 && s.dbg == nullptr && kn.pair != 0) ? 1 : 0;
+  pl.n_qt_lists = pl.pair ? 2 * pl.n_qp : pl.n_qt;
   const int n_tiles_full = pl.rq ? int((s.n_rows + RQ_BN - 1) / RQ_BN) : pl.n_tiles;   // tiles in the kernel's own unit
   pl.tile_stride = pre ? s.sample_stride : 1;
   const int n_tiles_u = (n_tiles_full + pl.tile_stride - 1) / pl.tile_stride;          // tiles the units iterate over
   pl.n_vtiles = n_tiles_u;
-  const int n_qu = pl.rq ? pl.n_qp : pl.n_qt;                                       // query blocks per slice
+  const int n_qu = (pl.rq || pl.pair) ? pl.n_qp : pl.n_qt;                          // query blocks per slice
   // Slices: units = n_qt * n_slices (query-tile major, so all slices of a query tile run at the same time and
   // share thresholds) are dealt round-robin to min(units, #SM) persistent CTAs.
   // Maximise SM utilisation units / (G * ceil(units / G)); few slices are preferred (longer units give
   // tighter thresholds and fewer candidate lists), and every unit should span enough tiles for its
   // threshold to become selective.
-  const int sms = st->sm_count;
+  const int sms = pl.pair ? st->sm_count / 2 : st->sm_count;   // persistent workers: CTAs, or CTA pairs
   const int min_tiles = pre ? 4 : std::max(4, (8 * pl.kp + TC_BN - 1) / TC_BN) * (pl.rq ? 2 : 1);
   const int s_cap = std::max(1, (TC_MAX_WAVES * sms) / n_qu);
   const int s_max = std::max(1, std::min(n_tiles_u / min_tiles, s_cap));
@@ -1535,19 +1729,19 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     double eff = double(units) / double(sms * ((units + g - 1) / g));
     if (eff > best + 0.02) { best = eff; best_s = sl; }
   }
-  if (const char* e = std::getenv("FENIX_TC_SLICES")) {   // tuning knob: force the slice count
-    int forced = std::atoi(e);
+  if (kn.slices > 0) {   // tuning knob: force the slice count
+    int forced = kn.slices;
     if (forced >= 1 && forced <= s_max) {
       int tps = (n_tiles_u + forced - 1) / forced;
       best_s = (n_tiles_u + tps - 1) / tps;
     }
   }
   pl.qt_major = 0;   // measured on C3: slice-major 94 ms vs query-tile-major 112 ms (profiles/r01_c3_sweep.txt)
-  if (const char* e = std::getenv("FENIX_TC_ORDER")) pl.qt_major = std::atoi(e) != 0;
+  if (kn.order >= 0) pl.qt_major = kn.order != 0;
   pl.n_slices = best_s;
   pl.tiles_per_slice = (n_tiles_u + best_s - 1) / best_s;
   pl.units = pl.n_slices * n_qu;
-  if (pl.rq) pl.qt_major = 0;
+  if (pl.rq || pl.pair) pl.qt_major = 0;
   // Each query's candidates are spread over L = TC_SPLIT * n_slices lists. A list does not need to keep K'
   // entries: the global top-k lands ~k/L per list, so keeping 2k/L + 16 (>= 32) per list gives much tighter
   // local thresholds (fewer appends and selections). If a query's neighbours are concentrated in few lists
@@ -1557,12 +1751,14 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     int m = std::max(32, (2 * s.k + lists - 1) / lists + 16);
     m = (m + 31) & ~31;
     pl.kp_list = (s.tau_fixed || pre) ? pl.kp : std::min(pl.kp, m);   // prepass: every list keeps the m best it sees
-    if (!pre) if (const char* e = std::getenv("FENIX_TC_KP_LIST")) { int f = std::atoi(e); if (f >= 32) pl.kp_list = std::min(pl.kp, (f + 31) & ~31); }
+    if (!pre && kn.kp_list >= 32) pl.kp_list = std::min(pl.kp, (kn.kp_list + 31) & ~31);
     pl.cap = (s.tau_fixed || pre) ? pl.cap : tc_cap(pl.kp_list);
   }
-  pl.grid = int(std::min<long>(pl.units, sms));
+  pl.grid = int(std::min<long>(pl.units, sms)) * (pl.pair ? 2 : 1);
+  const size_t list_units = size_t(pl.n_slices) * size_t(pl.pair ? 2 * pl.n_qp : n_qu);   // blocks of TC_SLOTS candidate lists
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  take(TC_HDR_BYTES);   // header: word 0 counts the queries the finish kernel flagged (read back with the results)
   const size_t q_rows_p = size_t(pl.n_qp) * 2 * TC_BM;   // queries are stored in whole tile pairs
   pl.off_qp = take(q_rows_p * s.pitch * 4);
   pl.off_qb = take(s.kind == 1 ? q_rows_p * s.pitch_b * 2 : 0);
@@ -1574,8 +1770,8 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     pl.off_wcnt = pl.off_wbuf = off;
     pl.off_pre = take(size_t(s.n_q) * pl.pre_pitch * 4);
   } else {
-    pl.off_wcnt = take(size_t(pl.units) * TC_SLOTS * 4);
-    pl.off_wbuf = take(size_t(pl.units) * TC_SLOTS * pl.cap * 8);
+    pl.off_wcnt = take(list_units * TC_SLOTS * 4);
+    pl.off_wbuf = take(list_units * TC_SLOTS * pl.cap * 8);
     pl.off_pre = off;
   }
   pl.total = off;
@@ -1583,20 +1779,30 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
 }
 
 inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan& main_pl, TcSearch* pre);
-inline bool tc_uses_prepass(const TcState* st, const TcSearch& s) {
+// Everything one search needs to know before it launches, computed ONCE per search: the plan of the main pass, whether
+// a sample prepass runs first (and its plan), and the scratch both need.
+struct TcLaunch {
+  TcPlan pl;
+  bool with_pre = false;
   TcSearch pre;
-  return tc_prepass_config(st, s, tc_plan(st, s), &pre);
+  TcPlan ppl;
+  size_t scratch_bytes = 0;
+};
+inline TcLaunch tc_prepare(const TcState* st, const TcSearch& s) {
+  TcLaunch L;
+  L.pl = tc_plan(st, s);
+  L.scratch_bytes = L.pl.total;
+  L.with_pre = tc_prepass_config(st, s, L.pl, &L.pre);
+  if (L.with_pre) {
+    L.ppl = tc_plan(st, L.pre);
+    L.scratch_bytes = std::max(L.scratch_bytes, L.ppl.total);
+  }
+  return L;
 }
-inline size_t tc_scratch_bytes(const TcState* st, const TcSearch& s) {
-  const TcPlan pl = tc_plan(st, s);
-  TcSearch pre;
-  size_t total = pl.total;
-  if (tc_prepass_config(st, s, pl, &pre)) total = std::max(total, tc_plan(st, pre).total);
-  return total;
+inline const int* tc_flags(const TcLaunch& L, void* scratch) {
+  return reinterpret_cast<const int*>(static_cast<char*>(scratch) + L.pl.off_flags);
 }
-inline const int* tc_flags(const TcState* st, const TcSearch& s, void* scratch) {
-  return reinterpret_cast<const int*>(static_cast<char*>(scratch) + tc_plan(st, s).off_flags);
-}
+inline const int* tc_flag_count(void* scratch) { return static_cast<const int*>(scratch); }   // header word 0
 // rigorous bound constant of the TF32 dot product: |acc - <q,x>| <= c * |q| * |x|
 // (operands truncated to 10 mantissa bits: 2^-10 each -> 2^-9 on the product, 25% margin;
 //  fp32 accumulation of D terms: D * 2^-21)
@@ -1615,23 +1821,23 @@ inline double tc_c_err(int dim, int kind = 0) {
 // `safety` x K' with m ~ 10 (relative spread ~ 1/sqrt(m); a threshold that turns out too tight only costs the query
 // a refinement pass, one that is too loose more appends - exactness never depends on the sample).
 inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan& main_pl, TcSearch* pre) {
-  (void)st;
+  const TcKnobs& kn = st->knobs;
   if (s.tau_fixed || s.no_prepass || s.sample_stride > 1 || s.kind != 1 || s.dbg != nullptr) return false;
   // Wide rows: with a large batch the tensor pipe binds and the sample's cost (1/stride of the scan) eats what the
   // tighter thresholds save (C3: neutral). Small batches are HBM-bound with a lightly loaded tensor pipe, and there
   // the epilogue's hit path and the finish kernel's candidate volume show: C5 batch 64 +18 %, batch 8 +6 %.
   const bool wide = main_pl.n_kblocks > 4;
-  if (wide && main_pl.n_qt > 3 && !std::getenv("FENIX_TC_PRE_WIDE")) return false;
+  if (wide && main_pl.n_qt > 3 && !kn.pre_wide) return false;
   if (s.epi != 2) return false;                            // a row mask (predicate / IVF cells) of unknown selectivity: the
                                                            // sample says nothing about how many LIVE rows pass a threshold
-  if (const char* e = std::getenv("FENIX_TC_PRE")) { if (std::atoi(e) == 0) return false; }
+  if (kn.pre == 0) return false;
   double safety = 3.0;
-  if (const char* e = std::getenv("FENIX_TC_PRE_SAFETY")) { double f = std::atof(e); if (f >= 1.0 && f <= 64.0) safety = f; }
+  if (kn.pre_safety >= 1.0 && kn.pre_safety <= 64.0) safety = kn.pre_safety;
   const int tile_rows = main_pl.rq ? RQ_BN : TC_BN;
   // rank m of the sample statistic: P(threshold too tight for k rows) = P(Gamma(m) < m k / (safety K')). Wide rows pay
   // for every sampled tile, so they take the thinner sample when k is small against K' (k = 10: m = 6, P ~ 1e-6)
   double target_m = (wide && double(s.k) <= 0.06 * safety * double(main_pl.kp)) ? 6.0 : 16.0;
-  if (const char* e = std::getenv("FENIX_TC_PRE_M")) { double f = std::atof(e); if (f >= 2.0 && f <= 256.0) target_m = f; }
+  if (kn.pre_m >= 2.0 && kn.pre_m <= 256.0) target_m = kn.pre_m;
   int stride = int(double(main_pl.kp) * safety / target_m);         // S = N / stride, m = safety K' S / N
   const int64_t n_tiles_full = (s.n_rows + tile_rows - 1) / tile_rows;
   if (stride < 4 || n_tiles_full / stride < 32) return false;       // shard too small for a sample to pay off
@@ -1669,41 +1875,57 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   p.aug_line0 = pl.aug_line0;
   p.xb = s.kind == 1 ? static_cast<const unsigned char*>(s.shadow == 1 ? s.Xn : s.Xb) : nullptr;
   p.pf_tiles = 0;   // off: measured neutral where operands come from L2 (C2, C4) and 1.9x slower where HBM binds (C5)
-  if (const char* e = std::getenv("FENIX_TC_PF")) p.pf_tiles = p.xb ? std::max(0, std::atoi(e)) : 0;
+  if (st->knobs.pf > 0 && p.xb) p.pf_tiles = st->knobs.pf;
   p.kp = pl.kp_list; p.cap = pl.cap;
   p.sleep_ns = pl.n_kblocks >= 6 ? 0u : 64u;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
   p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
   if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);
   const int epi = s.epi;   // epilogue form: 0 add, 1 multiply, 2 none
-  // dispatch on (epilogue form, operand kind, diagnostics dump)
-  auto launch = [&](auto kernel, const CUtensorMap& map_b) {
-    kernel<<<pl.grid, TC_THREADS, TC_SMEM_BYTES, s.stream>>>(map_q, map_b, p);
+  // dispatch on (epilogue form, operand kind, mode: filter / diagnostics dump / prepass, CTA pairs)
+  cudaError_t le = cudaSuccess;
+  auto launch = [&](auto kernel, const CUtensorMap& map_b, uint32_t smem, int cluster) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(pl.grid)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = unsigned(cluster); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = cluster > 1 ? 1 : 0;
+    le = cudaLaunchKernelEx(&cfg, kernel, map_q, map_b, p);
   };
   const bool dbg = s.dbg != nullptr;
   if (pl.rq) {
     const CUtensorMap& map_h = s.shadow == 1 ? tc->map_xn_h : tc->map_xb_h;
     p.rq_stages = rq_stages(pl.n_kblocks);
-    if (const char* e = std::getenv("FENIX_RQ_STAGES")) { int f = std::atoi(e); if (f >= 2 && f <= p.rq_stages) p.rq_stages = f; }
+    if (st->knobs.rq_stages >= 2 && st->knobs.rq_stages <= p.rq_stages) p.rq_stages = st->knobs.rq_stages;
     const uint32_t rq_smem = rq_smem_bytes(pl.n_kblocks);
     if (pre) {
-      if (epi == 0) knn_rq_filter_kernel<0, 2><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
-      else knn_rq_filter_kernel<2, 2><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+      if (epi == 0) launch(knn_rq_filter_kernel<0, 2>, map_h, rq_smem, 1);
+      else launch(knn_rq_filter_kernel<2, 2>, map_h, rq_smem, 1);
     } else {
-      if (epi == 0) knn_rq_filter_kernel<0, 0><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
-      else knn_rq_filter_kernel<2, 0><<<pl.grid, TC_THREADS, rq_smem, s.stream>>>(map_q, map_h, p);
+      if (epi == 0) launch(knn_rq_filter_kernel<0, 0>, map_h, rq_smem, 1);
+      else launch(knn_rq_filter_kernel<2, 0>, map_h, rq_smem, 1);
     }
+  } else if (pl.pair) {
+    // CTA pairs: each CTA loads 128-row half blocks of the tiled shadow
+    const CUtensorMap& map_h = s.shadow == 1 ? tc->map_xn_h : tc->map_xb_h;
+#define FX_TC2_CASE(E)                                                              \
+  if (epi == E) {                                                                   \
+    if (pre) launch(knn_tc_filter_kernel<E, 1, 2, 1>, map_h, TC2_SMEM_BYTES, 2);    \
+    else launch(knn_tc_filter_kernel<E, 1, 0, 1>, map_h, TC2_SMEM_BYTES, 2);        \
+  }
+    FX_TC2_CASE(0) FX_TC2_CASE(1) FX_TC2_CASE(2)
+#undef FX_TC2_CASE
   } else {
 #define FX_TC_CASE(E, K, MAP)                                                       \
   if (epi == E && s.kind == K) {                                                    \
     if (dbg) {                                                                      \
-      cudaFuncSetAttribute(knn_tc_filter_kernel<E, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
-      launch(knn_tc_filter_kernel<E, K, 1>, MAP);                                   \
+      cudaFuncSetAttribute(knn_tc_filter_kernel<E, K, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
+      launch(knn_tc_filter_kernel<E, K, 1, 0>, MAP, TC_SMEM_BYTES, 1);              \
     } else if (pre && K == 1) {                                                     \
-      cudaFuncSetAttribute(knn_tc_filter_kernel<E, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
-      launch(knn_tc_filter_kernel<E, 1, 2>, MAP);                                   \
+      launch(knn_tc_filter_kernel<E, 1, 2, 0>, MAP, TC_SMEM_BYTES, 1);              \
     } else {                                                                        \
-      launch(knn_tc_filter_kernel<E, K, 0>, MAP);                                   \
+      launch(knn_tc_filter_kernel<E, K, 0, 0>, MAP, TC_SMEM_BYTES, 1);              \
     }                                                                               \
   }
   FX_TC_CASE(0, 0, tc->map_x) FX_TC_CASE(1, 0, tc->map_x) FX_TC_CASE(2, 0, tc->map_x)
@@ -1711,6 +1933,7 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   FX_TC_CASE(0, 1, map_s) FX_TC_CASE(1, 1, map_s) FX_TC_CASE(2, 1, map_s)
 #undef FX_TC_CASE
   }
+  if (le != cudaSuccess) { *err = std::string("filter kernel launch failed: ") + cudaGetErrorString(le); return false; }
   if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
   if (pre) {
     if (pl.n_rec <= 32 * TAU0_PER) knn_tc_tau0_kernel<32><<<(s.n_q + 7) / 8, 256, 0, s.stream>>>(p.pre_max, s.n_q, pl.n_rec, s.pre_m, tau_g);
@@ -1723,7 +1946,8 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   }
 
   FinishParams f{};
-  f.X = s.X; f.pitch = s.pitch; f.dim = s.dim; f.row_base = s.row_base; f.Qp = qp; f.n_q = s.n_q; f.n_qt = pl.n_qt;
+  f.X = s.X; f.pitch = s.pitch; f.dim = s.dim; f.row_base = s.row_base; f.Qp = qp; f.n_q = s.n_q; f.n_qt = pl.n_qt_lists;
+  f.n_flagged = reinterpret_cast<int*>(base);
   f.n_slices = pl.n_slices; f.cap = pl.cap; f.metric = s.metric; f.k = s.k; f.kp = pl.kp;
   int sort2 = 2; while (sort2 < pl.kp) sort2 <<= 1;
   f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.qt_major = pl.qt_major; f.rq = pl.rq; f.n_qp = pl.n_qp; f.flags = flags; f.certify = s.certify ? 1 : 0;
@@ -1731,16 +1955,16 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + size_t(FIN_POOL) * 8 + 16;
   // many short lists per query (small batches split over all SMs): more warps sweep them in parallel
   int fin_threads = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices > 32 ? 1024 : 256;
-  if (const char* e = std::getenv("FENIX_FIN_THREADS")) { int f = std::atoi(e); if (f == 128 || f == 256 || f == 512 || f == 1024) fin_threads = f; }
+  { const int ft = st->knobs.fin_threads; if (ft == 128 || ft == 256 || ft == 512 || ft == 1024) fin_threads = ft; }
   knn_tc_finish_kernel<<<s.n_q, fin_threads, fin_smem, s.stream>>>(f);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("tensor-core path launch failed: ") + cudaGetErrorString(e); return false; }
   return true;
 }
 
-inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratch, int* launched, std::string* err,
-                      int* variant = nullptr) {
-  const TcPlan pl = tc_plan(st, s);
+inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, const TcLaunch& L, void* scratch, int* launched,
+                      std::string* err, int* variant = nullptr) {
+  const TcPlan& pl = L.pl;
   char* base = static_cast<char*>(scratch);
   float* qp = reinterpret_cast<float*>(base + pl.off_qp);
   uint32_t* tau_g = reinterpret_cast<uint32_t*>(base + pl.off_tau);
@@ -1758,16 +1982,13 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, void* scratc
   const int n_rows_p = pl.n_qp * 2 * TC_BM;
   const int prep_blocks = int(std::min<int64_t>((int64_t(n_rows_p) * s.pitch + 255) / 256, 4 * 148));
   knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, n_rows_p, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed,
-                                                                  (!s.tau_fixed && std::getenv("FENIX_TC_WARM")) ? 1 : 0,
-                                                                  (s.kind == 1 && s.aug) ? pl.aug_col : 0);
+                                                                  (!s.tau_fixed && st->knobs.warm) ? 1 : 0,
+                                                                  (s.kind == 1 && s.aug) ? pl.aug_col : 0, reinterpret_cast<int*>(base));
   *launched = 3;
   // threshold prepass over a strided sample (the padded queries and tau_g sit at the same scratch offsets in both plans)
-  TcSearch pre;
-  const bool with_pre = tc_prepass_config(st, s, pl, &pre);
-  if (variant) *variant = (pl.rq ? 1 : 0) | (with_pre ? 2 : 0);
-  if (with_pre) {
-    const TcPlan ppl = tc_plan(st, pre);
-    if (!tc_run_pass(st, tc, pre, ppl, scratch, map_q, err)) return false;
+  if (variant) *variant = (pl.rq ? 1 : 0) | (L.with_pre ? 2 : 0) | (pl.pair ? 4 : 0);
+  if (L.with_pre) {
+    if (!tc_run_pass(st, tc, L.pre, L.ppl, scratch, map_q, err)) return false;
     *launched += 2;
   }
   return tc_run_pass(st, tc, s, pl, scratch, map_q, err);

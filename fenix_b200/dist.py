@@ -11,7 +11,9 @@ New relative to the reference (it has no parallelism): rank r o
 contiguous rows [r*ceil(N/W), min(N,(r+1)*ceil(N/W))) so that global row = base + local row and
 "lowest row wins" tie-breaking survives sharding. Every rank answers all Q queries against its
 shard (shard-local top-k ordered by (distance, row)), the k*W candidates per query are
-all-gathered (NCCL over NVLink on GPUs, gloo on CPU for tests) and merged by fx_merge_topk.
+all-gathered over NVLink and merged - inside the C library (fx_search_sharded, its own NCCL communicator; see
+include/fenix_knn.h). The torch.distributed helpers below (candidate packing, gathers) serve the replicated-corpus
+mode and the CPU (gloo) tests of the host logic.
 """
 from __future__ import annotations
 
@@ -54,46 +56,80 @@ def gather_candidates(rows: torch.Tensor, dist: torch.Tensor, group=None) -> tup
     return unpack_candidates(out.view(world, *packed.shape))
 
 
+def broadcast_comm_id(make_id, group=None, device: Optional[torch.device] = None) -> bytes:
+    """Rank 0 draws the communicator id (`make_id()` -> 128 bytes, knn.Comm.unique_id), every rank receives it over
+    the process group that is already up (NCCL on GPUs, gloo in the CPU tests)."""
+    rank = td.get_rank(group)
+    buf = torch.zeros(knn.COMM_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        raw = make_id()
+        if len(raw) != knn.COMM_ID_BYTES:
+            raise ValueError(f"communicator id must be {knn.COMM_ID_BYTES} bytes")
+        buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    if device is not None:
+        buf = buf.to(device)
+    td.broadcast(buf, src=0, group=group)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
 class ShardedSearcher:
-    """This rank's shard + the collective merge. All ranks must call `search` together."""
+    """This rank's shard + the exchange. All ranks must call `search_*` together.
+
+    The whole step lives in the C library (fx_search_sharded*): query-slice upload + all-gather, shard search,
+    all-gather of the k*W candidates on the library's own NCCL communicator, merge, result copy - one stream, one host
+    synchronisation, no Python between the kernels. torch.distributed only carries the communicator id at start-up."""
 
     def __init__(self, corpus: knn.Corpus, group=None) -> None:
         self.corpus = corpus
         self.group = group
         self.world = td.get_world_size(group) if td.is_initialized() else 1
+        self.rank = td.get_rank(group) if td.is_initialized() else 0
         self.device = torch.device("cuda", corpus.ctx.device)
         self.merge_launches = 0
+        self.comm = None
+        if self.world > 1:
+            uid = broadcast_comm_id(knn.Comm.unique_id, group, self.device if td.get_backend(group) == "nccl" else None)
+            self.comm = knn.Comm(corpus.ctx, uid, self.world, self.rank)
 
     def search_device(self, d_queries: torch.Tensor, metric: int, k: int,
                       precision: int = knn.PREC_FP32) -> tuple[torch.Tensor, torch.Tensor]:
-        """d_queries: float32 [Q, D] on this rank's GPU. Returns the global (rows, dist) [Q, k]."""
+        """d_queries: float32 [Q, D], the whole batch, resident on this rank's GPU. Returns the global (rows, dist) [Q, k]
+        on the device."""
         n_q = d_queries.shape[0]
         rows = torch.empty((n_q, k), dtype=torch.int64, device=self.device)
         dist = torch.empty((n_q, k), dtype=torch.float32, device=self.device)
-        torch.cuda.current_stream(self.device).synchronize()
-        self.corpus.search_device(d_queries.data_ptr(), n_q, metric, k, precision, rows.data_ptr(), dist.data_ptr())
+        torch.cuda.current_stream(self.device).synchronize()   # the tensors above exist before the library's stream uses them
         if self.world == 1:
+            self.corpus.search_device(d_queries.data_ptr(), n_q, metric, k, precision, rows.data_ptr(), dist.data_ptr())
             return rows, dist
-        all_rows, all_dist = gather_candidates(rows, dist, self.group)
-        out_rows = torch.empty_like(rows)
-        out_dist = torch.empty_like(dist)
-        torch.cuda.current_stream(self.device).synchronize()
-        self.corpus.ctx.merge_topk_device(all_rows.data_ptr(), all_dist.data_ptr(), self.world, n_q, k,
-                                          out_rows.data_ptr(), out_dist.data_ptr())
+        self.corpus.search_sharded_raw(self.comm, d_queries.data_ptr(), n_q, metric, k, precision, rows.data_ptr(),
+                                       dist.data_ptr(), on_device=True)
         self.merge_launches += 1
-        return out_rows, out_dist
+        return rows, dist
 
     def search_host(self, h_queries: torch.Tensor, metric: int, k: int, precision: int = knn.PREC_FP32,
-                    h_rows: Optional[torch.Tensor] = None, h_dist: Optional[torch.Tensor] = None):
-        """End-to-end form: pinned host queries in, pinned host results out (H2D/D2H included)."""
-        d_q = h_queries.to(self.device, non_blocking=True)
-        rows, dist = self.search_device(d_q, metric, k, precision)
-        if h_rows is None:
-            return rows.cpu(), dist.cpu()
-        h_rows.copy_(rows, non_blocking=True)
-        h_dist.copy_(dist, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return h_rows, h_dist
+                    h_rows: Optional[torch.Tensor] = None, h_dist: Optional[torch.Tensor] = None,
+                    result_rank: Optional[int] = None):
+        """End-to-end form: (pinned) host queries in - every rank uploads 1/W of the batch, the slices are all-gathered
+        over NVLink - and (pinned) host results out, on every rank or on `result_rank` alone."""
+        n_q = h_queries.shape[0]
+        want = result_rank is None or result_rank == self.rank
+        if want and h_rows is None:
+            h_rows = torch.empty((n_q, k), dtype=torch.int64)
+            h_dist = torch.empty((n_q, k), dtype=torch.float32)
+        if self.world == 1:
+            self.corpus.search_raw(h_queries.data_ptr(), n_q, metric, k, precision, h_rows.data_ptr(), h_dist.data_ptr())
+            return h_rows, h_dist
+        self.corpus.search_sharded_raw(self.comm, h_queries.data_ptr(), n_q, metric, k, precision,
+                                       h_rows.data_ptr() if want else None, h_dist.data_ptr() if want else None)
+        if want:
+            self.merge_launches += 1
+        return (h_rows, h_dist) if want else (None, None)
+
+    def close(self) -> None:
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
 
 
 def gather_slices(rows: torch.Tensor, dist: torch.Tensor, n_q: int, group=None) -> tuple[torch.Tensor, torch.Tensor]:

@@ -18,13 +18,14 @@ from typing import Optional
 import numpy as np
 
 __all__ = [
-    "FenixKnnError", "Context", "Corpus", "Stats", "METRICS", "metric_code",
-    "PREC_FP32", "PREC_TF32", "PREC_BF16", "PREC_EXACT_SCAN", "load_library", "library_path", "K_MAX",
+    "FenixKnnError", "Context", "Corpus", "Comm", "Group", "Stats", "METRICS", "metric_code",
+    "PREC_FP32", "PREC_TF32", "PREC_BF16", "PREC_EXACT_SCAN", "load_library", "library_path", "COMM_ID_BYTES",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libfenix_knn.so"
-K_MAX = 2048
+COMM_ID_BYTES = 128
+ABI_VERSION = 2
 
 FX_OK = 0
 FX_EINVAL, FX_ECUDA, FX_ENOMEM, FX_ESTATE, FX_EUNSUP = -1, -2, -3, -4, -5
@@ -37,7 +38,9 @@ METRICS = {"l2": 0, "euclidean": 0, "cosine": 1, "dot": 2, "inner_product": 2}
 ABI_SYMBOLS = (
     "fx_init", "fx_shutdown", "fx_corpus_create", "fx_corpus_append", "fx_corpus_append_device",
     "fx_corpus_finalize", "fx_corpus_destroy", "fx_search", "fx_search_device", "fx_distances",
-    "fx_merge_topk", "fx_get_stats", "fx_debug_scores", "fx_last_error", "fx_abi_version",
+    "fx_merge_topk", "fx_get_stats", "fx_debug_scores", "fx_last_error", "fx_abi_version", "fx_set_option",
+    "fx_comm_unique_id", "fx_comm_init_rank", "fx_comm_destroy", "fx_search_sharded", "fx_search_sharded_device",
+    "fx_group_create", "fx_group_size", "fx_group_ctx", "fx_group_search", "fx_group_destroy",
 )
 
 
@@ -63,7 +66,7 @@ class _FxStats(ctypes.Structure):
         ("device_bytes", ctypes.c_int64), ("searches", ctypes.c_int64), ("queries", ctypes.c_int64),
         ("fallback_queries", ctypes.c_int64), ("refined_queries", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
         ("last_search_ms", ctypes.c_double), ("last_main_kernel_ms", ctypes.c_double),
-        ("last_path", ctypes.c_int32), ("last_variant", ctypes.c_int32),
+        ("last_path", ctypes.c_int32), ("last_variant", ctypes.c_int32), ("last_exchange_ms", ctypes.c_double),
     ]
 
 
@@ -82,6 +85,7 @@ class Stats:
     last_main_kernel_ms: float
     last_path: int
     last_variant: int = 0
+    last_exchange_ms: float = 0.0
 
 
 _lib_lock = threading.Lock()
@@ -122,11 +126,23 @@ def load_library() -> ctypes.CDLL:
         lib.fx_merge_topk.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp]
         lib.fx_get_stats.argtypes = [vp, ctypes.POINTER(_FxStats)]
         lib.fx_debug_scores.argtypes = [vp, vp, i64, i32, vp]
+        lib.fx_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
+        lib.fx_comm_unique_id.argtypes = [vp]
+        lib.fx_comm_init_rank.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp)]
+        lib.fx_comm_destroy.argtypes = [vp]
+        lib.fx_search_sharded.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]
+        lib.fx_search_sharded_device.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]
+        lib.fx_group_create.argtypes = [ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+        lib.fx_group_size.argtypes = [vp]
+        lib.fx_group_ctx.argtypes = [vp, i32]
+        lib.fx_group_search.argtypes = [vp, ctypes.POINTER(vp), vp, i64, i32, i32, i32, vp, vp, vp]
+        lib.fx_group_destroy.argtypes = [vp]
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
-            if name not in ("fx_last_error",):
+            if name not in ("fx_last_error", "fx_group_ctx"):
                 fn.restype = ctypes.c_int
         lib.fx_last_error.restype = ctypes.c_char_p
+        lib.fx_group_ctx.restype = vp
         _lib = lib
         return lib
 
@@ -144,15 +160,46 @@ def _check(lib: ctypes.CDLL, code: int) -> None:
     raise FenixKnnError(code, msg)
 
 
+_nccl_preloaded = False
+
+
+def preload_nccl() -> None:
+    """Make libnccl.so.2 resolvable for the library's dlopen: a process that imported torch has it already; a bare
+    server loads the copy bundled with the nvidia-nccl wheel (FENIX_NCCL_LIB overrides, see fenix_knn.h)."""
+    global _nccl_preloaded
+    if _nccl_preloaded or os.environ.get("FENIX_NCCL_LIB"):
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec is not None else ()):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass  # the library's own dlopen reports what is missing
+
+
 class Context:
     """One CUDA device (streams + scratch). Thread-safe: searches on one context serialise."""
 
-    def __init__(self, device: int = 0) -> None:
+    def __init__(self, device: int = 0, _borrowed: Optional[int] = None) -> None:
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         self.device = int(device)
         self._corpora: "weakref.WeakSet[Corpus]" = weakref.WeakSet()
-        _check(self._lib, self._lib.fx_init(self.device, ctypes.byref(self._h)))
+        self._owned = _borrowed is None
+        if _borrowed is not None:      # a context owned by a Group (fx_group_ctx)
+            self._h = ctypes.c_void_p(_borrowed)
+        else:
+            _check(self._lib, self._lib.fx_init(self.device, ctypes.byref(self._h)))
+
+    def set_option(self, name: str, value: Optional[object]) -> None:
+        """Tuning knob by the name of its environment variable (read once at fx_init); None restores the default."""
+        _check(self._lib, self._lib.fx_set_option(self._h, name.encode(), None if value is None else str(value).encode()))
 
     def close(self) -> None:
         """Shut the context down. Shards still alive on it are destroyed first: the C ABI requires every corpus to be
@@ -160,7 +207,8 @@ class Context:
         if getattr(self, "_h", None) is not None and self._h:
             for corpus in list(getattr(self, "_corpora", ())):
                 corpus.close()
-            self._lib.fx_shutdown(self._h)
+            if self._owned:
+                self._lib.fx_shutdown(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self) -> None:  # pragma: no cover - best effort
@@ -250,6 +298,14 @@ class Corpus:
         _check(self._lib, self._lib.fx_search_device(self._h, d_q_ptr, n_q, metric, k, precision, d_mask_ptr,
                                                      d_out_rows_ptr, d_out_dist_ptr))
 
+    def search_sharded_raw(self, comm: "Comm", q_ptr: int, n_q: int, metric: int, k: int, precision: int,
+                           out_rows_ptr: Optional[int], out_dist_ptr: Optional[int], mask_ptr: Optional[int] = None,
+                           on_device: bool = False) -> None:
+        """fx_search_sharded / fx_search_sharded_device: COLLECTIVE over the ranks of `comm` (query all-gather, shard
+        search, candidate all-gather, merge and result copy on one stream, one host synchronisation)."""
+        fn = self._lib.fx_search_sharded_device if on_device else self._lib.fx_search_sharded
+        _check(self._lib, fn(self._h, comm._h, q_ptr, n_q, metric, k, precision, mask_ptr, out_rows_ptr, out_dist_ptr))
+
     def distances(self, query: np.ndarray, metric: str | int) -> np.ndarray:
         """Distance of one query to every row (the reference's maxval=None branch)."""
         m = metric if isinstance(metric, int) else metric_code(metric)
@@ -282,6 +338,92 @@ class Corpus:
         if getattr(self, "_h", None) is not None and self._h:
             if self.ctx._h:   # the context destroys its shards when it is closed first
                 self._lib.fx_corpus_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """This rank's membership in a group of row shards (one NCCL communicator owned by the library).
+
+    One process per GPU: rank 0 calls `Comm.unique_id()`, the 128 bytes are broadcast by any means (torch.distributed,
+    a file, a socket) and every rank constructs `Comm(ctx, id, world, rank)` - collectively."""
+
+    def __init__(self, ctx: Context, unique_id: bytes, world: int, rank: int) -> None:
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError(f"unique id must be {COMM_ID_BYTES} bytes")
+        preload_nccl()
+        self._lib = ctx._lib
+        self.ctx, self.world, self.rank = ctx, int(world), int(rank)
+        self._h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        _check(self._lib, self._lib.fx_comm_init_rank(ctx._h, buf, self.world, self.rank, ctypes.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        preload_nccl()
+        lib = load_library()
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        _check(lib, lib.fx_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            if self.ctx._h:
+                self._lib.fx_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """ONE process owning several devices (the Flight server's deployment): a context, an NCCL communicator and a
+    worker thread per device, all inside the library (fx_group_*). Shard i of a corpus lives on `contexts[i]`."""
+
+    def __init__(self, devices: "list[int]") -> None:
+        preload_nccl()
+        self._lib = load_library()
+        self.devices = [int(d) for d in devices]
+        self._h = ctypes.c_void_p()
+        arr = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        _check(self._lib, self._lib.fx_group_create(arr, len(self.devices), ctypes.byref(self._h)))
+        self.contexts = [Context(d, _borrowed=self._lib.fx_group_ctx(self._h, i)) for i, d in enumerate(self.devices)]
+
+    def search(self, shards: "list[Corpus]", queries: np.ndarray, metric: str | int, k: int, precision: int = PREC_FP32,
+               row_mask: Optional[np.ndarray] = None) -> tuple[np.ndarray, np.ndarray]:
+        """Global k-NN over the row shards (contiguous, in order): every device searches its shard, candidates are
+        all-gathered over NVLink and merged on the device; queries and results are host arrays."""
+        m = metric if isinstance(metric, int) else metric_code(metric)
+        if len(shards) != len(self.devices):
+            raise ValueError(f"expected {len(self.devices)} shards, got {len(shards)}")
+        q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries)), dtype=np.float32)
+        if q.shape[1] != shards[0].dim:
+            raise ValueError(f"expected queries of shape (*, {shards[0].dim}), got {q.shape}")
+        n_q, k = q.shape[0], int(k)
+        out_rows = np.empty((n_q, max(k, 0)), dtype=np.int64)
+        out_dist = np.empty((n_q, max(k, 0)), dtype=np.float32)
+        mask_ptr = None
+        if row_mask is not None:
+            row_mask = np.ascontiguousarray(row_mask, dtype=np.uint8)
+            mask_ptr = row_mask.ctypes.data
+        handles = (ctypes.c_void_p * len(shards))(*[c._h for c in shards])
+        _check(self._lib, self._lib.fx_group_search(self._h, handles, q.ctypes.data, n_q, m, k, int(precision), mask_ptr,
+                                                    out_rows.ctypes.data, out_dist.ctypes.data))
+        return out_rows, out_dist
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            for ctx in self.contexts:
+                ctx.close()           # destroys the shards still alive on it; the group owns the context itself
+            self._lib.fx_group_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self) -> None:  # pragma: no cover - best effort

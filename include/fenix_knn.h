@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FX_ABI_VERSION 1
+#define FX_ABI_VERSION 2
 
 /* error codes */
 #define FX_OK 0
@@ -69,6 +69,8 @@ extern "C" {
 
 typedef struct fx_ctx fx_ctx;       /* one CUDA device + its streams and scratch */
 typedef struct fx_corpus fx_corpus; /* one device-resident, row-major corpus shard */
+typedef struct fx_comm fx_comm;     /* this rank's membership in a group of row shards (one NCCL communicator) */
+typedef struct fx_group fx_group;   /* ONE process owning several devices: contexts + communicators + a worker thread each */
 
 typedef struct fx_stats {
   int64_t n_rows;            /* rows resident in the shard */
@@ -84,7 +86,8 @@ typedef struct fx_stats {
   double last_main_kernel_ms;/* device time of the dominant kernel of the last search */
   int32_t last_path;         /* 0 = exact scan, 1 = tcgen05 TF32 filter + rerank, 2 = tcgen05 bf16 filter + rerank */
   int32_t last_variant;      /* tcgen05 paths: bit 0 = resident-query kernel (narrow rows; else the streaming kernel),
-                              * bit 1 = thresholds seeded by the sample prepass */
+                              * bit 1 = thresholds seeded by the sample prepass, bit 2 = CTA-pair (cta_group::2) streaming kernel */
+  double last_exchange_ms;   /* sharded searches: device time of all-gather + merge of the last search (CUDA events) */
 } fx_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -116,8 +119,15 @@ int fx_corpus_append_device(fx_corpus* c, const void* device_rows, int64_t n_row
  * cdist / F.normalize redo on every call in the reference, coder.py:40,44). */
 int fx_corpus_finalize(fx_corpus* c);
 
-/* Frees the shard (rows, norms, bf16 shadows). Must precede fx_shutdown of its context. */
+/* Frees the shard (rows, norms, bf16 shadows). Must precede fx_shutdown of its context. Safe against concurrent use:
+ * the handle is retired first (later calls on it fail with FX_EINVAL instead of touching freed memory) and the call
+ * waits for searches already running on the shard. */
 int fx_corpus_destroy(fx_corpus* c);
+
+/* Tuning knob of the context, by the name of the environment variable that provides its default (FENIX_TC_PRE,
+ * FENIX_TC_NO_RQ, FENIX_TC_PAIR, ...; see fenix_b200/csrc/tc_filter.cuh TcKnobs). The environment is read ONCE, at
+ * fx_init; the search path never calls getenv. value = NULL restores the built-in default. */
+int fx_set_option(fx_ctx* ctx, const char* name, const char* value);
 
 /* ---- search ---------------------------------------------------------------------------- */
 
@@ -128,6 +138,9 @@ int fx_corpus_destroy(fx_corpus* c);
  * Replaces index.py:162 (distance column) + index.py:165-168 (select_k + take indices). */
 int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, int32_t k,
               int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist);
+/* k is unbounded (the reference's select_k_unstable takes any maxval): k <= 320 on shards of >= 4096 rows takes the
+ * tensor-core path, larger k the fp64 scan - above 2048 in passes of 2048 neighbours, each pass admitting only keys
+ * above the last (distance, row) of the previous one. */
 
 /* Same with every pointer in DEVICE memory; enqueued on the context's stream and
  * synchronised before return. Used by the multi-GPU path so the shard-local top-k stays
@@ -143,9 +156,51 @@ int fx_distances(fx_corpus* c, const float* query, int32_t metric, float* out_di
 
 /* Merge `n_lists` per-shard results (DEVICE, each [n_q*k], laid out list-major:
  * rows[l*n_q*k + q*k + j]) into the global top-k ordered by (distance, row).
- * The step after the NCCL all-gather of the k*world candidates. */
+ * The step after the all-gather of the k*world candidates (fx_search_sharded does both itself). Any lists * k. */
 int fx_merge_topk(fx_ctx* ctx, const int64_t* d_rows, const float* d_dist, int32_t n_lists,
                   int64_t n_q, int32_t k, int64_t* d_out_rows, float* d_out_dist);
+
+/* ---- multi-GPU: row shards, one exchange step ------------------------------------------------
+ * Rank r of W owns the contiguous rows [r*ceil(N/W), ...) (fx_corpus_create's row_base), answers every query on its
+ * shard, and the k*W candidates per query are all-gathered (NCCL over NVLink / NVSwitch) and merged by (distance,
+ * row). Everything - query all-gather, shard search, candidate all-gather, merge, result copy - is enqueued on the
+ * context's stream with ONE host synchronisation at the end; a per-rank "flagged queries" word travels with the
+ * candidates, so that the rare certificate failure is settled collectively (second exchange) without a host round
+ * trip on the common path. The reference has no counterpart (no parallelism at all).
+ *
+ * Two deployments share the per-rank code:
+ *   - one process per GPU (torchrun): fx_comm_unique_id on rank 0, broadcast the 128 bytes by any means,
+ *     fx_comm_init_rank everywhere, then fx_search_sharded / fx_search_sharded_device collectively;
+ *   - one process owning all devices (the Flight server): fx_group_create, corpora on fx_group_ctx(g, i), then
+ *     fx_group_search from any thread (searches on a group serialise).
+ * NCCL is taken from the process (libnccl.so.2, dlopen; FENIX_NCCL_LIB overrides the name): nothing links against it. */
+#define FX_COMM_ID_BYTES 128
+int fx_comm_unique_id(void* out_id /* FX_COMM_ID_BYTES */);
+int fx_comm_init_rank(fx_ctx* ctx, const void* id, int32_t world, int32_t rank, fx_comm** out);
+int fx_comm_destroy(fx_comm* comm);
+
+/* Collective. `queries`: the WHOLE batch in HOST memory on every rank (each rank uploads only its 1/W slice and the
+ * slices are all-gathered over NVLink). `row_mask`: this shard's rows (HOST) or NULL. out_rows / out_dist: HOST
+ * [n_q*k], or both NULL on ranks that do not need the merged result (they skip merge and copy). */
+int fx_search_sharded(fx_corpus* c, fx_comm* comm, const float* queries, int64_t n_q, int32_t metric, int32_t k,
+                      int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist);
+/* Collective, everything in DEVICE memory: d_queries = the whole batch on every rank; d_out_* may be NULL. */
+int fx_search_sharded_device(fx_corpus* c, fx_comm* comm, const float* d_queries, int64_t n_q, int32_t metric,
+                             int32_t k, int32_t precision, const uint8_t* d_row_mask, int64_t* d_out_rows,
+                             float* d_out_dist);
+
+/* One process, n devices: contexts, an NCCL communicator per device (ncclCommInitAll) and one worker thread per
+ * device. fx_group_ctx(g, i) is the context shard i must be created on. */
+int fx_group_create(const int32_t* devices, int32_t n_devices, fx_group** out);
+int fx_group_size(fx_group* g);
+fx_ctx* fx_group_ctx(fx_group* g, int32_t i);
+/* shards[i] lives on fx_group_ctx(g, i) and holds the i-th contiguous row range. queries / out_* HOST; row_mask:
+ * HOST, one byte per row of the WHOLE corpus (shard i reads its range) or NULL. Replaces, for a corpus spread over
+ * the GPUs of one box, what fx_search replaces for one GPU (index.py:162-168). */
+int fx_group_search(fx_group* g, fx_corpus* const* shards, const float* queries, int64_t n_q, int32_t metric,
+                    int32_t k, int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist);
+/* Destroys the workers, communicators and contexts (destroy the shards first). */
+int fx_group_destroy(fx_group* g);
 
 /* ---- introspection --------------------------------------------------------------------- */
 

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported(built_library):
 
 def test_abi_version_and_no_torch_dependency(built_library):
     lib = knn.load_library()
-    assert lib.fx_abi_version() == 1
+    assert lib.fx_abi_version() == knn.ABI_VERSION
     out = subprocess.run(["ldd", built_library], capture_output=True, text=True).stdout
     assert "torch" not in out and "c10" not in out  # plain C ABI, no torch types behind it
 

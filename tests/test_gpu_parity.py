@@ -258,14 +258,22 @@ def test_resident_query_kernel_and_sample_prepass(ctx, metric, dim, k):
     sub = np.arange(0, nq, 37)
     rows_s, dist_s = c.search(qh[sub], metric, k, knn.PREC_EXACT_SCAN)
     assert np.array_equal(rows[sub], rows_s) and np.array_equal(dist[sub], dist_s)
-    for env in ({"FENIX_TC_PRE": "0"}, {"FENIX_TC_NO_RQ": "1"}, {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PRE": "0"}):
-        os.environ.update(env)
+    # the same search through the other kernels (tuning knobs are per-context options; the environment is only read
+    # once, at fx_init): adaptive thresholds, the streaming kernels (CTA pairs, one CTA per tile)
+    variants = ({"FENIX_TC_PRE": "0"}, {"FENIX_TC_NO_RQ": "1"}, {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PRE": "0"},
+                {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PAIR": "0"})
+    for opts in variants:
+        for key, value in opts.items():
+            ctx.set_option(key, value)
         try:
             rows_e, dist_e = c.search(qh, metric, k)
+            variant = c.stats().last_variant
         finally:
-            for key in env:
-                del os.environ[key]
-        assert np.array_equal(rows, rows_e) and np.array_equal(dist, dist_e), env
+            for key in opts:
+                ctx.set_option(key, None)
+        assert np.array_equal(rows, rows_e) and np.array_equal(dist, dist_e), opts
+        if "FENIX_TC_NO_RQ" in opts:
+            assert (variant & 1) == 0 and bool(variant & 4) == ("FENIX_TC_PAIR" not in opts), (opts, variant)
     c.close()
 
 
@@ -496,8 +504,11 @@ def test_bf16_shadow_filter_is_exact_in_fp32_mode(ctx, dim, monkeypatch):
     corpus = rng.standard_normal((20000, dim), dtype=np.float32)
     queries = rng.standard_normal((130, dim), dtype=np.float32)
     c = make_corpus(ctx, corpus)
-    monkeypatch.setenv("FENIX_DEBUG_BF16", "1")
-    s = c.debug_scores(queries, "dot").astype(np.float64)
+    ctx.set_option("FENIX_DEBUG_BF16", 1)
+    try:
+        s = c.debug_scores(queries, "dot").astype(np.float64)
+    finally:
+        ctx.set_option("FENIX_DEBUG_BF16", None)
     q, x = queries[:128].astype(np.float64), corpus[:256].astype(np.float64)
     bound = (1.1 * 2.0 ** -8 + dim * 2.0 ** -21) * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :]
     assert (np.abs(s - q @ x.T) / bound).max() < 0.6
