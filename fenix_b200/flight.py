@@ -40,6 +40,9 @@ class Server(fl.FlightServerBase):
         self.grpc = f"grpc://{host}:{port}"
         self._view: dict = {}  # per-server do_get options (set-*/del-* actions), as the reference keeps them
         super().__init__(location=self.grpc)
+        # FENIX_WARM="table:column,...": device shards of those columns are uploaded before the first request
+        if os.environ.get("FENIX_WARM"):
+            io.shards.warm(self.root)
 
     def get_flight_info(self, ctx, descriptor):
         raise NotImplementedError()
@@ -49,7 +52,15 @@ class Server(fl.FlightServerBase):
 
     # ---- tables --------------------------------------------------------------------------
     def do_put(self, ctx, descriptor, reader, writer) -> None:
-        io.table.make(self.root, descriptor.path[0].decode(), reader.to_reader())
+        name = descriptor.path[0].decode()
+        io.table.make(self.root, name, reader.to_reader())
+        # Upload at ingest: the table's vector columns go to the device(s) now (rows + norms + bf16 shadow), so the first
+        # search after a do_put does not pay for the upload. FENIX_UPLOAD_ON_PUT=0 restores the lazy behaviour.
+        if os.environ.get("FENIX_UPLOAD_ON_PUT", "1") != "0":
+            try:
+                io.shards.warm(self.root, name)
+            except Exception:   # no usable device now: the search that needs it will say so
+                pass
 
     def do_get(self, ctx, ticket):
         names = ticket.ticket.decode().split(":")
@@ -91,6 +102,7 @@ class Server(fl.FlightServerBase):
                     io.index.drop(self.root, parts[-1], os.sep.join(parts[:-2]), parts[-2])
         elif kind == "remove":
             io.shards.invalidate(self.root)
+            io.coder.forget(self.root)
             shutil.rmtree(self.root)
         elif kind.startswith("set-") and kind[4:] in ("coding", "column", "filter", "select"):
             self._view[kind[4:]] = config[kind[4:]]

@@ -27,6 +27,9 @@ class _Request:
         self.error = None
 
 
+_PROMOTED = object()   # marker handed to a follower that must take over as leader of the remaining group
+
+
 class MicroBatcher:
     def __init__(self, max_wait_us: float | None = None, max_batch: int | None = None) -> None:
         self.max_wait = (float(os.environ.get("FENIX_MICROBATCH_US", 300)) if max_wait_us is None else max_wait_us) * 1e-6
@@ -59,16 +62,31 @@ class MicroBatcher:
         try:
             if not leader:
                 req.done.wait()
-            else:
+                if req.error is _PROMOTED:       # the previous leader's batch was full: lead what is left
+                    req.error = None
+                    req.done = None
+                    leader, lonely = True, False
+            if leader:
                 if not lonely:
                     deadline = time.perf_counter() + self.max_wait
                     while time.perf_counter() < deadline:
                         with self._lock:
-                            if len(group) >= self.max_batch:
+                            if len(self._pending.get(key, ())) >= self.max_batch:
                                 break
                         time.sleep(50e-6)
                 with self._lock:
-                    batch = self._pending.pop(key)
+                    group = self._pending.pop(key)
+                    # max_batch is a cap, not only a wake-up condition: the overflow of a burst stays pending under a
+                    # new leader (its first member, woken below), so scratch buffers never grow past the cap
+                    batch, rest = group[: self.max_batch], group[self.max_batch:]
+                    if rest:
+                        self._pending[key] = rest
+                        promoted = rest[0]
+                    else:
+                        promoted = None
+                if promoted is not None:
+                    promoted.error = _PROMOTED
+                    promoted.done.set()
                 try:
                     rows, dist = runner(np.stack([r.query for r in batch]))
                     for i, r in enumerate(batch):

@@ -69,6 +69,7 @@ class Coding(TypedDict):
 
 _codings: dict[tuple, tuple] = {}     # (root, name) -> (file signature, Coding, device shards of the codebooks)
 _codings_lock = threading.Lock()
+_codings_gates: dict[tuple, threading.Lock] = {}   # one build per key at a time
 
 
 def path_of(root: str, name: str) -> str:
@@ -99,15 +100,27 @@ def _entry(root: str, name: str) -> tuple:
         hit = _codings.get(key)
         if hit is not None and hit[0] == sig:
             return hit
-    coding = _read(path)
-    books = [_book_shard(coding["tensor"][j]) for j in range(coding["tensor"].shape[0])]
-    with _codings_lock:
-        old = _codings.get(key)
-        _codings[key] = fresh = (sig, coding, books)
-    if old is not None:
-        for b in old[2]:
-            b.close()
+        gate = _codings_gates.setdefault(key, threading.Lock())
+    with gate:   # single-flight: concurrent first uses of a coding share one build
+        with _codings_lock:
+            hit = _codings.get(key)
+            if hit is not None and hit[0] == sig:
+                return hit
+        coding = _read(path)
+        books = [_book_shard(coding["tensor"][j]) for j in range(coding["tensor"].shape[0])]
+        with _codings_lock:
+            # a replaced entry is only dropped, never closed here: threads still ranking codes against its books hold
+            # references, and the device shards are freed when the last one lets go (Corpus.__del__)
+            _codings[key] = fresh = (sig, coding, books)
     return fresh
+
+
+def forget(root: Optional[str] = None, name: Optional[str] = None) -> None:
+    """Drop cached codings (and with them the device shards of their codebooks): all, those under `root`, or one."""
+    root = os.path.abspath(root) if root is not None else None
+    with _codings_lock:
+        for key in [k for k in _codings if (root is None or k[0] == root) and (name is None or k[1] == name)]:
+            _codings.pop(key)
 
 
 def _book_shard(codewords: np.ndarray) -> knn.Corpus:
@@ -256,8 +269,4 @@ def drop(root: str, name: str) -> None:
     path = path_of(root, name)
     if os.path.exists(path):
         os.unlink(path)
-    with _codings_lock:
-        old = _codings.pop((os.path.abspath(root), name), None)
-    if old is not None:
-        for b in old[2]:
-            b.close()
+    forget(root, name)

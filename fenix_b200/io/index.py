@@ -170,17 +170,31 @@ def call(
             raise AssertionError("metric is required")
         knn.metric_code(metric)  # ValueError on unknown names, as coder.py:50
 
-        if probe_codes is not None and batched:
-            # one row mask per query: the batched wire extension answers an IVF search query by query
-            parts = []
-            for qi in range(queries.shape[0]):
-                one = call(root, coding, source, column, queries[qi], metric=metric, select=select, filter=filter,
-                           maxval=maxval, probes=probes, precision=precision)
-                parts.append(one.append_column(QUERY_COL, pa.array(np.full(one.num_rows, qi, dtype=np.int32))))
-            return pa.concat_tables(parts).combine_chunks()
-
         out_cols = [*select] if select is not None else data.column_names
         mask = _row_mask(data, column, filter) if filter is not None else None
+
+        if probe_codes is not None and batched:
+            # Batched IVF: every query has its own probe cells, i.e. its own row mask. The shard, the predicate mask and
+            # the code column are prepared once; each query is one masked search on the resident shard.
+            codes = data.column(CODE_COL).to_numpy()
+            parts = []
+            for qi in range(queries.shape[0]):
+                cell = np.isin(codes, probe_codes[qi]).astype(np.uint8)
+                m_q = cell if mask is None else (mask & cell)
+                n_live = int(m_q.sum())
+                k = n_live if maxval is None else min(int(maxval), n_live)
+                if k < 1:
+                    continue
+                r_q, d_q = shard.search(queries[qi: qi + 1], metric, k, precision, m_q)
+                keep = r_q[0] >= 0
+                one = take_rows(data, out_cols, r_q[0][keep])
+                one = one.append_column(DIST_COL, _distance_array(d_q[0][keep], typ.value_type))
+                parts.append(one.append_column(QUERY_COL, pa.array(np.full(one.num_rows, qi, dtype=np.int32))))
+            if not parts:
+                empty = data.select(out_cols).slice(0, 0).append_column(DIST_COL, pa.array([], type=typ.value_type))
+                return empty.append_column(QUERY_COL, pa.array([], type=pa.int32())).combine_chunks()
+            return pa.concat_tables(parts).combine_chunks()
+
         if probe_codes is not None:
             # `__CODED_ID__ isin(probe codes)` AND the caller's predicate (index.py:119-126)
             cell = np.isin(data.column(CODE_COL).to_numpy(), probe_codes[0]).astype(np.uint8)
@@ -220,6 +234,8 @@ def call(
     finally:
         if owned:
             shard.close()
+        else:
+            shard.release()   # the lease taken by shards.get
 
 
 def _batched_input(target) -> bool:

@@ -22,7 +22,9 @@ from . import table as _table
 
 _lock = threading.Lock()
 _contexts: dict[int, knn.Context] = {}
+_groups: dict[tuple, knn.Group] = {}
 _cache: dict[tuple, "ShardSet"] = {}
+_building: dict[tuple, threading.Lock] = {}   # one upload per key at a time (single-flight)
 
 
 def devices() -> list[int]:
@@ -37,6 +39,17 @@ def context(device: int) -> knn.Context:
         if ctx is None:
             ctx = _contexts[device] = knn.Context(device)
         return ctx
+
+
+def group(device_ids: Sequence[int]) -> knn.Group:
+    """The process-wide device group for this device list (fx_group_create: contexts + NCCL communicators + a worker
+    thread per device inside the library). One per distinct list; lives as long as the process."""
+    key = tuple(int(d) for d in device_ids)
+    with _lock:
+        g = _groups.get(key)
+        if g is None:
+            g = _groups[key] = knn.Group(list(key))
+        return g
 
 
 def chunk_rows(chunk: pa.FixedSizeListArray) -> np.ndarray:
@@ -63,66 +76,72 @@ def chunk_rows(chunk: pa.FixedSizeListArray) -> np.ndarray:
 
 @dataclass
 class ShardSet:
-    """Row-sharded device copy of one vector column (one Corpus per device)."""
+    """Row-sharded device copy of one vector column (one Corpus per device).
+
+    Lifetime: request threads LEASE a set for the duration of a search (`with shard.lease():`); `retire()` - called when
+    the table changes or the cache drops the entry - closes it at once when idle, otherwise when the last lease is
+    returned. A set is never closed under a running search (the C library additionally validates every corpus handle,
+    include/fenix_knn.h fx_corpus_destroy)."""
 
     dim: int
     n_rows: int
     corpora: list[knn.Corpus] = field(default_factory=list)
     bases: list[int] = field(default_factory=list)
     signature: tuple = ()
+    group: Optional[knn.Group] = None      # >= 2 devices: the in-library device group that runs the exchange
+    _users: int = 0
+    _retired: bool = False
+    _guard: threading.Lock = field(default_factory=threading.Lock)
 
+    # ---- leases ----
+    def lease(self) -> "ShardSet":
+        with self._guard:
+            if self._retired and not self.corpora:
+                raise RuntimeError("shard set is closed")
+            self._users += 1
+        return self
+
+    def release(self) -> None:
+        with self._guard:
+            self._users -= 1
+            close_now = self._retired and self._users == 0
+        if close_now:
+            self._close()
+
+    def __enter__(self) -> "ShardSet":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.release()
+
+    def retire(self) -> None:
+        """No new searches; free the device memory as soon as the running ones are done."""
+        with self._guard:
+            self._retired = True
+            close_now = self._users == 0
+        if close_now:
+            self._close()
+
+    def close(self) -> None:
+        self.retire()
+
+    def _close(self) -> None:
+        for c in self.corpora:
+            c.close()
+        self.corpora = []
+
+    # ---- search ----
     def search(self, queries: np.ndarray, metric: str, k: int, precision: int = knn.PREC_FP32,
                row_mask: Optional[np.ndarray] = None) -> tuple[np.ndarray, np.ndarray]:
         if len(self.corpora) == 1:
             return self.corpora[0].search(queries, metric, k, precision, row_mask)
-        return self._search_sharded(queries, metric, k, precision, row_mask)
-
-    def _search_sharded(self, queries, metric, k, precision, row_mask):
-        # one thread per device (ctypes releases the GIL); shard-local top-k lists are copied to
-        # the first device and merged there by fx_merge_topk (order: distance, then row)
-        import torch
-
-        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
-        n_q = q.shape[0]
-        results: list = [None] * len(self.corpora)
-        errors: list = []
-
-        def work(i: int) -> None:
-            try:
-                c = self.corpora[i]
-                m = None
-                if row_mask is not None:
-                    m = row_mask[self.bases[i]: self.bases[i] + c.n_rows]
-                results[i] = c.search(q, metric, k, precision, m)
-            except BaseException as exc:  # surfaced below
-                errors.append(exc)
-
-        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(self.corpora))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        dev0 = self.corpora[0].ctx
-        device = torch.device("cuda", dev0.device)
-        rows = torch.from_numpy(np.stack([r[0] for r in results])).to(device)
-        dist = torch.from_numpy(np.stack([r[1] for r in results])).to(device)
-        out_rows = torch.empty((n_q, k), dtype=torch.int64, device=device)
-        out_dist = torch.empty((n_q, k), dtype=torch.float32, device=device)
-        torch.cuda.synchronize(device)
-        dev0.merge_topk_device(rows.data_ptr(), dist.data_ptr(), len(results), n_q, k,
-                               out_rows.data_ptr(), out_dist.data_ptr())
-        return out_rows.cpu().numpy(), out_dist.cpu().numpy()
+        # one process, several devices: fx_group_search - every device searches its shard concurrently (worker threads
+        # inside the library), the k x W candidates are all-gathered over NVLink and merged on the device
+        return self.group.search(self.corpora, queries, metric, k, precision, row_mask)
 
     def distances(self, query: np.ndarray, metric: str) -> np.ndarray:
         parts = [c.distances(query, metric) for c in self.corpora]
         return parts[0] if len(parts) == 1 else np.concatenate(parts)
-
-    def close(self) -> None:
-        for c in self.corpora:
-            c.close()
-        self.corpora = []
 
 
 def from_chunks(column: pa.ChunkedArray, device_ids: Optional[Sequence[int]] = None) -> ShardSet:
@@ -134,13 +153,17 @@ def from_chunks(column: pa.ChunkedArray, device_ids: Optional[Sequence[int]] = N
         raise NotImplementedError(f"embedding columns must be float16 / float32 / float64 (got {typ.value_type})")
     dim, n = typ.list_size, len(column)
     devs = list(device_ids) if device_ids is not None else devices()
-    world = max(1, min(len(devs), max(n, 1)))
+    world = max(1, len(devs))
     per = -(-n // world) if n else 0
     shard = ShardSet(dim=dim, n_rows=n)
+    ctxs = [context(devs[0])] if world == 1 else None
+    if world > 1:
+        shard.group = group(devs)
+        ctxs = shard.group.contexts
     for r in range(world):
-        lo, hi = r * per, min(n, (r + 1) * per)
+        lo, hi = min(n, r * per), min(n, (r + 1) * per)      # trailing shards of a tiny table are empty
         shard.bases.append(lo)
-        shard.corpora.append(knn.Corpus(context(devs[r]), max(hi - lo, 0), dim, row_base=lo))
+        shard.corpora.append(knn.Corpus(ctxs[r], max(hi - lo, 0), dim, row_base=lo))
     pos = 0
     for chunk in column.chunks:
         rows = chunk_rows(chunk)
@@ -186,22 +209,55 @@ def load_table(root: str, source: str | Sequence[str]) -> pa.Table:
 
 
 def get(root: str, source: str | Sequence[str], column: str, table: pa.Table) -> ShardSet:
-    """Cached shard set for `column` of the named table(s); uploads on first use."""
+    """LEASED shard set for `column` of the named table(s): `with shards.get(...) as shard:` (or release() it). Uploads
+    on first use - one upload per key however many request threads miss at once (single-flight); a set replaced by a
+    newer table version is retired, not closed under the searches still running on it."""
     names = (source,) if isinstance(source, str) else tuple(source)
     key = (os.path.abspath(root), names, column, tuple(devices()))
     sig = _signature(root, names)
     with _lock:
         hit = _cache.get(key)
         if hit is not None and hit.signature == sig:
-            return hit
-    fresh = from_chunks(table.column(column))
-    fresh.signature = sig
-    with _lock:
-        old = _cache.get(key)
-        _cache[key] = fresh
+            return hit.lease()
+        gate = _building.setdefault(key, threading.Lock())
+    with gate:
+        with _lock:   # somebody else may have finished the upload while this thread waited at the gate
+            hit = _cache.get(key)
+            if hit is not None and hit.signature == sig:
+                return hit.lease()
+        fresh = from_chunks(table.column(column))
+        fresh.signature = sig
+        with _lock:
+            old = _cache.get(key)
+            _cache[key] = fresh
+            leased = fresh.lease()
     if old is not None:
-        old.close()
-    return fresh
+        old.retire()
+    return leased
+
+
+def warm(root: str, spec: Optional[str] = None) -> list[str]:
+    """Upload shards ahead of the first search: `spec` (default: $FENIX_WARM) = "table:column,table2:column2,...".
+    A table without ":column" warms every FixedSizeList<float> column. Returns what was uploaded. Called by the server
+    at start-up and after every do_put."""
+    spec = os.environ.get("FENIX_WARM", "") if spec is None else spec
+    done = []
+    for item in [tok.strip() for tok in spec.split(",") if tok.strip()]:
+        name, _, column = item.partition(":")
+        try:
+            table = load_table(root, name)
+        except (FileNotFoundError, OSError):
+            continue
+        columns = [column] if column else vector_columns(table)
+        for col in columns:
+            get(root, name, col, table).release()
+            done.append(f"{name}:{col}")
+    return done
+
+
+def vector_columns(table: pa.Table) -> list[str]:
+    return [f.name for f in table.schema
+            if pa.types.is_fixed_size_list(f.type) and f.type.value_type in (pa.float16(), pa.float32(), pa.float64())]
 
 
 def invalidate(root: Optional[str] = None, name: Optional[str] = None) -> None:
@@ -213,4 +269,4 @@ def invalidate(root: Optional[str] = None, name: Optional[str] = None) -> None:
         for k in [k for k in _tables if (root is None or k[0] == root) and (name is None or name in k[1])]:
             _tables.pop(k)
     for v in victims:
-        v.close()
+        v.retire()

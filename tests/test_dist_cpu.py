@@ -108,3 +108,28 @@ def test_two_rank_gloo_query_sharded_gather():
         out = mgr.dict()
         mp.spawn(_replica_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _id_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        drawn = []
+
+        def make_id():
+            drawn.append(rank)
+            return bytes(range(128))
+
+        uid = fdist.broadcast_comm_id(make_id)
+        out[rank] = (uid == bytes(range(128)), drawn)
+    finally:
+        td.destroy_process_group()
+
+
+def test_two_rank_gloo_comm_id_broadcast():
+    """The library's communicator id (fx_comm_unique_id) is drawn on rank 0 only and reaches every rank intact."""
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_id_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: (True, [0]), 1: (True, [])}

@@ -149,8 +149,9 @@ def test_edge_cases(ctx):
     assert r0.shape == (0, 3)
     with pytest.raises(ValueError):
         c.search(corpus[:1], "l2", 0)
-    with pytest.raises(NotImplementedError):
-        c.search(corpus[:1], "l2", 5000)
+    # any k is served (the reference's select_k_unstable takes any maxval): far beyond N pads
+    rows, dist = c.search(corpus[:1], "l2", 5000)
+    assert rows.shape == (1, 5000) and sorted(rows[0, :50].tolist()) == list(range(50)) and (rows[0, 50:] == -1).all()
     with pytest.raises(ValueError):
         c.search(np.zeros((1, 5), np.float32), "l2", 3)
     with pytest.raises(knn.FenixKnnError):
@@ -201,6 +202,134 @@ def test_row_base_and_sharded_merge_equal_single_shard(ctx):
     assert np.array_equal(out_rows.cpu().numpy(), want_rows)
     assert np.array_equal(out_dist.cpu().numpy(), want_dist)
     whole.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_large_k_runs_in_passes(ctx, metric):
+    """k above 2048: the fp64 scan runs in passes of 2048 neighbours, each admitting only keys above the last key of the
+    pass before; duplicated rows sit across the pass boundary (ties are broken by row, so the passes still partition)."""
+    from oracle import brute_force_f64
+
+    rng = np.random.default_rng(77)
+    corpus = rng.standard_normal((9000, 24), dtype=np.float32)
+    corpus[4000:4100] = corpus[100:200]          # 100 duplicated rows
+    queries = np.concatenate([rng.standard_normal((3, 24), dtype=np.float32), corpus[150:151]])
+    c = make_corpus(ctx, corpus)
+    for k in (2049, 5000, 9000, 9500):
+        rows, dist = c.search(queries, metric, k)
+        want_rows, want_dist = brute_force_f64(corpus, queries, metric, k)
+        kk = min(k, len(corpus))
+        assert np.array_equal(rows[:, :kk], want_rows), (metric, k)
+        assert np.allclose(dist[:, :kk], want_dist, rtol=3e-7, atol=1e-7), (metric, k)
+        assert (rows[:, kk:] == -1).all()
+    c.close()
+
+
+def test_merge_of_many_long_lists(ctx):
+    """lists * k above 8192 entries: the rank merge (no shared-memory limit) equals one unsharded search; k = 1500 over 8
+    shards is the case a 1024 < k <= 2048 search hits on an 8-GPU box."""
+    import torch
+    from fenix_b200.dist import shard_bounds
+
+    rng = np.random.default_rng(31)
+    corpus = rng.standard_normal((24_000, 16), dtype=np.float32)
+    corpus[20_000:20_050] = corpus[:50]
+    queries = np.concatenate([rng.standard_normal((5, 16), dtype=np.float32), corpus[7:8]])
+    k, world = 1500, 8
+    whole = make_corpus(ctx, corpus)
+    want_rows, want_dist = whole.search(queries, "l2", k)
+    parts_r, parts_d = [], []
+    for r in range(world):
+        lo, hi = shard_bounds(len(corpus), world, r)
+        s = make_corpus(ctx, corpus[lo:hi], row_base=lo)
+        rr, dd = s.search(queries, "l2", k)
+        parts_r.append(rr)
+        parts_d.append(dd)
+        s.close()
+    dev = torch.device("cuda", 0)
+    g_rows = torch.from_numpy(np.stack(parts_r)).to(dev)
+    g_dist = torch.from_numpy(np.stack(parts_d)).to(dev)
+    out_rows = torch.empty((len(queries), k), dtype=torch.int64, device=dev)
+    out_dist = torch.empty((len(queries), k), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    ctx.merge_topk_device(g_rows.data_ptr(), g_dist.data_ptr(), world, len(queries), k, out_rows.data_ptr(), out_dist.data_ptr())
+    assert np.array_equal(out_rows.cpu().numpy(), want_rows)
+    assert np.array_equal(out_dist.cpu().numpy(), want_dist)
+    whole.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+@pytest.mark.parametrize("shape", [(20_000, 256, 300, 10), (50_000, 768, 130, 10), (30_000, 200, 257, 37), (12_345, 448, 129, 100)])
+def test_cta_pair_streaming_kernel(ctx, shape, metric):
+    """Wide rows and at least two query tiles take the CTA-pair (cta_group::2) streaming kernel: ragged query tiles (the
+    second CTA of a pair holds a near-empty tile), odd widths, a row mask, and cosine without the normalised shadow (the
+    multiplicative epilogue) - all against the fp64 scan, a few queries against the oracle."""
+    from oracle import search_rows
+
+    n, d, nq, k = shape
+    rng = np.random.default_rng(n + d)
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    queries = rng.standard_normal((nq, d), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    rows, dist = c.search(queries, metric, k)
+    assert c.stats().last_variant & 4, "expected the CTA-pair kernel"
+    rows_s, dist_s = c.search(queries, metric, k, knn.PREC_EXACT_SCAN)
+    assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
+    table = table_of(corpus, 4096)
+    for qi in (0, 128, nq - 1):
+        ref_rows, ref_dist = search_rows(table, "vector", queries[qi], metric, k)
+        assert_same_neighbours(rows[qi], dist[qi], ref_rows, ref_dist, corpus, queries[qi], metric)
+    mask = (np.arange(n) % 5 != 1).astype(np.uint8)
+    rows_m, dist_m = c.search(queries, metric, k, row_mask=mask)
+    assert c.stats().last_variant & 4
+    rows_ms, dist_ms = c.search(queries, metric, k, knn.PREC_EXACT_SCAN, row_mask=mask)
+    assert np.array_equal(rows_m, rows_ms) and np.array_equal(dist_m, dist_ms)
+    if metric == "cosine":
+        ctx.set_option("FENIX_NO_NORM_SHADOW", 1)
+        try:
+            c2 = make_corpus(ctx, corpus)            # a shard that never builds the normalised shadow
+            rows_e, dist_e = c2.search(queries, metric, k)
+            assert c2.stats().last_variant & 4
+            c2.close()
+        finally:
+            ctx.set_option("FENIX_NO_NORM_SHADOW", None)
+        assert np.array_equal(rows_e, rows_s) and np.array_equal(dist_e, dist_s)
+    c.close()
+
+
+def test_group_search_in_one_process(built_library):
+    """fx_group_*: one process owning the devices, an NCCL communicator and a worker thread per device inside the
+    library. On a single-GPU box the group has one member (no exchange); with >= 2 GPUs the shards are searched
+    concurrently, all-gathered over NVLink and merged on the device."""
+    import torch
+    from fenix_b200.dist import shard_bounds
+    from oracle import brute_force_f64
+
+    n_dev = min(torch.cuda.device_count(), 4)
+    rng = np.random.default_rng(55)
+    corpus = rng.standard_normal((40_003, 96), dtype=np.float32)
+    corpus[30_000] = corpus[11]                      # a cross-shard tie
+    queries = np.concatenate([rng.standard_normal((140, 96), dtype=np.float32), corpus[11:12]])
+    group = knn.Group(list(range(n_dev)))
+    shards = []
+    for r in range(n_dev):
+        lo, hi = shard_bounds(len(corpus), n_dev, r)
+        s = knn.Corpus(group.contexts[r], hi - lo, 96, row_base=lo)
+        s.append(corpus[lo:hi])
+        shards.append(s.finalize())
+    for metric, k in (("l2", 10), ("dot", 100), ("cosine", 1500)):
+        rows, dist = group.search(shards, queries, metric, k)
+        want_rows, want_dist = brute_force_f64(corpus, queries, metric, k)
+        assert np.array_equal(rows, want_rows), (metric, k)
+        assert np.allclose(dist, want_dist, rtol=3e-7, atol=1e-7), (metric, k)
+    mask = (np.arange(len(corpus)) % 3 != 0).astype(np.uint8)
+    rows, dist = group.search(shards, queries, "l2", 10, row_mask=mask)
+    live = np.nonzero(mask)[0]
+    want_rows, want_dist = brute_force_f64(corpus[live], queries, "l2", 10)
+    assert np.array_equal(rows, live[want_rows]) and np.allclose(dist, want_dist, rtol=3e-7, atol=1e-7)
+    for s in shards:
+        s.close()
+    group.close()
 
 
 def test_large_property_checks(ctx):
@@ -662,10 +791,28 @@ class TestFlightDropIn:
         qs = rng.random((5, self.VECTOR_SIZE), dtype=np.float32)
         out = client.search(qs, "test/table", "vector", "l2", select=["id"], maxval=3)
         assert out.column_names == ["id", "__DISTANCE__", "__QUERY__"] and out.num_rows == 15
-        for qi in range(5):
-            one = client.search(qs[qi], "test/table", "vector", "l2", select=["id"], maxval=3)
-            sel = out.filter(pc.field("__QUERY__") == qi)
-            assert sel.column("id").to_pylist() == one.column("id").to_pylist()
+        for metric in ("l2", "cosine", "dot"):
+            out = client.search(qs, "test/table", "vector", metric, select=["id"], maxval=7)
+            assert out.num_rows == 35
+            for qi in range(5):
+                # every query of the batch against the ORACLE (the reference's own single-query answer), not against
+                # this library's single-query path
+                sel = out.filter(pc.field("__QUERY__") == qi)
+                ref_rows, ref_dist = search_rows(source, "vector", qs[qi], metric, 7)
+                assert_same_neighbours(sel.column("id").to_numpy(), sel.column("__DISTANCE__").to_numpy(),
+                                       ref_rows, ref_dist, corpus, qs[qi], metric)
+        # batched IVF: one probe mask per query, answered on one resident shard
+        config = dict(metric="l2", codebook_size=4, num_codebooks=2, batch_size=256, num_epochs=1)
+        client.make_index("cbq", "test/table", "vector", config)
+        try:
+            full = client.search(qs, "test/table", "vector", "l2", coding="cbq", select=["id"], maxval=5, probes=16)
+            for qi in range(5):
+                sel = full.filter(pc.field("__QUERY__") == qi)
+                ref_rows, ref_dist = search_rows(source, "vector", qs[qi], "l2", 5)     # probing every cell = exact search
+                assert_same_neighbours(sel.column("id").to_numpy(), sel.column("__DISTANCE__").to_numpy(),
+                                       ref_rows, ref_dist, corpus, qs[qi], "l2")
+        finally:
+            client.drop_index("cbq")
 
     def test_errors_surface_as_flight_errors(self, served):
         import pyarrow.flight as fl

@@ -203,3 +203,119 @@ def test_micro_batcher_coalesces_concurrent_requests():
         raise RuntimeError("device lost")
     with pytest.raises(RuntimeError):
         mb.submit("x", np.zeros(4, np.float32), boom)
+
+
+def test_micro_batcher_caps_the_batch():
+    """max_batch is a cap: a burst larger than it is served in several batches, the remainder under a promoted leader."""
+    import threading
+    import time
+
+    from fenix_b200.io.batcher import MicroBatcher
+
+    calls = []
+
+    def runner(qs):
+        calls.append(len(qs))
+        time.sleep(0.01)
+        return qs.sum(axis=1, keepdims=True).astype(np.int64), qs[:, :1].astype(np.float32)
+
+    mb = MicroBatcher(max_wait_us=30000, max_batch=4)
+    out = {}
+
+    def client(i):
+        out[i] = mb.submit("k", np.full(4, float(i), np.float32), runner)
+
+    threads = [threading.Thread(target=client, args=(i,)) for i in range(19)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=20)
+    assert not any(t.is_alive() for t in threads), "a request was never answered"
+    assert all(out[i][0][0] == 4 * i for i in range(19))
+    assert sum(calls) == 19 and max(calls) <= 4, calls
+
+
+class _FakeCorpus:
+    closed = 0
+
+    def close(self):
+        type(self).closed += 1
+
+
+def test_shard_cache_is_single_flight_and_never_closes_a_leased_set(tmp_path, monkeypatch):
+    """Concurrent cold requests share ONE upload; a set replaced by a new table version is retired and only closed
+    when its last lease is returned (a closed set must never reach a request thread)."""
+    import threading
+    import time
+
+    root = str(tmp_path)
+    data = table_of(np.arange(40, dtype=np.float32).reshape(10, 4), 5)
+    fenix.io.table.make(root, "t", data.to_reader())
+    builds = []
+
+    def fake_from_chunks(column, device_ids=None):
+        builds.append(1)
+        time.sleep(0.05)      # an upload takes a while: the other threads arrive meanwhile
+        return shards.ShardSet(dim=4, n_rows=len(column), corpora=[_FakeCorpus()], bases=[0])
+
+    monkeypatch.setattr(shards, "from_chunks", fake_from_chunks)
+    _FakeCorpus.closed = 0
+    shards.invalidate(root)
+    table = shards.load_table(root, "t")
+    got = []
+
+    def request():
+        got.append(shards.get(root, "t", "vector", table))
+
+    threads = [threading.Thread(target=request) for _ in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(builds) == 1 and len({id(g) for g in got}) == 1
+    first = got[0]
+    assert first.corpora and first._users == 6
+    # a new version of the table arrives while those six searches are still running
+    fenix.io.table.make(root, "t", table_of(np.ones((7, 4), np.float32), 7).to_reader())
+    assert _FakeCorpus.closed == 0 and first.corpora, "a leased set was closed under its users"
+    with shards.get(root, "t", "vector", shards.load_table(root, "t")) as second:
+        assert second is not first and second.n_rows == 7 and len(builds) == 2
+    for _ in range(5):
+        first.release()
+    assert _FakeCorpus.closed == 0
+    first.release()                       # the last lease: now the retired set is freed
+    assert _FakeCorpus.closed == 1 and first.corpora == []
+    shards.invalidate(root)               # idle sets are closed at once
+    assert _FakeCorpus.closed == 2
+
+
+def test_arrow_make_replaces_the_file_atomically(tmp_path):
+    """A table already memory-mapped keeps reading its old version while (and after) a new one is written."""
+    from fenix_b200.io import arrow as fx_arrow
+
+    path = str(tmp_path / "sources" / "t.arrow")
+    old = fx_arrow.make(path, table_of(np.arange(32, dtype=np.float32).reshape(8, 4), 4).to_reader())
+    new = fx_arrow.make(path, table_of(np.full((3, 4), 9, np.float32), 3).to_reader())
+    assert old.num_rows == 8 and old.column("id").to_pylist() == list(range(8))       # old mapping intact
+    assert old.column("vector").chunk(1).values.to_numpy()[-1] == 31.0
+    assert new.num_rows == 3 and fx_arrow.load(path).num_rows == 3
+    assert os.listdir(os.path.dirname(path)) == ["t.arrow"]                            # no temp file left behind
+
+
+def test_warm_spec(tmp_path, monkeypatch):
+    """FENIX_WARM="table:column,table2": the named columns (or every vector column) are uploaded ahead of the first search."""
+    root = str(tmp_path)
+    fenix.io.table.make(root, "a", table_of(np.zeros((4, 4), np.float32), 4).to_reader())
+    fenix.io.table.make(root, "b", table_of(np.zeros((6, 4), np.float32), 6).to_reader())
+    seen = []
+
+    def fake_from_chunks(column, device_ids=None):
+        seen.append(len(column))
+        return shards.ShardSet(dim=4, n_rows=len(column), corpora=[_FakeCorpus()], bases=[0])
+
+    monkeypatch.setattr(shards, "from_chunks", fake_from_chunks)
+    shards.invalidate(root)
+    assert shards.warm(root, "a:vector, b, missing:vector") == ["a:vector", "b:vector"]
+    assert seen == [4, 6]
+    assert shards.warm(root, "a:vector") == ["a:vector"] and seen == [4, 6]           # cached: no second upload
+    shards.invalidate(root)
