@@ -95,7 +95,7 @@ struct TcKnobs {
   int slices = 0;          // FENIX_TC_SLICES      force the corpus slice count
   int order = -1;          // FENIX_TC_ORDER       unit order of the one-CTA streaming kernel (1 = query-tile major)
   int kp_list = 0;         // FENIX_TC_KP_LIST     candidates each (query, list) keeps at a selection
-  int pre_wide = 0;        // FENIX_TC_PRE_WIDE    sample prepass also for wide rows at large batches
+  int pre_wide = 1;        // FENIX_TC_PRE_WIDE    sample prepass also for wide rows at large batches (0: off)
   int pre = -1;            // FENIX_TC_PRE         0: no sample prepass
   double pre_safety = 0.0; // FENIX_TC_PRE_SAFETY
   double pre_m = 0.0;      // FENIX_TC_PRE_M
@@ -122,7 +122,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_TC_SLICES") k->slices = as_int(d.slices);
   else if (n == "FENIX_TC_ORDER") k->order = as_int(d.order);
   else if (n == "FENIX_TC_KP_LIST") k->kp_list = as_int(d.kp_list);
-  else if (n == "FENIX_TC_PRE_WIDE") k->pre_wide = as_flag();
+  else if (n == "FENIX_TC_PRE_WIDE") k->pre_wide = as_int(d.pre_wide);
   else if (n == "FENIX_TC_PRE") k->pre = as_int(d.pre);
   else if (n == "FENIX_TC_PRE_SAFETY") k->pre_safety = as_dbl();
   else if (n == "FENIX_TC_PRE_M") k->pre_m = as_dbl();
@@ -1823,9 +1823,13 @@ inline double tc_c_err(int dim, int kind = 0) {
 inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan& main_pl, TcSearch* pre) {
   const TcKnobs& kn = st->knobs;
   if (s.tau_fixed || s.no_prepass || s.sample_stride > 1 || s.kind != 1 || s.dbg != nullptr) return false;
-  // Wide rows: with a large batch the tensor pipe binds and the sample's cost (1/stride of the scan) eats what the
-  // tighter thresholds save (C3: neutral). Small batches are HBM-bound with a lightly loaded tensor pipe, and there
-  // the epilogue's hit path and the finish kernel's candidate volume show: C5 batch 64 +18 %, batch 8 +6 %.
+  // Wide rows: small batches are HBM-bound with a lightly loaded tensor pipe, and there the epilogue's hit path and the
+  // finish kernel's candidate volume show (C5 batch 64 +18 %, batch 8 +6 %). Large batches are tensor-bound and the
+  // sample costs 1/stride of the scan (3 %); on a whole 10M x 768 shard it pays that back and no more (round 1: neutral),
+  // but units get SHORT when the corpus is sharded (1.25M rows per GPU: 132 tiles per unit) and per-list thresholds - each
+  // list keeps its own 32 best, ~2400 admitted rows per query over 74 lists - stay loose for most of a unit: measured on
+  // one 8-GPU shard of C3 the filter kernel takes 6.35 ms without and 5.09 ms with the sample's GLOBAL thresholds
+  // (0.76 -> 0.95 of the burst bf16 peak, profiles/r02_sweep_prepass.txt). On by default; FENIX_TC_PRE_WIDE=0 disables.
   const bool wide = main_pl.n_kblocks > 4;
   if (wide && main_pl.n_qt > 3 && !kn.pre_wide) return false;
   if (s.epi != 2) return false;                            // a row mask (predicate / IVF cells) of unknown selectivity: the

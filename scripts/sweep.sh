@@ -1,15 +1,16 @@
 #!/bin/bash
-# tuning sweep over env knobs / bench configs; usage: scripts/sweep.sh "<bench args>" "ENV=1 ENV2=2" ...   ("-" = no env)
-BARGS=$1; shift
-for e in "$@"; do
-  [ "$e" = "-" ] && e="X=0"
-  OUT=$(env $e timeout 300 python bench.py $BARGS --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | tail -1)
-  python - "$OUT" "$BARGS $e" <<'PY'
-import sys, json
+# usage: scripts/sweep.sh "<bench args>" "ENV=.. ENV2=.." "ENV=.." ...   (one bench run per env set; "-" = no extra env)
+# prints per run: env, ms/step, kernel ms, search ms, QPS, roofline fraction (of burst / sustained), SM clock, parity
+ARGS="$1"; shift
+for E in "$@"; do
+  [ "$E" = "-" ] && E=""
+  OUT=$(env $E python bench.py $ARGS --no-cpu-baseline --no-also 2>/dev/null | tail -1)
+  python - "$E" <<PY
+import json,sys
 try:
-    d = json.loads(sys.argv[1])
-    print(f"{sys.argv[2]:70s} kernel_ms={d['roofline']['kernel_ms']:8.3f} ms_step={d['ms_per_step']:8.3f} qps={d['value']:10.1f} frac={d['roofline']['frac']:.3f} ref={d['config']['refined_queries']} fb={d['config']['fallback_queries']} clk={d['clocks']['sm_mhz']}")
+    d=json.loads('''$OUT'''); r=d["roofline"]
+    print("%-48s ms/step %8.3f kernel %8.3f search %8.3f qps %10.0f e2e %10.0f burst %.3f sust %.3f clk %s %s par=%s ref=%s fb=%s" % (sys.argv[1] or "-", d["ms_per_step"], r["kernel_ms"], r["search_device_ms"], d["value"], d["e2e"]["value"], r.get("frac_of_burst",0), r.get("frac_of_sustained",0), d["clocks"]["sm_mhz"], ",".join(d["clocks"]["reasons"]), d.get("parity",{}).get("ok"), d["details"]["refined_queries"], d["details"]["fallback_queries"]), flush=True)
 except Exception as e:
-    print(sys.argv[2], "FAILED", sys.argv[1][-300:])
+    print(sys.argv[1], "FAILED", e, flush=True)
 PY
 done
