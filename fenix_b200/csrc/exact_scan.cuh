@@ -287,10 +287,12 @@ merge_rank_kernel(const int64_t* __restrict__ rows, const float* __restrict__ di
 // and the largest |x_r|^2 of the shard (error-bound constant), via atomicMax on its bits.
 __global__ void __launch_bounds__(256)
 row_norms_kernel(const float* __restrict__ X, int64_t n_rows, int pitch,
-                 float* __restrict__ hx, float* __restrict__ rx, unsigned int* __restrict__ max_n2_bits) {
+                 float* __restrict__ hx, float* __restrict__ rx, unsigned int* __restrict__ max_n2_bits,
+                 double* __restrict__ norm_sum) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   float local_max = 0.f;
+  double local_sum = 0.0;   // sum of |x| over this warp's rows (mean norm of the shard: how far the norms spread)
   for (int64_t r = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); r < n_rows;
        r += int64_t(gridDim.x) * warps_per_block) {
     const float4* xp = reinterpret_cast<const float4*>(X + size_t(r) * pitch);
@@ -309,9 +311,11 @@ row_norms_kernel(const float* __restrict__ X, int64_t n_rows, int pitch,
       // round |x|^2 UP to fp32 so the bound constant never under-estimates
       float n2 = __double2float_ru(s);
       local_max = fmaxf(local_max, n2);
+      local_sum += n;
     }
   }
   if (lane == 0 && local_max > 0.f) atomicMax(max_n2_bits, __float_as_uint(local_max));
+  if (lane == 0 && local_sum > 0.0) atomicAdd(norm_sum, local_sum);
 }
 
 // Result slots of an empty shard: (row = -1, distance = +inf).

@@ -121,8 +121,9 @@ struct fx_corpus {
   int pitch_b = 0;                 // elements per row of the bf16 QUERY matrix that goes with the shadows (ShadowGeom::pitch_q)
   float* hx = nullptr;
   float* rx = nullptr;
-  unsigned int* max_n2_bits = nullptr;
+  unsigned int* max_n2_bits = nullptr;   // device: [0] bits of max |x|^2, [2..3] double: sum of |x| (16 bytes)
   float max_norm = 0.f;            // max |x| over the shard (host copy, set by finalize)
+  float mean_norm = 0.f;           // mean |x| over the shard: max / mean = how far the norms spread
   bool finalized = false;
   void* ring[2] = {nullptr, nullptr};
   cudaEvent_t ring_ev[2] = {nullptr, nullptr};
@@ -265,7 +266,7 @@ extern "C" int fx_corpus_create(fx_ctx* ctx, int64_t capacity_rows, int32_t dim,
   const size_t norm_alloc = ((rows_alloc + 255) / 256) * 256;
   if (e == cudaSuccess) e = cudaMalloc(&c->hx, norm_alloc * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&c->rx, norm_alloc * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&c->max_n2_bits, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&c->max_n2_bits, 16);
   if (e != cudaSuccess) {
     cudaGetLastError();
     if (c->X) cudaFree(c->X);
@@ -357,18 +358,21 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
   if (c->finalized) return FX_OK;
   FX_TRY(bind(ctx));
   FX_CUDA(cudaStreamSynchronize(ctx->upload));
-  FX_CUDA(cudaMemsetAsync(c->max_n2_bits, 0, sizeof(unsigned int), ctx->stream));
+  FX_CUDA(cudaMemsetAsync(c->max_n2_bits, 0, 16, ctx->stream));
   if (c->n > 0) {
     int blocks = int(std::min<int64_t>((c->n + 7) / 8, int64_t(ctx->sm_count) * 8));
-    fx::row_norms_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->hx, c->rx, c->max_n2_bits);
+    fx::row_norms_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->hx, c->rx, c->max_n2_bits,
+                                                          reinterpret_cast<double*>(c->max_n2_bits + 2));
     FX_CUDA(cudaGetLastError());
     ctx->launches++; c->stats.kernel_launches++;
   }
-  unsigned int bits = 0;
-  FX_CUDA(cudaMemcpyAsync(&bits, c->max_n2_bits, sizeof bits, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned int words[4] = {0, 0, 0, 0};
+  FX_CUDA(cudaMemcpyAsync(words, c->max_n2_bits, sizeof words, cudaMemcpyDeviceToHost, ctx->stream));
   FX_CUDA(cudaStreamSynchronize(ctx->stream));
-  float n2; std::memcpy(&n2, &bits, sizeof n2);
+  float n2; std::memcpy(&n2, &words[0], sizeof n2);
+  double nsum; std::memcpy(&nsum, &words[2], sizeof nsum);
   c->max_norm = std::sqrt(n2) * (1.0f + 1e-6f);
+  c->mean_norm = c->n > 0 ? float(nsum / double(c->n)) : 0.f;
   for (int i = 0; i < 2; ++i) {
     if (c->ring[i]) { cudaFreeHost(c->ring[i]); c->ring[i] = nullptr; cudaEventDestroy(c->ring_ev[i]); c->ring_ev[i] = nullptr; }
   }
@@ -397,8 +401,10 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
       if (c->Xb) {
         const int64_t total = int64_t(shadow_bytes / 4);
         int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
+        // -|x|^2/2 is stored shrunk by the accumulation-rounding allowance (10 % margin for the rounding of the product itself)
+        const float h_scale = float(1.0 - 1.1 * fx::tc_c_add(c->dim, true));
         fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim, c->hx, c->rx, 0,
-                                                                  static_cast<__nv_bfloat16*>(c->Xb), n_kb, n_tiles, g.aug_col, aug_blocks);
+                                                                  static_cast<__nv_bfloat16*>(c->Xb), n_kb, n_tiles, g.aug_col, aug_blocks, h_scale);
         FX_CUDA(cudaGetLastError());
         FX_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->launches++; c->stats.kernel_launches++;
@@ -558,7 +564,7 @@ static bool ensure_norm_shadow(fx_corpus* c) {
   const int64_t total = int64_t(shadow_bytes / 4);
   int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
   fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim, c->hx, c->rx, 1,
-                                                            static_cast<__nv_bfloat16*>(c->Xn), n_kb, n_tiles, 0, 0);
+                                                            static_cast<__nv_bfloat16*>(c->Xn), n_kb, n_tiles, 0, 0, 1.f);
   std::string err;
   if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
       !fx::tc_bind_shadow(&ctx->tc, &c->tc.map_xn, &c->tc.map_xn_h, c->Xn, c->n, n_kb, &err)) {
@@ -579,8 +585,13 @@ static int configure_filter(fx_corpus* c, int metric, int kind, const uint8_t* d
   s->kind = kind; s->pitch_b = c->pitch_b; s->shadow = 0; s->aug = 0; s->epi = metric;
   s->hx = c->hx; s->rx = c->rx; s->Xb = c->Xb; s->Xn = c->Xn;
   if (kind == 1) {
-    if (metric == 0) { s->aug = 1; s->epi = 2; }                       // -|x|^2/2 rides in the shadow's extra columns
+    const int errcol = ctx->tc.knobs.errcol;
+    if (metric == 0) { s->aug = 1; s->epi = 2; }                       // -|x|^2/2 and the row's error weight ride in the shadow's extra columns
     else if (metric == 1) { if (ensure_norm_shadow(c)) { s->shadow = 1; s->epi = 2; s->Xn = c->Xn; } }
+    else if (errcol == 1 || (errcol < 0 && c->max_norm > 1.5f * c->mean_norm)) s->aug = 2;   // inner product over rows whose norms spread:
+                                                                       // per-row error weights instead of c |q| max|x| for every row
+    if (s->aug != 0 && errcol == 0) { s->aug = metric == 0 ? 1 : 0; }
+    s->c_pair = s->aug != 0 ? fx::tc_c_pair(c->dim, s->aug) : 0.0;
   }
   if (d_mask) {
     const int64_t n_alloc = ((c->n + 255) / 256) * 256;
@@ -719,9 +730,10 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
     int64_t* rows2 = reinterpret_cast<int64_t*>(rb + o_rows);
     float* dist2 = reinterpret_cast<float*>(rb + o_dist);
     // gathers the flagged queries (and derives the preset thresholds tier 1 uses)
+    double c_err = 0.0, c_add = 0.0;
+    fx::tc_cert_consts(s, &c_err, &c_add);
     fx::refine_prep_kernel<<<n_f, 128, 0, ctx->stream>>>(d_q, static_cast<const int*>(ctx->d_qlist.p), c->dim, metric, k,
-                                                        d_out_dist, c->max_norm, fx::tc_c_err(c->dim, s.kind),
-                                                        fx::tc_c_add(c->dim, s.kind == 1 && s.aug), q_r, tau_fixed);
+                                                        d_out_dist, c->max_norm, c_err, c_add, q_r, tau_fixed);
     FX_CUDA(cudaGetLastError());
     fx::TcSearch s2 = s;
     s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.certify = true;

@@ -66,10 +66,12 @@ constexpr size_t TC_HDR_BYTES = 256;        // scratch header (word 0: flagged-q
 constexpr int TC_MAX_WAVES = 4;            // units per CTA at most (bounds the candidate-buffer scratch)
 constexpr uint32_t ORD_NEG_INF = 0x007fffffu;  // f2ord(-inf)
 
-// Geometry of a bf16 shadow of a [n][dim] shard (see to_bf16_tiled_kernel). The three -|x|^2/2 columns sit right
-// after the data when the last 64-column k-block has room for them; otherwise (dim % 64 == 0 or > 61) they get
-// one block per tile in a separate region behind the data blocks, so that searches that do not need them (inner
-// product, cosine) stream exactly the data blocks, back to back.
+// Geometry of a bf16 shadow of a [n][dim] shard (see to_bf16_tiled_kernel). The four augmented columns - three terms
+// of -|x|^2/2 and the row's error weight |x| - sit right after the data when the last 64-column k-block has room for
+// them; otherwise (dim % 64 == 0 or > 60) they get one block per tile in a separate region behind the data blocks, so
+// that searches that do not need them (inner product over rows of similar norm, cosine) stream exactly the data
+// blocks, back to back.
+constexpr int TC_AUG_COLS = 4;
 struct ShadowGeom {
   int n_kb_data;     // 64-column k-blocks that hold data, per tile
   int aug_col;       // query / shadow column of the first augmented term (dim, or 64 * n_kb_data when separate)
@@ -80,9 +82,9 @@ inline ShadowGeom shadow_geom(int dim) {
   ShadowGeom g;
   g.n_kb_data = (dim + 63) / 64;
   const int used = dim - 64 * (g.n_kb_data - 1);      // columns of the last data block that hold data
-  g.aug_separate = used + 3 > 64;
+  g.aug_separate = used + TC_AUG_COLS > 64;
   g.aug_col = g.aug_separate ? 64 * g.n_kb_data : dim;
-  g.pitch_q = 64 * ((g.aug_col + 3 + 63) / 64);   // whole 128-byte k-blocks: query tile rows stay 128 B aligned for TMA
+  g.pitch_q = 64 * ((g.aug_col + TC_AUG_COLS + 63) / 64);   // whole 128-byte k-blocks: query tile rows stay 128 B aligned for TMA
   return g;
 }
 
@@ -104,6 +106,8 @@ struct TcKnobs {
   int fin_threads = 0;     // FENIX_FIN_THREADS
   int warm = 0;            // FENIX_TC_WARM        keep thresholds of the previous search (experiments only)
   int pair = -1;           // FENIX_TC_PAIR        CTA-pair streaming kernel: 0 never, 1 whenever possible, -1 auto
+  int errcol = -1;         // FENIX_TC_ERRCOL      certified upper-bound scores (row error weight in the shadow): -1 auto (L2 always,
+                           //                      inner product when the shard's norms spread), 0 never, 1 always
   int fp32_filter_tf32 = 0;// FENIX_FP32_FILTER_TF32  exact mode filters with TF32 over the fp32 rows even when a shadow exists
   int no_refine = 0;       // FENIX_NO_REFINE      flagged queries go straight to the fp64 scan
   int no_norm_shadow = 0;  // FENIX_NO_NORM_SHADOW cosine keeps the plain shadow + multiplicative epilogue
@@ -131,6 +135,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_FIN_THREADS") k->fin_threads = as_int(d.fin_threads);
   else if (n == "FENIX_TC_WARM") k->warm = as_flag();
   else if (n == "FENIX_TC_PAIR") k->pair = as_int(d.pair);
+  else if (n == "FENIX_TC_ERRCOL") k->errcol = as_int(d.errcol);
   else if (n == "FENIX_FP32_FILTER_TF32") k->fp32_filter_tf32 = as_flag();
   else if (n == "FENIX_NO_REFINE") k->no_refine = as_flag();
   else if (n == "FENIX_NO_NORM_SHADOW") k->no_norm_shadow = as_flag();
@@ -142,7 +147,7 @@ inline void tc_knobs_from_env(TcKnobs* k) {
   static const char* const names[] = {
       "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
       "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
-      "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
+      "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
       "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16"};
   for (const char* name : names) {
     if (const char* v = std::getenv(name)) tc_set_knob(k, name, v);
@@ -174,7 +179,10 @@ struct TcSearch {
   int epi;                   // epilogue form: 0 score = acc + hx[row], 1 score = acc * rx[row], 2 score = acc
   int shadow;                // kind 1: 0 = plain shadow (+ augmented columns), 1 = normalised shadow
   const void* Xb; const void* Xn;   // device addresses of the two shadows (L2 prefetch)
-  int aug;                   // kind 1, L2: the query gets three 1.0 columns that pick up the shadow's -|x|^2/2 columns
+  int aug;                   // kind 1: the query's augmented columns. 1 (L2): [1, 1, 1, u] pick up the shadow's -|x|^2/2 terms
+                             // and the row's error weight; 2 (inner product, rows of very different norm): [0, 0, 0, u];
+                             // u = c |q| rounded up, so that the filter score is a certified UPPER bound of the exact score
+  double c_pair;             // aug != 0: the constant c of u = c |q| (product rounding + accumulation, see tc_c_err / tc_c_add)
   int sample_stride;         // > 1: threshold prepass over every sample_stride-th corpus tile (set by tc_search)
   int pre_m;                 // prepass: rank of the sample's block maximum that becomes the query's initial threshold
   int no_prepass;            // 1: adaptive thresholds only (re-run of queries the sample threshold failed)
@@ -1108,10 +1116,24 @@ knn_rq_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // ---------------------------------------------------------------------------------------------
 // query preparation: pad to the TMA pitch, reset per-query state
 // ---------------------------------------------------------------------------------------------
+// Error weight of every query for the certified upper-bound scores: qerr[q] = c |q| (fp64 norm, rounded up to fp32 with
+// a 2^-10 relative margin that also covers the bf16 round-up of the two factors being applied AFTER this product bound).
+__global__ void __launch_bounds__(128)
+knn_qerr_kernel(const float* __restrict__ Q, int n_q, int dim, double c, float* __restrict__ qerr) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_q) return;
+  double s = 0.0;
+  for (int d = lane; d < dim; d += 32) { const double v = double(Q[size_t(warp) * dim + d]); s = fma(v, v, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) qerr[warp] = __double2float_ru(c * sqrt(s) * (1.0 + 1.0 / 1024.0));
+}
+
 __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int n_rows_p, int dim, int pitch, float* __restrict__ Qp,
                                 uint32_t* __restrict__ tau_g, int* __restrict__ flags,
                                 __nv_bfloat16* __restrict__ Qb, int pitch_b,
-                                const uint32_t* __restrict__ tau_fixed, int keep_tau, int aug_col, int* __restrict__ n_flagged) {
+                                const uint32_t* __restrict__ tau_fixed, int keep_tau, int aug_col, int* __restrict__ n_flagged,
+                                int aug_mode, const float* __restrict__ qerr) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_flagged = 0;
   // Rows are written in TILE order: row qt*128 + j holds query qt*128 + (j % 32) * 4 + j / 32 (zeros past the last
   // query), so that consecutive queries land in different TMEM lane groups.
@@ -1130,7 +1152,11 @@ __global__ void knn_prep_kernel(const float* __restrict__ Q, int n_q, int n_rows
       int j = row % TC_BM;
       int q = row - j + (j % 32) * 4 + j / 32;
       float v = (d < dim && q < n_q) ? Q[size_t(q) * dim + d] : 0.f;
-      if (aug_col > 0 && q < n_q && d >= aug_col && d < aug_col + 3) v = 1.f;   // picks up the shadow's three -|x|^2/2 columns
+      if (aug_col > 0 && q < n_q && d >= aug_col && d < aug_col + 3 && aug_mode == 1) v = 1.f;   // picks up the shadow's three -|x|^2/2 columns
+      if (aug_col > 0 && q < n_q && d == aug_col + 3) {
+        Qb[i] = __float2bfloat16_ru(qerr[q]);            // u = c |q|, rounded UP (times the row's |x|, also rounded up)
+        continue;
+      }
       Qb[i] = __float2bfloat16_rn(v);
     }
   }
@@ -1527,7 +1553,8 @@ __global__ void masked_norms_kernel(const uint8_t* __restrict__ mask, const floa
 //   mode 1 (normalised): columns [0, dim) = x / max(|x|, eps): cosine scores straight out of the MMA.
 __global__ void to_bf16_tiled_kernel(const float* __restrict__ X, int64_t n_rows, int pitch, int dim,
                                      const float* __restrict__ hx, const float* __restrict__ rx, int mode,
-                                     __nv_bfloat16* __restrict__ Xb, int n_kb, int64_t n_tiles, int aug_col, int aug_blocks) {
+                                     __nv_bfloat16* __restrict__ Xb, int n_kb, int64_t n_tiles, int aug_col, int aug_blocks,
+                                     float h_scale) {
   const int64_t total = n_tiles * (n_kb + aug_blocks) * int64_t(TC_BN) * 32;   // bf16 pairs
   const int64_t main_pairs = n_tiles * n_kb * int64_t(TC_BN) * 32;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -1541,6 +1568,7 @@ __global__ void to_bf16_tiled_kernel(const float* __restrict__ X, int64_t n_rows
     const int64_t r = (in_aug ? blk : blk / n_kb) * TC_BN + rr;
     const int d = kb * 64 + dd;
     float ab[2] = {0.f, 0.f};
+    bool up[2] = {false, false};
     if (r < n_rows) {
       const float scale = mode == 1 ? rx[r] : 1.f;
 #pragma unroll
@@ -1548,14 +1576,25 @@ __global__ void to_bf16_tiled_kernel(const float* __restrict__ X, int64_t n_rows
         const int de = d + e;
         if (de < dim) ab[e] = X[size_t(r) * pitch + de] * scale;
         else if (mode == 0 && de >= aug_col && de < aug_col + 3) {
-          const float h = hx[r];
+          // -|x|^2/2, shrunk by the accumulation-rounding allowance (h_scale = 1 - c_add: the score errs upwards),
+          // as three bf16 terms that reproduce the fp32 value exactly
+          const float h = hx[r] * h_scale;
           const float hi = __bfloat162float(__float2bfloat16_rn(h));
           const float mid = __bfloat162float(__float2bfloat16_rn(h - hi));
           ab[e] = de == aug_col ? hi : (de == aug_col + 1 ? mid : (h - hi) - mid);
+        } else if (mode == 0 && de == aug_col + 3) {
+          // the row's error weight |x|, rounded up (hx = -|x|^2/2 is an fp32 rounding of the fp64 sum)
+          const float nx = sqrtf(-2.f * hx[r]) * (1.f + 1.f / 4096.f);
+          reinterpret_cast<__nv_bfloat16*>(Xb)[2 * i + e] = __float2bfloat16_ru(nx);
+          up[e] = true;
         }
       }
     }
-    reinterpret_cast<__nv_bfloat162*>(Xb)[i] = __floats2bfloat162_rn(ab[0], ab[1]);
+    if (!up[0] && !up[1]) reinterpret_cast<__nv_bfloat162*>(Xb)[i] = __floats2bfloat162_rn(ab[0], ab[1]);
+    else {
+      if (!up[0]) Xb[2 * i] = __float2bfloat16_rn(ab[0]);
+      if (!up[1]) Xb[2 * i + 1] = __float2bfloat16_rn(ab[1]);
+    }
   }
 }
 
@@ -1667,7 +1706,7 @@ struct TcPlan {
   int n_qt_lists;// query tiles the candidate-list layout is indexed with (2 n_qp for the pair kernel, else n_qt)
   int n_qp;      // query pairs
   int kp_list;   // candidates each (query, list) keeps at a selection (<= kp)
-  size_t off_qp, off_qb, off_tau, off_flags, off_wcnt, off_wbuf, off_pre, total;
+  size_t off_qp, off_qb, off_tau, off_flags, off_qerr, off_wcnt, off_wbuf, off_pre, total;
   int n_rec, pre_pitch;   // threshold prepass: block-maximum records per query (= row pitch of the record matrix)
 };
 
@@ -1690,7 +1729,7 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   } else {
     const ShadowGeom g = shadow_geom(s.dim);
     pl.n_kb_data = g.n_kb_data;
-    const int used = s.dim - 64 * (g.n_kb_data - 1) + ((s.aug && !g.aug_separate) ? 3 : 0);
+    const int used = s.dim - 64 * (g.n_kb_data - 1) + ((s.aug && !g.aug_separate) ? TC_AUG_COLS : 0);
     pl.nk_last = (used + 15) / 16;
     pl.n_kblocks = g.n_kb_data + ((s.aug && g.aug_separate) ? 1 : 0);
     pl.aug_line0 = pl.n_tiles * g.n_kb_data * TC_BN;
@@ -1764,6 +1803,7 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.off_qb = take(s.kind == 1 ? q_rows_p * s.pitch_b * 2 : 0);
   pl.off_tau = take(size_t(s.n_q) * 4);
   pl.off_flags = take(size_t(s.n_q) * 4);
+  pl.off_qerr = take(size_t(s.n_q) * 4);
   pl.n_rec = pl.n_vtiles * (pl.rq ? 1 : TC_SPLIT);
   pl.pre_pitch = pl.n_rec;
   if (pre) {
@@ -1809,10 +1849,25 @@ inline const int* tc_flag_count(void* scratch) { return static_cast<const int*>(
 // bf16 operands are rounded to nearest (2^-9 each -> 2^-8 on the product, 10% margin).
 // L2 only: rounding of the -|x|^2/2 term and of its addition, relative to |x|^2/2 + |q||x|. When the term rides
 // through the MMA (augmented shadow) every one of the tile's accumulation steps may round it again.
-inline double tc_c_add(int dim, bool aug) { return 4.8e-7 + (aug ? double((dim + 3 + 15) / 16) * 1.2e-7 : 0.0); }
+inline double tc_c_add(int dim, bool aug) { return 4.8e-7 + (aug ? double((dim + TC_AUG_COLS + 15) / 16) * 1.2e-7 : 0.0); }
 inline double tc_c_err(int dim, int kind = 0) {
   const double prod = kind == 0 ? 1.25 * std::ldexp(1.0, -9) : 1.10 * std::ldexp(1.0, -8);
   return prod + double(dim) * std::ldexp(1.0, -21);
+}
+
+// Error constants the certificate and the refinement thresholds use. With augmented queries (TcSearch::aug) the filter
+// score already carries c |q| |x| per row plus the folded |x|^2/2 allowance - it IS an upper bound of the exact score -
+// so nothing is added on top and the certificate no longer depends on the largest norm of the shard: one 100x-norm
+// outlier (or clustered rows far from the origin) inflates only its own row's score.
+inline void tc_cert_consts(const TcSearch& s, double* c_err, double* c_add) {
+  if (s.kind == 1 && s.aug != 0) { *c_err = 0.0; *c_add = 0.0; return; }
+  *c_err = tc_c_err(s.dim, s.kind);
+  *c_add = tc_c_add(s.dim, false);
+}
+// c of the query's error weight u = c |q| (augmented queries): product rounding + fp32 accumulation over the data and
+// augmented columns, plus (L2) the |q||x| share of the accumulation-rounding allowance
+inline double tc_c_pair(int dim, int aug) {
+  return tc_c_err(dim + TC_AUG_COLS + 4, 1) + (aug == 1 ? tc_c_add(dim, true) : 0.0);
 }
 
 // Threshold prepass (narrow rows, where the epilogue - not the tensor pipe - binds): the same filter kernel runs over
@@ -1955,7 +2010,7 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   f.n_slices = pl.n_slices; f.cap = pl.cap; f.metric = s.metric; f.k = s.k; f.kp = pl.kp;
   int sort2 = 2; while (sort2 < pl.kp) sort2 <<= 1;
   f.sort2 = sort2; f.tau_g = tau_g; f.wbuf = wbuf; f.wcnt = wcnt; f.qt_major = pl.qt_major; f.rq = pl.rq; f.n_qp = pl.n_qp; f.flags = flags; f.certify = s.certify ? 1 : 0;
-  f.max_norm = s.max_norm; f.c_err = tc_c_err(s.dim, s.kind); f.c_add = tc_c_add(s.dim, s.kind == 1 && s.aug); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
+  f.max_norm = s.max_norm; tc_cert_consts(s, &f.c_err, &f.c_add); f.out_rows = s.out_rows; f.out_dist = s.out_dist;
   const size_t fin_smem = size_t(sort2) * 12 + size_t(s.pitch) * 4 + size_t(FIN_POOL) * 8 + 16;
   // many short lists per query (small batches split over all SMs): more warps sweep them in parallel
   int fin_threads = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices > 32 ? 1024 : 256;
@@ -1985,10 +2040,16 @@ inline bool tc_search(TcState* st, TcCorpus* tc, const TcSearch& s, const TcLaun
 
   const int n_rows_p = pl.n_qp * 2 * TC_BM;
   const int prep_blocks = int(std::min<int64_t>((int64_t(n_rows_p) * s.pitch + 255) / 256, 4 * 148));
+  float* qerr = reinterpret_cast<float*>(base + pl.off_qerr);
+  const bool aug = s.kind == 1 && s.aug != 0;
+  *launched = 3;
+  if (aug) {
+    knn_qerr_kernel<<<(s.n_q + 3) / 4, 128, 0, s.stream>>>(s.Q, s.n_q, s.dim, s.c_pair, qerr);
+    *launched += 1;
+  }
   knn_prep_kernel<<<std::max(prep_blocks, 1), 256, 0, s.stream>>>(s.Q, s.n_q, n_rows_p, s.dim, s.pitch, qp, tau_g, flags, qb, s.pitch_b, s.tau_fixed,
                                                                   (!s.tau_fixed && st->knobs.warm) ? 1 : 0,
-                                                                  (s.kind == 1 && s.aug) ? pl.aug_col : 0, reinterpret_cast<int*>(base));
-  *launched = 3;
+                                                                  aug ? pl.aug_col : 0, reinterpret_cast<int*>(base), s.aug, qerr);
   // threshold prepass over a strided sample (the padded queries and tau_g sit at the same scratch offsets in both plans)
   if (variant) *variant = (pl.rq ? 1 : 0) | (L.with_pre ? 2 : 0) | (pl.pair ? 4 : 0);
   if (L.with_pre) {

@@ -332,6 +332,37 @@ def test_group_search_in_one_process(built_library):
     group.close()
 
 
+@pytest.mark.parametrize("metric", ["l2", "dot"])
+def test_norm_outliers_do_not_defeat_the_certificate(ctx, metric):
+    """0.1 % of the rows carry 100x the norm. The filter score of a row is a certified UPPER bound of its exact score (the
+    row's own error weight rides in the shadow), so the certificate does not depend on the largest norm of the shard:
+    no query falls back to the fp64 scan, and the result still equals it."""
+    import torch
+
+    n, d, nq, k = 300_000, 128, 700, 100
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn((n, d), generator=g, device="cuda", dtype=torch.float32)
+    x[torch.arange(3, n, 1000, device="cuda")] *= 100.0
+    q = torch.randn((nq, d), generator=g, device="cuda", dtype=torch.float32)
+    c = knn.Corpus(ctx, n, d)
+    torch.cuda.synchronize()
+    c.append_device(x.data_ptr(), n)
+    c.finalize()
+    qh = q.cpu().numpy()
+    before = c.stats()
+    rows, dist = c.search(qh, metric, k)
+    after = c.stats()
+    assert after.last_path == 2
+    assert after.fallback_queries == before.fallback_queries, "the certificate should hold without the scan"
+    assert after.refined_queries - before.refined_queries <= nq // 50
+    sub = np.arange(0, nq, 23)
+    rows_s, dist_s = c.search(qh[sub], metric, k, knn.PREC_EXACT_SCAN)
+    assert np.array_equal(rows[sub], rows_s) and np.array_equal(dist[sub], dist_s)
+    if metric == "dot":   # the outliers ARE the nearest neighbours under inner product (100x the dot product)
+        assert (rows[:, 0] % 1000 == 3).all()
+    c.close()
+
+
 def test_large_property_checks(ctx):
     """BASELINE-sized shape (1M x 128, k = 100): size-independent properties instead of the oracle:
     planted neighbours are found, results are sorted by (distance, row), sharding is invariant,
@@ -406,7 +437,7 @@ def test_resident_query_kernel_and_sample_prepass(ctx, metric, dim, k):
     c.close()
 
 
-@pytest.mark.parametrize("dim", [61, 62, 64, 65, 125, 128, 189, 190, 256])
+@pytest.mark.parametrize("dim", [60, 61, 62, 64, 65, 124, 125, 128, 188, 189, 190, 256])
 def test_shadow_geometry_boundaries(ctx, dim):
     """The bf16 shadow keeps -|x|^2/2 in three extra K columns: inside the last 64-column block when it has room
     (dim % 64 <= 61), in a separate block per tile otherwise; rows of up to 3 blocks take the resident-query kernel.
