@@ -563,7 +563,7 @@ def run_ours(args, cfg: dict) -> dict:
     by_queries = par == "queries" and world > 1
     lo, hi = (0, cfg["n"]) if by_queries else shard_bounds(cfg["n"], world, rank)
     t_build = time.perf_counter()
-    corpus = build_shard(cfg, ctx, lo, hi, device)
+    corpus = build_shard(cfg, ctx, lo, hi, device, args.variant)
     t_build = time.perf_counter() - t_build
     searcher = ReplicaSearcher(corpus) if by_queries else ShardedSearcher(corpus)
     metric, k, n_q, d = knn.metric_code(cfg["metric"]), cfg["k"], cfg["q"], cfg["d"]
@@ -651,7 +651,8 @@ def run_ours(args, cfg: dict) -> dict:
             tq = torch.from_numpy(qs).to(device)
             r, dd = searcher.search_device(tq, metric, k, knn.PREC_EXACT_SCAN)
             return r.cpu().numpy(), dd.cpu().numpy()
-        parity = parity_block(cfg, scan, rows_h, dist_h, h_q.numpy(), device, rank)
+        parity = parity_block(cfg, scan, rows_h, dist_h, h_q.numpy(), device, rank, variant=args.variant,
+                              max_norm2={"clustered": 130.0 * d, "norm_outliers": 1.3e4 * d}.get(args.variant))
 
     out = None
     if rank == 0:
@@ -744,14 +745,16 @@ def main() -> None:
     ap.add_argument("--parallelism", default="auto", choices=["auto", "rows", "queries"],
                     help="N > 1: row-shard the corpus, or replicate it and split the query batch (auto: replicate when the "
                          "corpus and its shadows take <= 8 GB and every rank still gets >= 256 queries)")
+    ap.add_argument("--variant", default=None, choices=[v for v in STRESS if v != "queries_from_corpus"],
+                    help="tuning only: a stress variant of the synthetic corpus (SURVEY.md section 8d)")
     ap.add_argument("--rows", type=int, default=0, help="tuning only: override the corpus row count of the config")
     ap.add_argument("--queries", type=int, default=0, help="tuning only: override the query batch of the config")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
-    if args.rows or args.queries:
+    if args.rows or args.queries or args.variant:
         cfg["n"] = args.rows or cfg["n"]
         cfg["q"] = args.queries or cfg["q"]
-        cfg["label"] += f" [TUNING OVERRIDE rows={cfg['n']} queries={cfg['q']}: not a benchmark configuration]"
+        cfg["label"] += f" [TUNING OVERRIDE rows={cfg['n']} queries={cfg['q']} variant={args.variant}: not a benchmark configuration]"
     out = run_reference(args, cfg) if args.impl == "reference" else run_ours(args, cfg)
     if out is not None:
         print(json.dumps(out), flush=True)

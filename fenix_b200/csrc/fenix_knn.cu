@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
@@ -705,13 +706,19 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
   FX_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<int> bad, starved;
   for (int64_t i = 0; i < n_q; ++i) { if (h_flags[i] == 2) starved.push_back(int(i)); else if (h_flags[i]) bad.push_back(int(i)); }
+  const bool trace = ctx->tc.knobs.debug_tiers != 0;
+  auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_mark = now_ms();
+  if (trace) fprintf(stderr, "[fenix tiers] main pass: %zu certificate failures, %zu starved (of %lld queries, prepass %d)\n",
+                     bad.size(), starved.size(), (long long)n_q, int(run->L.with_pre));
   // Flagged queries are settled by up to two more filter passes over their own (small) batch:
-  //  tier 0 (only when the main pass took its thresholds from the sample prepass): the adaptive search without
-  //         prepass - a sample threshold that came out too tight leaves a query with fewer than k candidates,
-  //         and then there is no k-th distance to refine from;
+  //  tier 0 (queries left with fewer than k candidates): the adaptive search without prepass and with FULL candidate lists
+  //         (K' entries each). Two things starve a query: a sample threshold that came out too tight, and neighbours
+  //         concentrated in one candidate list (clustered rows in row order) when the lists keep fewer than k entries;
+  //         either way there is no k-th distance to refine from;
   //  tier 1: preset-threshold refinement: the admission threshold is the query's k-th distance minus the error
   //         bound and every survivor is reranked, so the result is exact.
-  if (!run->L.with_pre) { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }
+
   for (int tier = starved.empty() ? 1 : 0; tier <= 1 && !ctx->tc.knobs.no_refine; ++tier) {
     if (tier == 0) bad.swap(starved);                                    // tier 0 takes the starved queries only ...
     else { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }   // ... what it leaves flagged joins tier 1
@@ -737,7 +744,7 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
     FX_CUDA(cudaGetLastError());
     fx::TcSearch s2 = s;
     s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.certify = true;
-    s2.tau_fixed = tier == 1 ? tau_fixed : nullptr; s2.no_prepass = 1;
+    s2.tau_fixed = tier == 1 ? tau_fixed : nullptr; s2.no_prepass = 1; s2.full_lists = tier == 0 ? 1 : 0;
     s2.ev_k0 = nullptr; s2.ev_k1 = nullptr;   // keep the timing of the main pass
     const fx::TcLaunch L2 = fx::tc_prepare(&ctx->tc, s2);
     FX_TRY(ctx->d_tc.ensure(L2.scratch_bytes));
@@ -755,16 +762,34 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
     std::vector<int> still;
     for (int i = 0; i < n_f; ++i) if (h_flags[i]) still.push_back(bad[i]);
     c->stats.refined_queries += int64_t(n_f - int(still.size()));
+    if (trace) { const double t = now_ms(); fprintf(stderr, "[fenix tiers] tier %d: %d queries in, %zu still flagged, %.3f ms\n", tier, n_f, still.size(), t - t_mark); t_mark = t; }
     bad.swap(still);
   }
   if (!bad.empty()) {
     // tier 2: the certificate-free fp64 scan
+    std::vector<int64_t> before_rows; std::vector<float> before_dist;
+    if (trace) {   // what the tiers had for the first still-flagged query, to compare with the scan's answer
+      before_rows.resize(k); before_dist.resize(k);
+      cudaMemcpy(before_rows.data(), d_out_rows + size_t(bad[0]) * k, size_t(k) * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(before_dist.data(), d_out_dist + size_t(bad[0]) * k, size_t(k) * 4, cudaMemcpyDeviceToHost);
+    }
     FX_TRY(ctx->d_qlist.ensure(bad.size() * sizeof(int)));
     FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), bad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     FX_TRY(run_exact_scan(c, d_q, int(n_q), static_cast<int*>(ctx->d_qlist.p), int(bad.size()), metric, k,
                           run->d_mask, d_out_rows, d_out_dist));
     FX_CUDA(cudaStreamSynchronize(ctx->stream));  // `bad` must outlive the H2D copy
+    if (trace) {
+      std::vector<int64_t> after_rows(k); std::vector<float> after_dist(k);
+      cudaMemcpy(after_rows.data(), d_out_rows + size_t(bad[0]) * k, size_t(k) * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(after_dist.data(), d_out_dist + size_t(bad[0]) * k, size_t(k) * 4, cudaMemcpyDeviceToHost);
+      int differ = 0;
+      for (int i = 0; i < k; ++i) differ += before_rows[i] != after_rows[i];
+      fprintf(stderr, "[fenix tiers] query %d: tiers vs scan: %d of %d ranks differ; tiers d[0]=%.7g d[k-1]=%.7g rows %lld..%lld | scan d[0]=%.7g d[k-1]=%.7g rows %lld..%lld\n",
+              bad[0], differ, k, before_dist[0], before_dist[k - 1], (long long)before_rows[0], (long long)before_rows[k - 1],
+              after_dist[0], after_dist[k - 1], (long long)after_rows[0], (long long)after_rows[k - 1]);
+    }
     c->stats.fallback_queries += int64_t(bad.size());
+    if (trace) fprintf(stderr, "[fenix tiers] tier 2 (fp64 scan): %zu queries, %.3f ms\n", bad.size(), now_ms() - t_mark);
   }
   FX_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));   // the search now ends here
   return FX_OK;

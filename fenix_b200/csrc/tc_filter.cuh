@@ -112,6 +112,7 @@ struct TcKnobs {
   int no_refine = 0;       // FENIX_NO_REFINE      flagged queries go straight to the fp64 scan
   int no_norm_shadow = 0;  // FENIX_NO_NORM_SHADOW cosine keeps the plain shadow + multiplicative epilogue
   int debug_bf16 = 0;      // FENIX_DEBUG_BF16     fx_debug_scores dumps the bf16 filter's scores
+  int debug_tiers = 0;     // FENIX_DEBUG_TIERS    stderr trace of the certificate-failure tiers (counts, host-clock times)
 };
 // name = the environment variable's name; value = its text, or null to restore the default. False: unknown name.
 inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
@@ -140,6 +141,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_NO_REFINE") k->no_refine = as_flag();
   else if (n == "FENIX_NO_NORM_SHADOW") k->no_norm_shadow = as_flag();
   else if (n == "FENIX_DEBUG_BF16") k->debug_bf16 = as_flag();
+  else if (n == "FENIX_DEBUG_TIERS") k->debug_tiers = as_flag();
   else return false;
   return true;
 }
@@ -148,7 +150,7 @@ inline void tc_knobs_from_env(TcKnobs* k) {
       "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
       "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
       "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
-      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16"};
+      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS"};
   for (const char* name : names) {
     if (const char* v = std::getenv(name)) tc_set_knob(k, name, v);
   }
@@ -186,6 +188,8 @@ struct TcSearch {
   int sample_stride;         // > 1: threshold prepass over every sample_stride-th corpus tile (set by tc_search)
   int pre_m;                 // prepass: rank of the sample's block maximum that becomes the query's initial threshold
   int no_prepass;            // 1: adaptive thresholds only (re-run of queries the sample threshold failed)
+  int full_lists;            // 1: every candidate list keeps K' entries (re-run of starved queries: when a query's neighbours sit in
+                             // ONE list - clustered rows in row order - a list that keeps fewer than k can never supply them)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1789,8 +1793,8 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     const int lists = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices;
     int m = std::max(32, (2 * s.k + lists - 1) / lists + 16);
     m = (m + 31) & ~31;
-    pl.kp_list = (s.tau_fixed || pre) ? pl.kp : std::min(pl.kp, m);   // prepass: every list keeps the m best it sees
-    if (!pre && kn.kp_list >= 32) pl.kp_list = std::min(pl.kp, (kn.kp_list + 31) & ~31);
+    pl.kp_list = (s.tau_fixed || pre || s.full_lists) ? pl.kp : std::min(pl.kp, m);   // prepass: every list keeps the m best it sees
+    if (!pre && !s.full_lists && kn.kp_list >= 32) pl.kp_list = std::min(pl.kp, (kn.kp_list + 31) & ~31);
     pl.cap = (s.tau_fixed || pre) ? pl.cap : tc_cap(pl.kp_list);
   }
   pl.grid = int(std::min<long>(pl.units, sms)) * (pl.pair ? 2 : 1);

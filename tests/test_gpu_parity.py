@@ -439,8 +439,9 @@ def test_resident_query_kernel_and_sample_prepass(ctx, metric, dim, k):
 
 @pytest.mark.parametrize("dim", [60, 61, 62, 64, 65, 124, 125, 128, 188, 189, 190, 256])
 def test_shadow_geometry_boundaries(ctx, dim):
-    """The bf16 shadow keeps -|x|^2/2 in three extra K columns: inside the last 64-column block when it has room
-    (dim % 64 <= 61), in a separate block per tile otherwise; rows of up to 3 blocks take the resident-query kernel.
+    """The bf16 shadow keeps -|x|^2/2 (three terms) and the row's error weight in four extra K columns: inside the last
+    64-column block when it has room (dim % 64 <= 60), in a separate block per tile otherwise; rows of up to 3 blocks
+    take the resident-query kernel.
     Every metric, both kernels (a 300-query and a 40-query batch), against the fp64 scan."""
     import torch
 
