@@ -5,6 +5,7 @@
 // scan, merges, row norms) and tc_filter.cuh (tcgen05/TMEM filter kernels, prepass, finish + rerank).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <dlfcn.h>
 
@@ -57,6 +58,12 @@ static int fail(int code, const char* fmt, ...) {
     if (_r != FX_OK) return _r;   \
   } while (0)
 
+// NVTX ranges (header-only NVTX 3; no-ops unless a profiler is attached): upload, shadow build, search, exchange.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 // ----------------------------------------------------------------------------------------
 // objects
 // ----------------------------------------------------------------------------------------
@@ -106,6 +113,8 @@ struct fx_ctx {
   int* h_word = nullptr;           // pinned: [0] flagged-query count of the last main pass, [1..] gathered per-rank counts
   int64_t launches = 0;
   fx::TcState tc;                  // driver entry points / kernel attributes / tuning knobs of the TC path
+  bool capturing = false;          // the search being enqueued is captured into a CUDA graph (events become external nodes)
+  uint64_t knob_epoch = 0;         // bumped by fx_set_option: captured graphs bake the plan in
 };
 constexpr int H_WORDS = 64;
 
@@ -119,6 +128,8 @@ struct fx_corpus {
   void* Xb = nullptr;              // bf16 shadow of X (+ three -|x|^2/2 columns) for the bf16 filter, tiled (tc_filter.cuh)
   void* Xn = nullptr;              // bf16 shadow of the normalised rows (cosine), built by the first cosine search
   bool xn_failed = false;          // no memory for Xn: cosine keeps the plain shadow + multiplicative epilogue
+  bool xb_failed = false;          // no memory for Xb: the TF32 filter over the fp32 rows serves L2 / inner product
+  int shadow_mode = -1;            // FENIX_BF16_SHADOW at finalize: -1 lazy (default), 0 never, 1 plain shadow built at finalize
   int pitch_b = 0;                 // elements per row of the bf16 QUERY matrix that goes with the shadows (ShadowGeom::pitch_q)
   float* hx = nullptr;
   float* rx = nullptr;
@@ -131,6 +142,15 @@ struct fx_corpus {
   int ring_next = 0;
   fx_stats stats{};
   fx::TcCorpus tc;                 // tensor map of the shard for the TC path
+  struct GraphEntry {              // a small search captured as one CUDA graph (H2D, kernels, D2H), replayed from its second call on
+    int64_t n_q = 0; int metric = 0, k = 0, precision = 0;
+    int state = 0;                 // 0 new, 2 seen once (the next identical call captures), 1 ready, -1 capture failed (never again)
+    cudaGraphExec_t exec = nullptr;
+    void* ptrs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // buffers baked into the graph
+    uint64_t knob_epoch = 0;
+    int path = 0, variant = 0, launches = 0;
+  };
+  std::vector<GraphEntry> graphs;
 };
 
 static int bind(fx_ctx* ctx) {
@@ -294,6 +314,7 @@ extern "C" int fx_set_option(fx_ctx* ctx, const char* name, const char* value) {
   if (!ctx || !name) return fail(FX_EINVAL, "fx_set_option: NULL argument");
   std::lock_guard<std::mutex> lock(ctx->mu);
   if (!fx::tc_set_knob(&ctx->tc.knobs, name, value)) return fail(FX_EINVAL, "fx_set_option: unknown option '%s'", name);
+  ctx->knob_epoch++;
   return FX_OK;
 }
 
@@ -309,6 +330,7 @@ static int ensure_ring(fx_corpus* c) {
 
 static int append_impl(fx_corpus* c, const void* rows, int64_t n_rows, bool on_device) {
   FX_LEASE(c, "fx_corpus_append");
+  NvtxRange nvtx("fenix:corpus_append");
   if (n_rows < 0) return fail(FX_EINVAL, "fx_corpus_append: negative row count");
   if (n_rows == 0) return FX_OK;
   if (!rows) return fail(FX_EINVAL, "fx_corpus_append: rows is NULL");
@@ -352,8 +374,11 @@ extern "C" int fx_corpus_append_device(fx_corpus* c, const void* device_rows, in
   return append_impl(c, device_rows, n_rows, true);
 }
 
+static bool ensure_plain_shadow(fx_corpus* c);
+
 extern "C" int fx_corpus_finalize(fx_corpus* c) {
   FX_LEASE(c, "fx_corpus_finalize");
+  NvtxRange nvtx("fenix:corpus_finalize");
   fx_ctx* ctx = c->ctx;
   std::lock_guard<std::mutex> lock(ctx->mu);
   if (c->finalized) return FX_OK;
@@ -377,50 +402,27 @@ extern "C" int fx_corpus_finalize(fx_corpus* c) {
   for (int i = 0; i < 2; ++i) {
     if (c->ring[i]) { cudaFreeHost(c->ring[i]); c->ring[i] = nullptr; cudaEventDestroy(c->ring_ev[i]); c->ring_ev[i] = nullptr; }
   }
-  // bf16 shadow (tiled for streaming, see tc_filter.cuh): the exact (fp32) mode then filters with 2x-rate bf16
-  // MMAs and half the operand bytes - measured gains: C3 (D=768) 95 -> 49 ms, one C4 shard (D=96) 49 -> 39 ms.
-  // Built by default whenever it fits comfortably (costs +50 % HBM per shard); FENIX_BF16_SHADOW=0 disables,
-  // =1 forces it.
+  // bf16 shadows (tiled for streaming, see tc_filter.cuh): the exact (fp32) mode filters with 2x-rate bf16 MMAs and half
+  // the operand bytes - measured gains: C3 (D=768) 95 -> 49 ms, one C4 shard (D=96) 49 -> 39 ms. Each of the two shadows
+  // costs +50 % HBM per shard and only ONE is read by any given metric (plain + augmented columns: L2 / inner product;
+  // normalised rows: cosine), so each is built by the first search that streams it (ensure_plain_shadow /
+  // ensure_norm_shadow) - a table searched with one metric holds fp32 rows + one shadow. FENIX_BF16_SHADOW=0: never
+  // build one (TF32 filter over the fp32 rows); =1: build the plain shadow here, at finalize.
   {
+    const fx::ShadowGeom g = fx::shadow_geom(c->dim);
+    c->pitch_b = g.pitch_q;
     const char* e = std::getenv("FENIX_BF16_SHADOW");
-    bool want = e ? std::atoi(e) != 0 : c->dim >= 16;
-    if (want && !e) {
-      size_t free_b = 0, total_b = 0;
-      const fx::ShadowGeom g0 = fx::shadow_geom(c->dim);
-      const size_t need = size_t((c->n + 255) / 256) * size_t(g0.n_kb_data + (g0.aug_separate ? 1 : 0)) * 256 * 64 * 2;
-      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < need + (size_t(4) << 30)) want = false;
-      cudaGetLastError();
-    }
-    if (want && c->n >= 4096) {
-      const fx::ShadowGeom g = fx::shadow_geom(c->dim);
-      c->pitch_b = g.pitch_q;
-      const int n_kb = g.n_kb_data, aug_blocks = g.aug_separate ? 1 : 0;
-      const int64_t n_tiles = (c->n + fx::TC_BN - 1) / fx::TC_BN;
-      const size_t shadow_bytes = size_t(n_tiles) * (n_kb + aug_blocks) * fx::TC_BN * 64 * 2;
-      cudaError_t me = cudaMalloc(&c->Xb, shadow_bytes);
-      if (me != cudaSuccess) { cudaGetLastError(); c->Xb = nullptr; }   // not fatal: the TF32 filter needs no shadow
-      if (c->Xb) {
-        const int64_t total = int64_t(shadow_bytes / 4);
-        int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
-        // -|x|^2/2 is stored shrunk by the accumulation-rounding allowance (10 % margin for the rounding of the product itself)
-        const float h_scale = float(1.0 - 1.1 * fx::tc_c_add(c->dim, true));
-        fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim, c->hx, c->rx, 0,
-                                                                  static_cast<__nv_bfloat16*>(c->Xb), n_kb, n_tiles, g.aug_col, aug_blocks, h_scale);
-        FX_CUDA(cudaGetLastError());
-        FX_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->launches++; c->stats.kernel_launches++;
-        c->stats.device_bytes += int64_t(shadow_bytes);
-      }
-    }
+    c->shadow_mode = e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
   }
   {
     std::string err;
     const fx::ShadowGeom g = fx::shadow_geom(c->dim);
-    if (!fx::tc_bind_corpus(&ctx->tc, &c->tc, c->X, c->n, c->dim, c->pitch, c->Xb, g.n_kb_data + (g.aug_separate ? 1 : 0), &err))
+    if (!fx::tc_bind_corpus(&ctx->tc, &c->tc, c->X, c->n, c->dim, c->pitch, nullptr, g.n_kb_data + (g.aug_separate ? 1 : 0), &err))
       return fail(FX_ECUDA, "fx_corpus_finalize: %s", err.c_str());
   }
   c->stats.n_rows = c->n;
   c->finalized = true;
+  if (c->shadow_mode == 1) ensure_plain_shadow(c);
   return FX_OK;
 }
 
@@ -443,6 +445,7 @@ extern "C" int fx_corpus_destroy(fx_corpus* c) {
   for (int i = 0; i < 2; ++i) {
     if (c->ring[i]) { cudaFreeHost(c->ring[i]); cudaEventDestroy(c->ring_ev[i]); }
   }
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c->X) cudaFree(c->X);
   if (c->Xb) cudaFree(c->Xb);
   if (c->Xn) cudaFree(c->Xn);
@@ -549,10 +552,48 @@ static int run_exact_scan(fx_corpus* c, const float* d_q, int n_q, const int* d_
 // ----------------------------------------------------------------------------------------
 // The normalised bf16 shadow (cosine scores straight out of the MMA) is built by the first cosine search that
 // can use it; when HBM is short the search keeps the plain shadow and the multiplicative epilogue.
+static bool shadow_allowed(const fx_corpus* c) { return c->shadow_mode != 0 && c->dim >= 16 && c->n >= 4096 && c->tc.ok; }
+
+// The plain bf16 shadow (+ four augmented columns per row): operand of the L2 / inner-product filter, and of cosine
+// when there is no room for the normalised shadow.
+static bool ensure_plain_shadow(fx_corpus* c) {
+  fx_ctx* ctx = c->ctx;
+  if (c->tc.ok_b) return true;
+  NvtxRange nvtx("fenix:build_plain_shadow");
+  if (c->xb_failed || !shadow_allowed(c)) return false;
+  const fx::ShadowGeom g = fx::shadow_geom(c->dim);
+  const int n_kb = g.n_kb_data, aug_blocks = g.aug_separate ? 1 : 0;
+  const int64_t n_tiles = (c->n + fx::TC_BN - 1) / fx::TC_BN;
+  const size_t shadow_bytes = size_t(n_tiles) * (n_kb + aug_blocks) * fx::TC_BN * 64 * 2;
+  size_t free_b = 0, total_b = 0;
+  const bool forced = c->shadow_mode == 1;
+  if ((!forced && (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < shadow_bytes + (size_t(4) << 30))) ||
+      cudaMalloc(&c->Xb, shadow_bytes) != cudaSuccess) {
+    cudaGetLastError(); c->Xb = nullptr; c->xb_failed = true;   // not fatal: the TF32 filter needs no shadow
+    return false;
+  }
+  const int64_t total = int64_t(shadow_bytes / 4);
+  int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16));
+  // -|x|^2/2 is stored shrunk by the accumulation-rounding allowance (10 % margin for the rounding of the product itself)
+  const float h_scale = float(1.0 - 1.1 * fx::tc_c_add(c->dim, true));
+  fx::to_bf16_tiled_kernel<<<blocks, 256, 0, ctx->stream>>>(c->X, c->n, c->pitch, c->dim, c->hx, c->rx, 0,
+                                                            static_cast<__nv_bfloat16*>(c->Xb), n_kb, n_tiles, g.aug_col, aug_blocks, h_scale);
+  std::string err;
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+      !fx::tc_bind_shadow(&ctx->tc, &c->tc.map_xb, &c->tc.map_xb_h, c->Xb, c->n, n_kb + aug_blocks, &err)) {
+    cudaGetLastError(); cudaFree(c->Xb); c->Xb = nullptr; c->xb_failed = true;
+    return false;
+  }
+  ctx->launches++; c->stats.kernel_launches++;
+  c->stats.device_bytes += int64_t(shadow_bytes);
+  c->tc.ok_b = true;
+  return true;
+}
+
 static bool ensure_norm_shadow(fx_corpus* c) {
   fx_ctx* ctx = c->ctx;
   if (c->tc.ok_n) return true;
-  if (c->xn_failed || !c->tc.ok_b || ctx->tc.knobs.no_norm_shadow) return false;
+  if (c->xn_failed || !shadow_allowed(c) || ctx->tc.knobs.no_norm_shadow) return false;
   const int n_kb = fx::shadow_geom(c->dim).n_kb_data;
   const int64_t n_tiles = (c->n + fx::TC_BN - 1) / fx::TC_BN;
   const size_t shadow_bytes = size_t(n_tiles) * n_kb * fx::TC_BN * 64 * 2;
@@ -588,11 +629,12 @@ static int configure_filter(fx_corpus* c, int metric, int kind, const uint8_t* d
   if (kind == 1) {
     const int errcol = ctx->tc.knobs.errcol;
     if (metric == 0) { s->aug = 1; s->epi = 2; }                       // -|x|^2/2 and the row's error weight ride in the shadow's extra columns
-    else if (metric == 1) { if (ensure_norm_shadow(c)) { s->shadow = 1; s->epi = 2; s->Xn = c->Xn; } }
+    else if (metric == 1) { if (ensure_norm_shadow(c)) { s->shadow = 1; s->epi = 2; s->Xn = c->Xn; } else ensure_plain_shadow(c); }
     else if (errcol == 1 || (errcol < 0 && c->max_norm > 1.5f * c->mean_norm)) s->aug = 2;   // inner product over rows whose norms spread:
                                                                        // per-row error weights instead of c |q| max|x| for every row
     if (s->aug != 0 && errcol == 0) { s->aug = metric == 0 ? 1 : 0; }
     s->c_pair = s->aug != 0 ? fx::tc_c_pair(c->dim, s->aug) : 0.0;
+    s->Xb = c->Xb; s->Xn = c->Xn;   // (a shadow may just have been built)
   }
   if (d_mask) {
     const int64_t n_alloc = ((c->n + 255) / 256) * 256;
@@ -647,7 +689,8 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
   run->tc = false; run->path = 0; run->d_q = d_q; run->n_q = n_q; run->metric = metric; run->k = k;
   run->d_mask = d_mask; run->d_out_rows = d_out_rows; run->d_out_dist = d_out_dist;
   ctx->h_word[0] = 0;
-  FX_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+  const unsigned ev_flags = ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+  FX_CUDA(cudaEventRecordWithFlags(ctx->ev_start, ctx->stream, ev_flags));
   const bool want_tc = precision != FX_PREC_EXACT_SCAN &&
                        fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q));
   if (c->n == 0) {
@@ -655,18 +698,22 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
     fx::fill_pad_kernel<<<int(std::min<int64_t>((n_q * k + 255) / 256, 65535)), 256, 0, ctx->stream>>>(d_out_rows, d_out_dist, n_q * k);
     FX_CUDA(cudaGetLastError());
     ctx->launches++; c->stats.kernel_launches++;
-    FX_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
-    FX_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+    FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k0, ctx->stream, ev_flags));
+    FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k1, ctx->stream, ev_flags));
   } else if (want_tc) {
     fx::TcSearch& s = run->s;
     s = fx::TcSearch{};
     s.X = c->X; s.hx = c->hx; s.rx = c->rx; s.n_rows = c->n; s.dim = c->dim; s.pitch = c->pitch;
     s.row_base = c->row_base; s.max_norm = c->max_norm; s.Q = d_q; s.n_q = int(n_q); s.metric = metric; s.k = k;
     s.certify = precision == FX_PREC_FP32; s.out_rows = d_out_rows; s.out_dist = d_out_dist;
-    s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.dbg = nullptr; s.tau_fixed = nullptr;
+    s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1; s.ev_flags = ev_flags; s.dbg = nullptr; s.tau_fixed = nullptr;
     // operand kind of the filter: exact mode takes the bf16 shadow when the shard has one
-    const int kind = (precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && c->tc.ok_b && !ctx->tc.knobs.fp32_filter_tf32)) ? 1 : 0;
-    if (kind == 1 && !c->tc.ok_b) return fail(FX_ESTATE, "fx_search: FX_PREC_BF16 needs the bf16 shadow (FENIX_BF16_SHADOW=1 at finalize)");
+    // (the shadow this metric streams is built here, by its first search: normalised rows for cosine, else the plain one)
+    const bool want_bf16 = precision == FX_PREC_BF16 || (precision == FX_PREC_FP32 && !ctx->tc.knobs.fp32_filter_tf32);
+    const bool have_shadow = want_bf16 && ((metric == 1 && ensure_norm_shadow(c)) || ensure_plain_shadow(c));
+    const int kind = have_shadow ? 1 : 0;
+    if (precision == FX_PREC_BF16 && !have_shadow)
+      return fail(FX_ESTATE, "fx_search: FX_PREC_BF16 needs a bf16 shadow (none could be built: FENIX_BF16_SHADOW=0, a tiny shard, or no HBM left)");
     FX_TRY(configure_filter(c, metric, kind, d_mask, &s));
     run->L = fx::tc_prepare(&ctx->tc, s);
     FX_TRY(ctx->d_tc.ensure(run->L.scratch_bytes));
@@ -678,11 +725,11 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
     ctx->launches += launched; c->stats.kernel_launches += launched;
     if (s.certify) FX_CUDA(cudaMemcpyAsync(ctx->h_word, fx::tc_flag_count(ctx->d_tc.p), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   } else {
-    FX_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k0, ctx->stream, ev_flags));
     FX_TRY(run_exact_scan(c, d_q, int(n_q), nullptr, int(n_q), metric, k, d_mask, d_out_rows, d_out_dist));
-    FX_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+    FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k1, ctx->stream, ev_flags));
   }
-  FX_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+  FX_CUDA(cudaEventRecordWithFlags(ctx->ev_stop, ctx->stream, ev_flags));
   return FX_OK;
 }
 
@@ -808,6 +855,7 @@ static void search_account(fx_corpus* c, const SearchRun& run) {
 extern "C" int fx_search_device(fx_corpus* c, const float* d_queries, int64_t n_q, int32_t metric, int32_t k,
                                 int32_t precision, const uint8_t* d_row_mask, int64_t* d_out_rows, float* d_out_dist) {
   FX_LEASE(c, "fx_search_device");
+  NvtxRange nvtx("fenix:search_device");
   FX_TRY(check_search_args(c, d_queries, n_q, metric, k, precision, d_out_rows, d_out_dist));
   if (n_q == 0) return FX_OK;
   fx_ctx* ctx = c->ctx;
@@ -830,9 +878,69 @@ static bool is_pinned(const void* p) {
   return pinned;
 }
 
+// Small searches are launch-bound: six kernels, three copies and their host calls around a few microseconds of device
+// work each. From its second identical call on (same shard, batch size, metric, k, precision; no row mask) such a
+// search is ONE cudaGraphLaunch: queries are staged in the context's pinned buffer, the graph copies them in, runs
+// prep / filter / finish and copies results and the flagged-query counter back to pinned memory. A flagged query (rare)
+// sends the call down the ordinary path.
+constexpr int64_t GRAPH_MAX_Q = 64;
+
+static fx_corpus::GraphEntry* graph_entry(fx_corpus* c, int64_t n_q, int metric, int k, int precision) {
+  for (auto& g : c->graphs)
+    if (g.n_q == n_q && g.metric == metric && g.k == k && g.precision == precision) return &g;
+  if (c->graphs.size() >= 16) {          // bounded: drop the oldest
+    if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);
+    c->graphs.erase(c->graphs.begin());
+  }
+  c->graphs.emplace_back();
+  auto& g = c->graphs.back();
+  g.n_q = n_q; g.metric = metric; g.k = k; g.precision = precision;
+  return &g;
+}
+
+static bool graph_buffers_match(const fx_ctx* ctx, const fx_corpus::GraphEntry& g) {
+  const void* now[7] = {ctx->d_q.p, ctx->d_rows.p, ctx->d_dist.p, ctx->d_tc.p, ctx->h_q.p, ctx->h_rows.p, ctx->h_dist.p};
+  for (int i = 0; i < 7; ++i) if (now[i] != g.ptrs[i]) return false;
+  return g.knob_epoch == ctx->knob_epoch;
+}
+
+// Captures H2D + search + D2H of this call into an executable graph (the caller launches it). false: not captured - the
+// entry is marked and the caller takes the ordinary path.
+static bool graph_capture(fx_corpus* c, fx_corpus::GraphEntry* g, int64_t n_q, int metric, int k, int precision,
+                                     size_t q_bytes, size_t r_bytes, size_t d_bytes, SearchRun* run) {
+  fx_ctx* ctx = c->ctx;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g->state = -1; return false; }
+  ctx->capturing = true;
+  bool ok = cudaMemcpyAsync(ctx->d_q.p, ctx->h_q.p, q_bytes, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+  const int64_t launches0 = c->stats.kernel_launches;
+  ok = ok && search_enqueue(c, static_cast<const float*>(ctx->d_q.p), n_q, metric, k, precision, nullptr,
+                            static_cast<int64_t*>(ctx->d_rows.p), static_cast<float*>(ctx->d_dist.p), run) == FX_OK;
+  ok = ok && cudaMemcpyAsync(ctx->h_rows.p, ctx->d_rows.p, r_bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+  ok = ok && cudaMemcpyAsync(ctx->h_dist.p, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+  ctx->capturing = false;
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+  if (!ok || ee != cudaSuccess || !graph || !run->tc) {      // only the tensor-core path is worth a graph
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g->state = -1;
+    return false;
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); g->state = -1; return false; }
+  cudaGraphDestroy(graph);
+  g->exec = exec; g->state = 1; g->knob_epoch = ctx->knob_epoch;
+  const void* now[7] = {ctx->d_q.p, ctx->d_rows.p, ctx->d_dist.p, ctx->d_tc.p, ctx->h_q.p, ctx->h_rows.p, ctx->h_dist.p};
+  for (int i = 0; i < 7; ++i) g->ptrs[i] = const_cast<void*>(now[i]);
+  g->path = run->path; g->variant = c->stats.last_variant; g->launches = int(c->stats.kernel_launches - launches0);
+  c->stats.kernel_launches = launches0;   // counted when the graph runs
+  return true;
+}
+
 extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, int32_t k,
                          int32_t precision, const uint8_t* row_mask, int64_t* out_rows, float* out_dist) {
   FX_LEASE(c, "fx_search");
+  NvtxRange nvtx("fenix:search");
   FX_TRY(check_search_args(c, queries, n_q, metric, k, precision, out_rows, out_dist));
   if (n_q == 0) return FX_OK;
   fx_ctx* ctx = c->ctx;
@@ -843,6 +951,51 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
   FX_TRY(ctx->d_q.ensure(q_bytes));
   FX_TRY(ctx->d_rows.ensure(r_bytes));
   FX_TRY(ctx->d_dist.ensure(d_bytes));
+  // ---- small searches: replay (or capture) the whole call as one CUDA graph ----
+  if (n_q <= GRAPH_MAX_Q && !row_mask && c->n > 0 && ctx->tc.knobs.graph != 0 && precision != FX_PREC_EXACT_SCAN &&
+      fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q))) {
+    fx_corpus::GraphEntry* g = graph_entry(c, n_q, metric, k, precision);
+    if (g->state == 1 && !graph_buffers_match(ctx, *g)) {     // a buffer grew or a knob changed since the capture
+      cudaGraphExecDestroy(g->exec); g->exec = nullptr; g->state = 0;
+    }
+    bool launched = false;
+    SearchRun run;
+    if (g->state >= 0) {
+      FX_TRY(ctx->h_q.ensure(q_bytes));
+      FX_TRY(ctx->h_rows.ensure(r_bytes));
+      FX_TRY(ctx->h_dist.ensure(d_bytes));
+    }
+    if (g->state == 1) {
+      std::memcpy(ctx->h_q.p, queries, q_bytes);
+      ctx->h_word[0] = 0;
+      FX_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+      run.tc = true; run.path = g->path; run.n_q = n_q;
+      c->stats.last_variant = g->variant;
+      ctx->launches += g->launches; c->stats.kernel_launches += g->launches;
+      launched = true;
+    } else if (g->state == 2) {
+      // second identical call: everything it needs (shadows, scratch) exists and is big enough - capture it
+      std::memcpy(ctx->h_q.p, queries, q_bytes);
+      if (graph_capture(c, g, n_q, metric, k, precision, q_bytes, r_bytes, d_bytes, &run)) {
+        ctx->h_word[0] = 0;
+        FX_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+        ctx->launches += g->launches; c->stats.kernel_launches += g->launches;
+        launched = true;
+      }
+    } else if (g->state == 0) {
+      g->state = 2;   // seen once: the next identical call captures
+    }
+    if (launched) {
+      FX_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->h_word[0] == 0) {
+        std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
+        std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
+        search_account(c, run);
+        return FX_OK;
+      }
+      // a certificate failed: the ordinary path below recomputes the call, with its repair tiers
+    }
+  }
   // queries: direct DMA when the caller's buffer is pinned, otherwise through pinned staging
   const void* q_src = queries;
   if (!is_pinned(queries)) {
@@ -941,7 +1094,7 @@ extern "C" int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, 
   s.metric = metric; s.k = 10; s.certify = false; s.out_rows = static_cast<int64_t*>(ctx->d_rows.p);
   s.out_dist = static_cast<float*>(ctx->d_dist.p); s.stream = ctx->stream; s.ev_k0 = ctx->ev_k0; s.ev_k1 = ctx->ev_k1;
   s.dbg = d_dbg; s.tau_fixed = nullptr;
-  FX_TRY(configure_filter(c, metric, (ctx->tc.knobs.debug_bf16 && c->tc.ok_b) ? 1 : 0, nullptr, &s));
+  FX_TRY(configure_filter(c, metric, (ctx->tc.knobs.debug_bf16 && ((metric == 1 && ensure_norm_shadow(c)) || ensure_plain_shadow(c))) ? 1 : 0, nullptr, &s));
   const fx::TcLaunch L = fx::tc_prepare(&ctx->tc, s);
   FX_TRY(ctx->d_tc.ensure(L.scratch_bytes));
   std::string err; int launched = 0;
@@ -1097,6 +1250,7 @@ static int sharded_search_locked(fx_corpus* c, fx_comm* cm, const float* queries
                                  float* out_dist, bool out_on_device) {
   fx_ctx* ctx = c->ctx;
   NcclApi* api = nccl_api();
+  NvtxRange nvtx("fenix:search_sharded");
   const int W = cm->world, rank = cm->rank;
   const int64_t per = (n_q + W - 1) / W;                    // queries per rank slice (the last slices may be short / empty)
   const size_t row_bytes = size_t(c->dim) * sizeof(float);
@@ -1163,6 +1317,7 @@ static int sharded_search_locked(fx_corpus* c, fx_comm* cm, const float* queries
       FX_CUDA(cudaMemcpyAsync(mine + hdr_off, fx::tc_flag_count(ctx->d_tc.p), sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     else
       FX_CUDA(cudaMemsetAsync(mine + hdr_off, 0, 16, ctx->stream));
+    NvtxRange nvtx_x("fenix:exchange (all-gather + merge)");
     FX_CUDA(cudaEventRecord(ctx->ev_x0, ctx->stream));
     if (W > 1) FX_NCCL(api->AllGather(mine, xb, slot, kNcclInt8, cm->comm, ctx->stream));
     if (want_out) {

@@ -112,6 +112,8 @@ struct TcKnobs {
   int no_refine = 0;       // FENIX_NO_REFINE      flagged queries go straight to the fp64 scan
   int no_norm_shadow = 0;  // FENIX_NO_NORM_SHADOW cosine keeps the plain shadow + multiplicative epilogue
   int debug_bf16 = 0;      // FENIX_DEBUG_BF16     fx_debug_scores dumps the bf16 filter's scores
+  int graph = 1;           // FENIX_GRAPH          small searches (<= 64 queries, no mask) replay a captured CUDA graph from their second
+                           //                      identical call on (0: always launch kernel by kernel)
   int debug_tiers = 0;     // FENIX_DEBUG_TIERS    stderr trace of the certificate-failure tiers (counts, host-clock times)
 };
 // name = the environment variable's name; value = its text, or null to restore the default. False: unknown name.
@@ -142,6 +144,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_NO_NORM_SHADOW") k->no_norm_shadow = as_flag();
   else if (n == "FENIX_DEBUG_BF16") k->debug_bf16 = as_flag();
   else if (n == "FENIX_DEBUG_TIERS") k->debug_tiers = as_flag();
+  else if (n == "FENIX_GRAPH") k->graph = as_int(d.graph);
   else return false;
   return true;
 }
@@ -150,7 +153,7 @@ inline void tc_knobs_from_env(TcKnobs* k) {
       "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
       "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
       "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
-      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS"};
+      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH"};
   for (const char* name : names) {
     if (const char* v = std::getenv(name)) tc_set_knob(k, name, v);
   }
@@ -174,6 +177,7 @@ struct TcSearch {
   const float* X; const float* hx; const float* rx; int64_t n_rows; int dim; int pitch; int64_t row_base;
   float max_norm; const float* Q; int n_q; int metric; int k; bool certify;
   int64_t* out_rows; float* out_dist; cudaStream_t stream; cudaEvent_t ev_k0, ev_k1;
+  unsigned ev_flags;       // cudaEventRecordExternal while the search is being captured into a CUDA graph, else 0
   float* dbg;              // optional [128][256] raw score dump (diagnostics)
   int kind;                // 0: TF32 filter over the fp32 rows, 1: bf16 filter over the bf16 shadow
   int pitch_b;             // elements per row of the bf16 shadow (multiple of 8)
@@ -1904,6 +1908,9 @@ inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan
   int stride = int(double(main_pl.kp) * safety / target_m);         // S = N / stride, m = safety K' S / N
   const int64_t n_tiles_full = (s.n_rows + tile_rows - 1) / tile_rows;
   if (stride < 4 || n_tiles_full / stride < 32) return false;       // shard too small for a sample to pay off
+  // one query tile over a small shard (single-query searches of a 100k-row table): the whole scan is a few microseconds
+  // per SM, two more launches cost more than loose thresholds do
+  if (main_pl.n_qt == 1 && n_tiles_full < 2048) return false;
   const int rec_per_tile = main_pl.rq ? 1 : TC_SPLIT;
   // at most 4096 records per query (they are held in registers by the tau0 kernel) and 256 MB of records in all
   const int64_t max_rec = std::min<int64_t>(4096, std::max<int64_t>(64, (int64_t(1) << 26) / std::max(s.n_q, 1)));
@@ -1943,7 +1950,7 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   p.sleep_ns = pl.n_kblocks >= 6 ? 0u : 64u;
   p.hx = s.hx; p.rx = s.rx; p.dbg = s.dbg; p.wbuf = wbuf; p.wcnt = wcnt; p.tau_g = tau_g;
   p.qt_major = pl.qt_major; p.fixed = s.tau_fixed ? 1 : 0; p.flags = flags;
-  if (s.ev_k0) cudaEventRecord(s.ev_k0, s.stream);
+  if (s.ev_k0) cudaEventRecordWithFlags(s.ev_k0, s.stream, s.ev_flags);
   const int epi = s.epi;   // epilogue form: 0 add, 1 multiply, 2 none
   // dispatch on (epilogue form, operand kind, mode: filter / diagnostics dump / prepass, CTA pairs)
   cudaError_t le = cudaSuccess;
@@ -1997,7 +2004,7 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
 #undef FX_TC_CASE
   }
   if (le != cudaSuccess) { *err = std::string("filter kernel launch failed: ") + cudaGetErrorString(le); return false; }
-  if (s.ev_k1) cudaEventRecord(s.ev_k1, s.stream);
+  if (s.ev_k1) cudaEventRecordWithFlags(s.ev_k1, s.stream, s.ev_flags);
   if (pre) {
     if (pl.n_rec <= 32 * TAU0_PER) knn_tc_tau0_kernel<32><<<(s.n_q + 7) / 8, 256, 0, s.stream>>>(p.pre_max, s.n_q, pl.n_rec, s.pre_m, tau_g);
     else if (pl.n_rec <= 64 * TAU0_PER) knn_tc_tau0_kernel<64><<<(s.n_q + 3) / 4, 256, 0, s.stream>>>(p.pre_max, s.n_q, pl.n_rec, s.pre_m, tau_g);

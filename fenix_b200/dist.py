@@ -87,6 +87,7 @@ class ShardedSearcher:
         self.device = torch.device("cuda", corpus.ctx.device)
         self.merge_launches = 0
         self.comm = None
+        self._out_key, self._out_rows, self._out_dist = None, None, None
         if self.world > 1:
             uid = broadcast_comm_id(knn.Comm.unique_id, group, self.device if td.get_backend(group) == "nccl" else None)
             self.comm = knn.Comm(corpus.ctx, uid, self.world, self.rank)
@@ -96,9 +97,7 @@ class ShardedSearcher:
         """d_queries: float32 [Q, D], the whole batch, resident on this rank's GPU. Returns the global (rows, dist) [Q, k]
         on the device."""
         n_q = d_queries.shape[0]
-        rows = torch.empty((n_q, k), dtype=torch.int64, device=self.device)
-        dist = torch.empty((n_q, k), dtype=torch.float32, device=self.device)
-        torch.cuda.current_stream(self.device).synchronize()   # the tensors above exist before the library's stream uses them
+        rows, dist = self._out(n_q, k)
         if self.world == 1:
             self.corpus.search_device(d_queries.data_ptr(), n_q, metric, k, precision, rows.data_ptr(), dist.data_ptr())
             return rows, dist
@@ -106,6 +105,17 @@ class ShardedSearcher:
                                        dist.data_ptr(), on_device=True)
         self.merge_launches += 1
         return rows, dist
+
+    def _out(self, n_q: int, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """Result tensors of a device-resident search, reused from call to call (the library synchronises its stream before
+        it returns, so the previous result has been consumed or copied by then; callers that keep results clone them)."""
+        key = (n_q, k)
+        if self._out_key != key:
+            self._out_rows = torch.empty((n_q, k), dtype=torch.int64, device=self.device)
+            self._out_dist = torch.empty((n_q, k), dtype=torch.float32, device=self.device)
+            torch.cuda.current_stream(self.device).synchronize()   # they exist before the library's stream writes them
+            self._out_key = key
+        return self._out_rows, self._out_dist
 
     def search_host(self, h_queries: torch.Tensor, metric: int, k: int, precision: int = knn.PREC_FP32,
                     h_rows: Optional[torch.Tensor] = None, h_dist: Optional[torch.Tensor] = None,

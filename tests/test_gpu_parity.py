@@ -564,6 +564,64 @@ def test_other_float_widths_of_the_vector_column(built_library, value_type, tmp_
         fenix.io.shards.invalidate(root)
 
 
+@pytest.mark.parametrize("metric,nq", [("l2", 1), ("cosine", 5), ("dot", 64)])
+def test_small_searches_replay_a_cuda_graph(ctx, metric, nq):
+    """From its second identical call on a small search (<= 64 queries, no mask) is one captured CUDA graph: call 1 runs
+    kernel by kernel, call 2 captures, calls 3+ replay. Every call gets DIFFERENT queries through the same graph and must
+    equal the fp64 scan; a bigger search in between (scratch grows) and a knob change both force a re-capture."""
+    rng = np.random.default_rng(1234)
+    n, d, k = 100_000, 128, 10
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    launches = []
+    for call in range(6):
+        q = rng.standard_normal((nq, d), dtype=np.float32)
+        if call == 4:
+            c.search(rng.standard_normal((700, d), dtype=np.float32), metric, k)      # grows the scratch buffers
+        if call == 5:
+            ctx.set_option("FENIX_TC_KP", 96)
+        before = c.stats().kernel_launches
+        rows, dist = c.search(q, metric, k)
+        launches.append(c.stats().kernel_launches - before)
+        assert c.stats().last_path == 2
+        rows_s, dist_s = c.search(q, metric, k, knn.PREC_EXACT_SCAN)
+        assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s), (metric, nq, call)
+    ctx.set_option("FENIX_TC_KP", None)
+    assert len(set(launches[:4])) == 1, launches            # the graph runs the same kernels as the plain path
+    # graphs off: same answers
+    ctx.set_option("FENIX_GRAPH", 0)
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    r0, d0 = c.search(q, metric, k)
+    ctx.set_option("FENIX_GRAPH", None)
+    for _ in range(3):
+        r1, d1 = c.search(q, metric, k)
+        assert np.array_equal(r0, r1) and np.array_equal(d0, d1)
+    c.close()
+
+
+def test_each_shadow_is_built_by_the_first_search_that_streams_it(ctx):
+    """A shard searched with one metric holds its fp32 rows and ONE bf16 shadow (the normalised rows for cosine, the plain
+    rows + augmented columns for L2 / inner product); the second shadow appears only when the other kind of search comes."""
+    rng = np.random.default_rng(8)
+    n, d = 16_384, 128
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    queries = rng.standard_normal((8, d), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    rows_bytes = c.stats().device_bytes
+    assert rows_bytes == n * (d + 2) * 4                       # rows + the two cached norm terms, no shadow yet
+    c.search(queries, "cosine", 5)
+    norm_shadow = c.stats().device_bytes - rows_bytes
+    assert c.stats().last_path == 2 and norm_shadow == n * d * 2
+    c.search(queries, "cosine", 5)
+    assert c.stats().device_bytes == rows_bytes + norm_shadow  # nothing more for the same metric
+    c.search(queries, "dot", 5)
+    plain_shadow = c.stats().device_bytes - rows_bytes - norm_shadow
+    assert plain_shadow == n * (d + 64) * 2                    # data blocks + one block per tile for the augmented columns
+    c.search(queries, "l2", 5)
+    assert c.stats().device_bytes == rows_bytes + norm_shadow + plain_shadow
+    c.close()
+
+
 def test_tensor_core_path_runs_and_certifies(ctx):
     """fp32 mode must take the tcgen05 path on ordinary data (no silent fallback to the scan) and the
     certificate must hold for (nearly) every query; tf32 mode reports its recall."""
