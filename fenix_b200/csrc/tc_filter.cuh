@@ -99,6 +99,7 @@ struct TcKnobs {
   int kp_list = 0;         // FENIX_TC_KP_LIST     candidates each (query, list) keeps at a selection
   int pre_wide = 1;        // FENIX_TC_PRE_WIDE    sample prepass also for wide rows at large batches (0: off)
   int pre = -1;            // FENIX_TC_PRE         0: no sample prepass
+  int pre_small = 1;       // FENIX_TC_PRE_SMALL   0: no sample prepass for one query tile over < 2048 tiles
   double pre_safety = 0.0; // FENIX_TC_PRE_SAFETY
   double pre_m = 0.0;      // FENIX_TC_PRE_M
   int pf = 0;              // FENIX_TC_PF          L2 prefetch distance in tiles
@@ -131,6 +132,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_TC_KP_LIST") k->kp_list = as_int(d.kp_list);
   else if (n == "FENIX_TC_PRE_WIDE") k->pre_wide = as_int(d.pre_wide);
   else if (n == "FENIX_TC_PRE") k->pre = as_int(d.pre);
+  else if (n == "FENIX_TC_PRE_SMALL") k->pre_small = as_int(d.pre_small);
   else if (n == "FENIX_TC_PRE_SAFETY") k->pre_safety = as_dbl();
   else if (n == "FENIX_TC_PRE_M") k->pre_m = as_dbl();
   else if (n == "FENIX_TC_PF") k->pf = as_int(d.pf);
@@ -151,7 +153,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
 inline void tc_knobs_from_env(TcKnobs* k) {
   static const char* const names[] = {
       "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
-      "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
+      "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SMALL", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
       "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
       "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH"};
   for (const char* name : names) {
@@ -1908,9 +1910,8 @@ inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan
   int stride = int(double(main_pl.kp) * safety / target_m);         // S = N / stride, m = safety K' S / N
   const int64_t n_tiles_full = (s.n_rows + tile_rows - 1) / tile_rows;
   if (stride < 4 || n_tiles_full / stride < 32) return false;       // shard too small for a sample to pay off
-  // one query tile over a small shard (single-query searches of a 100k-row table): the whole scan is a few microseconds
-  // per SM, two more launches cost more than loose thresholds do
-  if (main_pl.n_qt == 1 && n_tiles_full < 2048) return false;
+  // FENIX_TC_PRE_SMALL=0: no sample for one query tile over a small shard (single-query searches of a 100k-row table)
+  if (main_pl.n_qt == 1 && n_tiles_full < 2048 && kn.pre_small == 0) return false;
   const int rec_per_tile = main_pl.rq ? 1 : TC_SPLIT;
   // at most 4096 records per query (they are held in registers by the tau0 kernel) and 256 MB of records in all
   const int64_t max_rec = std::min<int64_t>(4096, std::max<int64_t>(64, (int64_t(1) << 26) / std::max(s.n_q, 1)));

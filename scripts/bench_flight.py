@@ -3,28 +3,52 @@
 Runs the fenix_b200 server + client over loopback (sequential single-query RPCs, as the reference serves
 them, then the batched wire extension), and the same server class with io.index.call swapped for the oracle
 port of the reference's CPU path (so both arms pay the same RPC cost). Prints one JSON line per arm."""
-import json, os, sys, time, tempfile, shutil
+import argparse, json, os, sys, time, tempfile, shutil
 import numpy as np
 import pyarrow as pa
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--devices", type=int, default=1, help="GPUs the ONE server process row-shards the table over (FENIX_DEVICES=0..N-1): "
+                "fx_group_search - a worker thread, a context and an NCCL communicator per device inside the library")
+ap.add_argument("--rows", type=int, default=100_000)
+ap.add_argument("--dim", type=int, default=128)
+ap.add_argument("--metric", default="l2")
+ap.add_argument("--batch", type=int, default=1000, help="queries per RPC of the batched wire extension arm")
+ap.add_argument("--chunk", type=int, default=1000, help="rows per record batch of the table")
+ap.add_argument("--no-reference", action="store_true")
+args = ap.parse_args()
+os.environ["FENIX_DEVICES"] = ",".join(str(i) for i in range(args.devices))
 import fenix_b200 as fenix
 from fenix_b200 import io as fio
 
-N, D, K, NQ, CHUNK = 100_000, 128, 10, 1000, 1000
+N, D, K, NQ, CHUNK, METRIC = args.rows, args.dim, 10, max(1000, args.batch), args.chunk, args.metric
 rng = np.random.default_rng(1001)
-corpus = rng.standard_normal((N, D), dtype=np.float32)
 queries = np.random.default_rng(2001).standard_normal((NQ, D), dtype=np.float32)
-batches = []
-for lo in range(0, N, CHUNK):
-    x = corpus[lo:lo + CHUNK]
-    batches.append(pa.record_batch([pa.array(np.arange(lo, lo + CHUNK, dtype=np.int64)),
-                                    pa.FixedSizeListArray.from_arrays(pa.array(x.reshape(-1)), D)], names=["id", "vector"]))
-table = pa.Table.from_batches(batches)
+
+
+def gen_batches():
+    for lo in range(0, N, CHUNK):
+        x = rng.standard_normal((min(CHUNK, N - lo), D), dtype=np.float32)
+        yield pa.record_batch([pa.array(np.arange(lo, lo + len(x), dtype=np.int64)),
+                               pa.FixedSizeListArray.from_arrays(pa.array(x.reshape(-1)), D)], names=["id", "vector"])
+
+
+schema = pa.schema({"id": pa.int64(), "vector": pa.list_(pa.float32(), D)})
 root = tempfile.mkdtemp(prefix="fenix_c1_")
 port = 9311
 server = fenix.Server(root, "127.0.0.1", port)
 client = fenix.Flight("127.0.0.1", port)
-client.make_table("c1", table.to_reader())
+t0 = time.perf_counter()
+client.make_table("c1", pa.RecordBatchReader.from_batches(schema, gen_batches()))
+t_put = time.perf_counter() - t0
+t0 = time.perf_counter()
+client.search(queries[0], "c1", "vector", METRIC, select=["id"], maxval=K)
+t_first = time.perf_counter() - t0
+print(json.dumps({"arm": "ingest", "devices": args.devices, "rows": N, "dim": D, "do_put_s": t_put,
+                  "first_search_after_put_ms": t_first * 1e3,
+                  "note": "do_put uploads the vector column(s) to the device shard(s) before it returns (FENIX_UPLOAD_ON_PUT=0: lazily, by the first search); "
+                          "the first search only builds the bf16 shadow its metric streams"}), flush=True)
 
 def run(label, n_q, fn):
     fn(0)
@@ -38,28 +62,34 @@ def run(label, n_q, fn):
 
 ours = {}
 def ours_single(i):
-    ours[i] = client.search(queries[i], "c1", "vector", "l2", select=["id"], maxval=K)
+    ours[i] = client.search(queries[i], "c1", "vector", METRIC, select=["id"], maxval=K)
 run("fenix_b200 Flight, 1 query per RPC (GPU)", NQ, ours_single)
 run("fenix_b200 Flight, 1 query per RPC, default select (the 10 winning vectors are gathered and returned)", NQ,
-    lambda i: client.search(queries[i], "c1", "vector", "l2", maxval=K))
-client.search(queries, "c1", "vector", "l2", select=["id"], maxval=K)   # warm-up (scratch growth for a 1000-query batch)
+    lambda i: client.search(queries[i], "c1", "vector", METRIC, maxval=K))
+qb = queries[: args.batch]
+client.search(qb, "c1", "vector", METRIC, select=["id"], maxval=K)   # warm-up (scratch growth for the batch)
 t0 = time.perf_counter()
 for _ in range(5):
-    out = client.search(queries, "c1", "vector", "l2", select=["id"], maxval=K)
+    out = client.search(qb, "c1", "vector", METRIC, select=["id"], maxval=K)
 dt = (time.perf_counter() - t0) / 5
-print(json.dumps({"arm": "fenix_b200 Flight, batched wire extension: 1000 queries in one RPC (GPU)", "queries": NQ, "qps": NQ / dt, "ms_per_rpc": dt * 1e3}), flush=True)
+print(json.dumps({"arm": f"fenix_b200 Flight, batched wire extension: {args.batch} queries in one RPC ({args.devices} GPU(s))",
+                  "queries": args.batch, "qps": args.batch / dt, "ms_per_rpc": dt * 1e3}), flush=True)
+# the batched answer against the sequential single-query answers (same server)
+same_b = sum(out.filter(pa.compute.field("__QUERY__") == i).column("id").to_pylist() == ours[i].column("id").to_pylist() for i in range(0, min(args.batch, NQ), 41))
+print(json.dumps({"batched_vs_single": f"{same_b}/{len(range(0, min(args.batch, NQ), 41))} sampled queries identical"}), flush=True)
 
 # concurrent clients: 16 threads, each with its own connection, sequential single-query RPCs
 import threading
+import pyarrow.compute  # noqa: F401
 def concurrent(label, n_threads=16, per_thread=125):
     clients = [fenix.Flight("127.0.0.1", port) for _ in range(n_threads)]
     for c in clients:
-        c.search(queries[0], "c1", "vector", "l2", select=["id"], maxval=K)
+        c.search(queries[0], "c1", "vector", METRIC, select=["id"], maxval=K)
     res = {}
     def work(t):
         for j in range(per_thread):
             i = t * per_thread + j
-            res[i] = clients[t].search(queries[i % NQ], "c1", "vector", "l2", select=["id"], maxval=K)
+            res[i] = clients[t].search(queries[i % NQ], "c1", "vector", METRIC, select=["id"], maxval=K)
     b0, r0 = fio.index._batcher.batches, fio.index._batcher.requests
     ths = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
     t0 = time.perf_counter()
@@ -85,9 +115,12 @@ def cpu_call(root_, coding, source, column, target, metric=None, select=None, fi
 fio.index.call = cpu_call
 ref = {}
 def ref_single(i):
-    ref[i] = client.search(queries[i], "c1", "vector", "l2", select=["id"], maxval=K)
-run("reference CPU path (oracle port) behind the same Flight server", 100, ref_single)
+    ref[i] = client.search(queries[i], "c1", "vector", METRIC, select=["id"], maxval=K)
+n_ref = 0 if args.no_reference else (100 if N * D <= 2e7 else 8)
+if n_ref:
+    run("reference CPU path (oracle port) behind the same Flight server", n_ref, ref_single)
 fio.index.call = real_call
-same = sum(sorted(ours[i].column("id").to_pylist()) == sorted(ref[i].column("id").to_pylist()) for i in range(100))
-print(json.dumps({"parity": f"{same}/100 queries return identical id sets"}), flush=True)
+if n_ref:
+    same = sum(ours[i].column("id").to_pylist() == ref[i].column("id").to_pylist() for i in range(n_ref))
+    print(json.dumps({"parity": f"{same}/{n_ref} queries return identical ids in identical order (served GPU path vs the reference's CPU path behind the same server)"}), flush=True)
 client.remove(); server.shutdown(); shutil.rmtree(root, ignore_errors=True)

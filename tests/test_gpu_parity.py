@@ -460,7 +460,7 @@ def test_shadow_geometry_boundaries(ctx, dim):
         before = c.stats()
         rows, dist = c.search(qh, metric, k)
         st = c.stats()
-        blocks = -(-(dim + (3 if metric == "l2" else 0)) // 64)      # 64-column k-blocks the search multiplies
+        blocks = -(-(dim + (4 if metric == "l2" else 0)) // 64)      # 64-column k-blocks the search multiplies
         assert st.last_path == 2 and (st.last_variant & 1) == (1 if blocks <= 3 else 0), (metric, st.last_variant)
         assert st.fallback_queries - before.fallback_queries <= 2
         rows_s, dist_s = c.search(qh[sub], metric, k, knn.PREC_EXACT_SCAN)
@@ -937,3 +937,76 @@ class TestFlightDropIn:
         finally:
             client.drop_index("cb")
         assert [*fenix.io.index.list(client_root(served))] == []
+
+
+@pytest.mark.gpu
+def test_flight_serves_the_row_sharded_path(built_library, tmp_path, monkeypatch):
+    """FENIX_DEVICES lists several GPUs: ONE server process row-shards the table over them and `Server.do_exchange`
+    answers through fx_group_search (worker thread + NCCL communicator per device inside the library, candidates
+    all-gathered over NVLink, merged on the device). Same answers as the oracle, single-query and batched, with a
+    predicate; concurrent clients; a do_put during the searches (the replaced shard set is retired, never closed under
+    a running search). Skipped on a single-GPU box."""
+    import threading
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n_dev = min(torch.cuda.device_count(), 4)
+    monkeypatch.setenv("FENIX_DEVICES", ",".join(str(i) for i in range(n_dev)))
+    root = str(tmp_path / "served")
+    port = 9151
+    server = fenix.Server(root, "127.0.0.1", port)
+    client = fenix.Flight("127.0.0.1", port)
+    rng = np.random.default_rng(314)
+    corpus = rng.standard_normal((30_011, 64), dtype=np.float32)
+    source = table_of(corpus, 1000)
+    try:
+        client.make_table("t", source.to_reader())
+        shard = fenix.io.shards.get(root, "t", "vector", fenix.io.shards.load_table(root, "t"))
+        assert len(shard.corpora) == n_dev and shard.group is not None
+        shard.release()
+        qs = rng.standard_normal((9, 64), dtype=np.float32)
+        for metric in ("l2", "cosine", "dot"):
+            for qi in range(3):
+                out = client.search(qs[qi], "t", "vector", metric, select=["id"], maxval=10)
+                ref_rows, ref_dist = search_rows(source, "vector", qs[qi], metric, 10)
+                assert_same_neighbours(out.column("id").to_numpy(), out.column("__DISTANCE__").to_numpy(), ref_rows, ref_dist,
+                                       corpus, qs[qi], metric)
+            out = client.search(qs, "t", "vector", metric, select=["id"], maxval=7)
+            for qi in range(len(qs)):
+                sel = out.filter(pc.field("__QUERY__") == qi)
+                ref_rows, ref_dist = search_rows(source, "vector", qs[qi], metric, 7)
+                assert_same_neighbours(sel.column("id").to_numpy(), sel.column("__DISTANCE__").to_numpy(), ref_rows, ref_dist,
+                                       corpus, qs[qi], metric)
+        flt = pc.field("id") > 20_000        # only the last shard(s) hold live rows
+        out = client.search(qs[0], "t", "vector", "l2", select=["id"], filter=flt, maxval=5)
+        ref_rows, ref_dist = search_rows(source, "vector", qs[0], "l2", 5, filter=flt)
+        assert_same_neighbours(out.column("id").to_numpy(), out.column("__DISTANCE__").to_numpy(), ref_rows, ref_dist, corpus, qs[0], "l2")
+        # concurrent clients while the table is replaced
+        errors, answers = [], []
+
+        def hammer(t):
+            try:
+                cl = fenix.Flight("127.0.0.1", port)
+                for j in range(20):
+                    answers.append(cl.search(qs[(t + j) % len(qs)], "t", "vector", "l2", select=["id"], maxval=5).num_rows)
+            except BaseException as exc:
+                errors.append(exc)
+
+        threads = [threading.Thread(target=hammer, args=(t,)) for t in range(4)]
+        for t in threads:
+            t.start()
+        client.make_table("t", table_of(corpus[:20_000] + np.float32(1.0), 1000).to_reader())
+        for t in threads:
+            t.join()
+        assert not errors, errors[:1]
+        assert all(a == 5 for a in answers)
+        out = client.search(qs[1], "t", "vector", "l2", select=["id"], maxval=5)
+        ref_rows, ref_dist = search_rows(table_of(corpus[:20_000] + np.float32(1.0), 1000), "vector", qs[1], "l2", 5)
+        assert_same_neighbours(out.column("id").to_numpy(), out.column("__DISTANCE__").to_numpy(), ref_rows, ref_dist,
+                               corpus[:20_000] + np.float32(1.0), qs[1], "l2")
+    finally:
+        client.remove()
+        server.shutdown()
+        fenix.io.shards.invalidate(root)
