@@ -630,7 +630,7 @@ static int configure_filter(fx_corpus* c, int metric, int kind, const uint8_t* d
     const int errcol = ctx->tc.knobs.errcol;
     if (metric == 0) { s->aug = 1; s->epi = 2; }                       // -|x|^2/2 and the row's error weight ride in the shadow's extra columns
     else if (metric == 1) { if (ensure_norm_shadow(c)) { s->shadow = 1; s->epi = 2; s->Xn = c->Xn; } else ensure_plain_shadow(c); }
-    else if (errcol == 1 || (errcol < 0 && c->max_norm > 1.5f * c->mean_norm)) s->aug = 2;   // inner product over rows whose norms spread:
+    else if (errcol == 1 || (errcol < 0 && c->max_norm > 2.0f * c->mean_norm)) s->aug = 2;   // inner product over rows whose norms spread:
                                                                        // per-row error weights instead of c |q| max|x| for every row
     if (s->aug != 0 && errcol == 0) { s->aug = metric == 0 ? 1 : 0; }
     s->c_pair = s->aug != 0 ? fx::tc_c_pair(c->dim, s->aug) : 0.0;

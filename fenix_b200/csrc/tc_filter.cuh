@@ -95,6 +95,7 @@ struct TcKnobs {
   int fullk = 0;           // FENIX_TC_FULLK       multiply the zero padding of the last k-block too
   int no_rq = 0;           // FENIX_TC_NO_RQ       never take the resident-query kernel
   int slices = 0;          // FENIX_TC_SLICES      force the corpus slice count
+  int max_waves = 0;       // FENIX_TC_MAX_WAVES   units per worker at most (bounds the slice count and the candidate-list scratch)
   int order = -1;          // FENIX_TC_ORDER       unit order of the one-CTA streaming kernel (1 = query-tile major)
   int kp_list = 0;         // FENIX_TC_KP_LIST     candidates each (query, list) keeps at a selection
   int pre_wide = 1;        // FENIX_TC_PRE_WIDE    sample prepass also for wide rows at large batches (0: off)
@@ -128,6 +129,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_TC_FULLK") k->fullk = as_flag();
   else if (n == "FENIX_TC_NO_RQ") k->no_rq = as_flag();
   else if (n == "FENIX_TC_SLICES") k->slices = as_int(d.slices);
+  else if (n == "FENIX_TC_MAX_WAVES") k->max_waves = as_int(d.max_waves);
   else if (n == "FENIX_TC_ORDER") k->order = as_int(d.order);
   else if (n == "FENIX_TC_KP_LIST") k->kp_list = as_int(d.kp_list);
   else if (n == "FENIX_TC_PRE_WIDE") k->pre_wide = as_int(d.pre_wide);
@@ -152,7 +154,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
 }
 inline void tc_knobs_from_env(TcKnobs* k) {
   static const char* const names[] = {
-      "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
+      "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_MAX_WAVES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
       "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SMALL", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
       "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
       "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH"};
@@ -1766,7 +1768,8 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   // threshold to become selective.
   const int sms = pl.pair ? st->sm_count / 2 : st->sm_count;   // persistent workers: CTAs, or CTA pairs
   const int min_tiles = pre ? 4 : std::max(4, (8 * pl.kp + TC_BN - 1) / TC_BN) * (pl.rq ? 2 : 1);
-  const int s_cap = std::max(1, (TC_MAX_WAVES * sms) / n_qu);
+  const int max_waves = kn.max_waves > 0 ? kn.max_waves : TC_MAX_WAVES;
+  const int s_cap = std::max(1, (max_waves * sms) / n_qu);
   const int s_max = std::max(1, std::min(n_tiles_u / min_tiles, s_cap));
   double best = -1.0; int best_s = 1;
   for (int sl = 1; sl <= s_max; ++sl) {
@@ -1900,7 +1903,10 @@ inline bool tc_prepass_config(const TcState* st, const TcSearch& s, const TcPlan
   if (s.epi != 2) return false;                            // a row mask (predicate / IVF cells) of unknown selectivity: the
                                                            // sample says nothing about how many LIVE rows pass a threshold
   if (kn.pre == 0) return false;
-  double safety = 3.0;
+  // the threshold passes ~ safety x K' rows of the shard. Tensor-bound searches (wide rows, large batches) have epilogue
+  // time to spare for a few more hits, so they take a thinner sample: safety 8 -> every ~85th tile, 1.2 % of the scan
+  // instead of 3 % (profiles/r02_sweep_prepass.txt)
+  double safety = (wide && main_pl.n_qt > 3) ? 8.0 : 3.0;
   if (kn.pre_safety >= 1.0 && kn.pre_safety <= 64.0) safety = kn.pre_safety;
   const int tile_rows = main_pl.rq ? RQ_BN : TC_BN;
   // rank m of the sample statistic: P(threshold too tight for k rows) = P(Gamma(m) < m k / (safety K')). Wide rows pay

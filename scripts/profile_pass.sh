@@ -1,4 +1,5 @@
 #!/bin/bash
+# (filter launches alternate sample prepass / main pass: launch index 5 is the main pass of the third search)
 # One GPU call that refreshes the round's evidence: GPU tests, smoke, the default bench line, ncu captures of the dominant
 # kernels (C3 CTA-pair main pass, one C4 shard, C5 batch 8), the C1 Flight / latency numbers. Outputs under gpurun_out/.
 R=${1:-r02}
@@ -6,9 +7,9 @@ timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${R}_pytest_gpu.lo
 timeout 300 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${R}_smoke.log
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${R}_bench_default.json 2> gpurun_out/${R}_bench_default.err; echo "bench rc=$?"
 B="python bench.py --steps 2 --warmup 2 --no-also --no-cpu-baseline --no-parity"
-ncu --set full --clock-control none --import-source on -k "regex:filter_kernel<2, 1, 0, 1>" -s 2 -c 1 -o gpurun_out/${R}_prof_c3 $B > gpurun_out/${R}_ncu_c3.log 2>&1; echo "ncu c3 rc=$?"
-ncu --set full --clock-control none --import-source on -k "regex:rq_filter_kernel<2, 0>" -s 2 -c 1 -o gpurun_out/${R}_prof_c4s $B --config c4s > gpurun_out/${R}_ncu_c4s.log 2>&1; echo "ncu c4s rc=$?"
-ncu --set full --clock-control none --import-source on -k "regex:filter_kernel<2, 1, 0, 0>" -s 2 -c 1 -o gpurun_out/${R}_prof_c5_8 $B --config c5_8 > gpurun_out/${R}_ncu_c5_8.log 2>&1; echo "ncu c5_8 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:knn_tc_filter_kernel -s 5 -c 1 -o gpurun_out/${R}_prof_c3 $B > gpurun_out/${R}_ncu_c3.log 2>&1; echo "ncu c3 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:knn_rq_filter_kernel -s 5 -c 1 -o gpurun_out/${R}_prof_c4s $B --config c4s > gpurun_out/${R}_ncu_c4s.log 2>&1; echo "ncu c4s rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:knn_tc_filter_kernel -s 5 -c 1 -o gpurun_out/${R}_prof_c5_8 $B --config c5_8 > gpurun_out/${R}_ncu_c5_8.log 2>&1; echo "ncu c5_8 rc=$?"
 timeout 300 python scripts/bench_flight.py > gpurun_out/${R}_flight_c1.txt 2> gpurun_out/${R}_flight_c1.err; echo "flight rc=$?"
 timeout 300 python scripts/latency_c1.py --c5 > gpurun_out/${R}_latency_c1.txt 2>&1; echo "latency rc=$?"
 ls -la gpurun_out/${R}_*

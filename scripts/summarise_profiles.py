@@ -23,17 +23,23 @@ METRICS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
     "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
-    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__cluster_dim_x", "launch__cluster_size",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 # capture file -> (summary name, config key for ncu_traffic.json or None, note)
 CAPTURES = {
-    "r55_prof_c3.ncu-rep": ("r01_ncu_full_c3_main", "c3", "python bench.py --steps 3 --warmup 3 --no-cpu-baseline; main filter launch"),
-    "r55_prof_c4s.ncu-rep": ("r01_ncu_full_c4s_rq_main", "c4s", "python bench.py --config c4s ...; resident-query filter, main pass"),
-    "r77_prof_c2_rq.ncu-rep": ("r01_ncu_full_c2_rq_main", "c2", "python bench.py --config c2 ...; resident-query filter, main pass"),
-    "r77_prof_c2_finish.ncu-rep": ("r01_ncu_full_c2_finish", None, "python bench.py --config c2 ...; finish kernel of the main pass"),
-    "r55_prof_c5_8.ncu-rep": ("r01_ncu_full_c5_8", "c5_8", "python bench.py --config c5_8 ...; streaming filter, batch 8"),
+    # round 2 (the code at HEAD): scripts/profile_pass.sh
+    "r02_prof_c3.ncu-rep": ("r02_ncu_full_c3_pair_main", "c3", "python bench.py --steps 2 --warmup 2 ...; CTA-pair (cta_group::2) streaming filter, main pass (after the sample prepass)"),
+    "r02_prof_c3_eighth.ncu-rep": ("r02_ncu_full_c3_eighth_pair_main", None, "python bench.py --rows 1250000 ...: one 8-GPU shard of C3 on one GPU; CTA-pair streaming filter, main pass"),
+    "r02_prof_c4s.ncu-rep": ("r02_ncu_full_c4s_rq_main", "c4s", "python bench.py --config c4s ...; resident-query filter, main pass"),
+    "r02_prof_c5_8.ncu-rep": ("r02_ncu_full_c5_8", "c5_8", "python bench.py --config c5_8 ...; one-CTA streaming filter, batch 8, main pass"),
+    "r2i_c2_rq.ncu-rep": ("r02_ncu_full_c2_rq_main", "c2", "python bench.py --config c2 ...; resident-query filter, main pass"),
+    # round 2, experiments that decided the design (before the sample prepass became the default for wide rows)
+    "r2b_eighth_pair.ncu-rep": ("r02_ncu_full_c3_eighth_pair_noprepass", None, "one 8-GPU shard of C3, CTA-pair kernel, adaptive thresholds only (FENIX_TC_PRE_WIDE=0)"),
+    "r2b_eighth_one.ncu-rep": ("r02_ncu_full_c3_eighth_onecta_noprepass", None, "one 8-GPU shard of C3, one-CTA kernel (FENIX_TC_PAIR=0), adaptive thresholds only"),
+    "r2b_c3_pair.ncu-rep": ("r02_ncu_full_c3_pair_noprepass", None, "C3, CTA-pair kernel, adaptive thresholds only (FENIX_TC_PRE_WIDE=0)"),
 }
 
 
@@ -62,6 +68,9 @@ def main():
             wr = float(col["dram__bytes_write.sum"][1]) * UNIT[col["dram__bytes_write.sum"][0]]
             traffic[cfg] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                             "kernel": col["Kernel Name"][1], "capture": name + "_summary.csv"}
+    for _b in (1, 2, 4, 16, 32, 64):        # the same kernel and the same corpus pass at every small batch
+        if "c5_8" in traffic:
+            traffic.setdefault(f"c5_{_b}", dict(traffic["c5_8"], note="capture taken at batch 8"))
     with open(os.path.join(OUT, "ncu_traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1, sort_keys=True)
     print(json.dumps(traffic, indent=1))
