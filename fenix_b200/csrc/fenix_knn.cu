@@ -2,7 +2,8 @@
 //
 // Host side of the B200 exact k-NN path: device shard ownership, pinned staging, kernel
 // dispatch and the certificate / refinement tiers. Kernels live in exact_scan.cuh (fp64 CUDA-core
-// scan, merges, row norms) and tc_filter.cuh (tcgen05/TMEM filter kernels, prepass, finish + rerank).
+// scan, merges, row norms), tc_filter.cuh (tcgen05/TMEM filter kernels, prepass, finish + rerank) and direct_scan.cuh
+// (the single-launch latency path for a handful of queries over a small shard).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
@@ -27,6 +28,7 @@
 
 #include "../../include/fenix_knn.h"
 #include "exact_scan.cuh"
+#include "direct_scan.cuh"
 #include "tc_filter.cuh"
 
 // ----------------------------------------------------------------------------------------
@@ -110,6 +112,7 @@ struct fx_ctx {
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;   // exchange (all-gather + merge) of a sharded search
   DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref, d_maskn, d_floor, d_xchg, d_hdr;
   HostBuf h_q, h_rows, h_dist, h_flags;
+  unsigned int* d_ticket = nullptr;   // direct scan: "last CTA merges" counter (zero between launches)
   int* h_word = nullptr;           // pinned: [0] flagged-query count of the last main pass, [1..] gathered per-rank counts
   int64_t launches = 0;
   fx::TcState tc;                  // driver entry points / kernel attributes / tuning knobs of the TC path
@@ -237,6 +240,9 @@ extern "C" int fx_init(int device, fx_ctx** out) {
   FX_CUDA(cudaFuncSetAttribute(fx::exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  FX_CUDA(fx::direct_set_attributes());
+  FX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_ticket), 256));
+  FX_CUDA(cudaMemset(ctx->d_ticket, 0, 256));
   {
     std::string err;
     if (!fx::tc_init(&ctx->tc, ctx->sm_count, &err)) {
@@ -258,6 +264,7 @@ extern "C" int fx_shutdown(fx_ctx* ctx) {
   ctx->d_floor.release(); ctx->d_xchg.release(); ctx->d_hdr.release();
   ctx->h_q.release(); ctx->h_rows.release(); ctx->h_dist.release(); ctx->h_flags.release();
   if (ctx->h_word) cudaFreeHost(ctx->h_word);
+  if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_stop);
   cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
   cudaEventDestroy(ctx->ev_x0); cudaEventDestroy(ctx->ev_x1);
@@ -674,13 +681,23 @@ static int check_search_args(fx_corpus* c, const void* q, int64_t n_q, int metri
 //   search_settle   after the caller's ONE synchronisation: nothing to do when no certificate failed (the common
 //                   case); otherwise the re-run / refinement / scan tiers repair the flagged queries' results in place
 //                   and the caller repeats its copies.
+// The single-launch direct scan (direct_scan.cuh) takes exact searches of a handful of queries over a shard small enough
+// that reading its fp32 rows once beats the fixed cost of the tensor-core pipeline (FENIX_DIRECT, FENIX_DIRECT_MAX_MB).
+static fx::DirectPlan direct_plan_for(const fx_corpus* c, int64_t n_q, int k, int precision) {
+  const fx::TcKnobs& kn = c->ctx->tc.knobs;
+  if (kn.direct == 0 || precision != FX_PREC_FP32) return fx::DirectPlan{};
+  if (double(c->n) * c->pitch * 4.0 > double(kn.direct_mb) * 1048576.0) return fx::DirectPlan{};
+  return fx::direct_plan(c->n, c->pitch, n_q, k, c->ctx->sm_count);
+}
+
 struct SearchRun {
   bool tc = false;            // the tensor-core path ran (flags are meaningful)
-  int path = 0;               // 0 exact scan, 1 tensor-core TF32 filter, 2 tensor-core bf16 filter
+  int path = 0;               // 0 exact scan, 1 tensor-core TF32 filter, 2 tensor-core bf16 filter, 3 direct scan (one launch)
   fx::TcSearch s{};
   fx::TcLaunch L{};
   const float* d_q = nullptr; int64_t n_q = 0; int metric = 0, k = 0;
   const uint8_t* d_mask = nullptr; int64_t* d_out_rows = nullptr; float* d_out_dist = nullptr;
+  const float* inline_q = nullptr;   // set by the caller: HOST queries small enough to ride in the direct scan's kernel parameters
 };
 
 static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metric, int k, int precision,
@@ -691,7 +708,8 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
   ctx->h_word[0] = 0;
   const unsigned ev_flags = ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
   FX_CUDA(cudaEventRecordWithFlags(ctx->ev_start, ctx->stream, ev_flags));
-  const bool want_tc = precision != FX_PREC_EXACT_SCAN &&
+  const fx::DirectPlan dpl = direct_plan_for(c, n_q, k, precision);
+  const bool want_tc = !dpl.ok && precision != FX_PREC_EXACT_SCAN &&
                        fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q));
   if (c->n == 0) {
     // empty shard: all pads
@@ -700,6 +718,19 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
     ctx->launches++; c->stats.kernel_launches++;
     FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k0, ctx->stream, ev_flags));
     FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k1, ctx->stream, ev_flags));
+  } else if (dpl.ok) {
+    // one kernel: fp64 distances of every (live) row, per-CTA top-k, merge by the last CTA. d_out_* may be mapped pinned
+    // host memory (fx_search passes its staging buffers and, for small query blocks, the queries by value: no copies)
+    FX_TRY(ctx->d_partial.ensure(dpl.partial_bytes));
+    fx::DirectParams p{};
+    p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.row_base = c->row_base;
+    p.Q = d_q; p.n_q = int(n_q); p.metric = metric; p.k = k; p.mask = d_mask;
+    if (run->inline_q != nullptr) { p.Q = nullptr; std::memcpy(p.q_inline, run->inline_q, size_t(n_q) * c->dim * sizeof(float)); }
+    p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.ticket = ctx->d_ticket;
+    p.out_rows = d_out_rows; p.out_dist = d_out_dist;
+    FX_CUDA(fx::direct_launch(dpl, p, ctx->stream));
+    ctx->launches++; c->stats.kernel_launches++;
+    run->path = 3;
   } else if (want_tc) {
     fx::TcSearch& s = run->s;
     s = fx::TcSearch{};
@@ -847,7 +878,8 @@ static void search_account(fx_corpus* c, const SearchRun& run) {
   fx_ctx* ctx = c->ctx;
   float ms = 0.f, kms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
-  cudaEventElapsedTime(&kms, ctx->ev_k0, ctx->ev_k1);
+  if (run.path == 3) kms = ms;   // the direct scan is its one kernel (no inner events: they cost host time on the latency path)
+  else cudaEventElapsedTime(&kms, ctx->ev_k0, ctx->ev_k1);
   c->stats.last_search_ms = ms; c->stats.last_main_kernel_ms = kms; c->stats.last_path = run.path;
   c->stats.searches++; c->stats.queries += run.n_q;
 }
@@ -951,6 +983,34 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
   FX_TRY(ctx->d_q.ensure(q_bytes));
   FX_TRY(ctx->d_rows.ensure(r_bytes));
   FX_TRY(ctx->d_dist.ensure(d_bytes));
+  // ---- a handful of queries over a small shard: one launch. Small query blocks ride in the kernel parameters, the
+  // results are written straight to mapped pinned staging (cudaMallocHost memory is device-addressable under unified
+  // addressing): no H2D / D2H copies on the common single-query call ----
+  if (c->n > 0 && direct_plan_for(c, n_q, k, precision).ok) {
+    FX_TRY(ctx->h_rows.ensure(r_bytes));
+    FX_TRY(ctx->h_dist.ensure(d_bytes));
+    SearchRun run;
+    if (n_q * int64_t(c->dim) <= fx::DS_INLINE_FLOATS) {
+      run.inline_q = queries;
+    } else {
+      FX_TRY(ctx->h_q.ensure(q_bytes));
+      std::memcpy(ctx->h_q.p, queries, q_bytes);
+      FX_CUDA(cudaMemcpyAsync(ctx->d_q.p, ctx->h_q.p, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const uint8_t* d_mask = nullptr;
+    if (row_mask) {
+      FX_TRY(ctx->d_mask.ensure(size_t(c->n)));
+      FX_CUDA(cudaMemcpyAsync(ctx->d_mask.p, row_mask, size_t(c->n), cudaMemcpyHostToDevice, ctx->stream));
+      d_mask = static_cast<const uint8_t*>(ctx->d_mask.p);
+    }
+    FX_TRY(search_enqueue(c, static_cast<const float*>(ctx->d_q.p), n_q, metric, k, precision, d_mask,
+                          static_cast<int64_t*>(ctx->h_rows.p), static_cast<float*>(ctx->h_dist.p), &run));
+    FX_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
+    std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
+    search_account(c, run);
+    return FX_OK;
+  }
   // ---- small searches: replay (or capture) the whole call as one CUDA graph ----
   if (n_q <= GRAPH_MAX_Q && !row_mask && c->n > 0 && ctx->tc.knobs.graph != 0 && precision != FX_PREC_EXACT_SCAN &&
       fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q))) {

@@ -57,6 +57,9 @@ extern "C" {
  *   TF32 / BF16: the same tensor-core pass (TF32 over the fp32 rows / bf16 over the shadow) without
  *         slack or certificate; distances of the returned rows are still exact, membership is
  *         approximate (recall reported by bench.py). BF16 needs the shadow (FX_ESTATE otherwise).
+ *         A handful of queries (<= 8, k <= 128) over a small shard (fp32 rows <= FENIX_DIRECT_MAX_MB, default 256 MB)
+ *         skip all of that: ONE launch computes the fp64-accumulated distance of every row and selects (the latency
+ *         path; same distances bit for bit, FENIX_DIRECT=0 disables it).
  *   EXACT_SCAN: forces the fp64-accumulating CUDA-core scan kernel (checker / fallback path).
  */
 #define FX_PREC_FP32 0
@@ -84,7 +87,8 @@ typedef struct fx_stats {
   int64_t kernel_launches;   /* kernels of this library launched so far */
   double last_search_ms;     /* device time of the last search (CUDA events) */
   double last_main_kernel_ms;/* device time of the dominant kernel of the last search */
-  int32_t last_path;         /* 0 = exact scan, 1 = tcgen05 TF32 filter + rerank, 2 = tcgen05 bf16 filter + rerank */
+  int32_t last_path;         /* 0 = exact scan, 1 = tcgen05 TF32 filter + rerank, 2 = tcgen05 bf16 filter + rerank,
+                              * 3 = direct scan: one launch, fp64 distances of every row (<= 8 queries over a small shard) */
   int32_t last_variant;      /* tcgen05 paths: bit 0 = resident-query kernel (narrow rows; else the streaming kernel),
                               * bit 1 = thresholds seeded by the sample prepass, bit 2 = CTA-pair (cta_group::2) streaming kernel */
   double last_exchange_ms;   /* sharded searches: device time of all-gather + merge of the last search (CUDA events) */

@@ -36,17 +36,29 @@ def raw(i):
     c.search_raw(qs[i % 300].ctypes.data, 1, m, K, knn.PREC_FP32, out_rows.ctypes.data, out_dist.ctypes.data)
 
 
-for graph in (1, 0):
-    c.ctx.set_option("FENIX_GRAPH", graph)
-    print(f"--- CUDA graph replay of small searches: {'on' if graph else 'off'}")
+def report(title):
+    print(f"--- {title}")
     print("index.call select=[id]    ", timeit(lambda i: fio.index.call(root, None, "c1", "vector", qs[i % 300], metric="l2", select=["id"], maxval=K)))
     print("index.call default select ", timeit(lambda i: fio.index.call(root, None, "c1", "vector", qs[i % 300], metric="l2", maxval=K)))
     print("shard.search              ", timeit(lambda i: shard.search(qs[i % 300: i % 300 + 1], "l2", K)))
     print("fx_search (raw C ABI)     ", timeit(raw, 1000))
-    st = c.stats()
-    print(f"device time of the last search {st.last_search_ms * 1e3:.1f} us, filter kernel {st.last_main_kernel_ms * 1e3:.1f} us, "
-          f"variant {st.last_variant}, launches/search {st.kernel_launches and ''}")
+    st0 = c.stats(); raw(0); st = c.stats()
+    print(f"device time of the last search {st.last_search_ms * 1e3:.1f} us, main kernel {st.last_main_kernel_ms * 1e3:.1f} us, "
+          f"path {st.last_path}, variant {st.last_variant}, launches/search {st.kernel_launches - st0.kernel_launches}")
+
+
+# the library's own routing: a single query over a 51 MB shard is ONE launch (direct_scan.cuh, path 3)
+report("default routing (single-launch direct scan)")
+for b in (2, 4, 8):
+    o_r = np.empty((b, K), np.int64); o_d = np.empty((b, K), np.float32)
+    print(f"fx_search, {b} queries        ", timeit(lambda i: c.search_raw(qs[i % 290:].ctypes.data, b, m, K, knn.PREC_FP32, o_r.ctypes.data, o_d.ctypes.data), 500),
+          f" device {c.stats().last_search_ms * 1e3:.1f} us path {c.stats().last_path}")
+c.ctx.set_option("FENIX_DIRECT", 0)
+for graph in (1, 0):
+    c.ctx.set_option("FENIX_GRAPH", graph)
+    report(f"FENIX_DIRECT=0: tensor-core pipeline, CUDA graph replay of small searches {'on' if graph else 'off'}")
 c.ctx.set_option("FENIX_GRAPH", None)
+c.ctx.set_option("FENIX_DIRECT", None)
 shard.release()
 
 if "--c5" in sys.argv:

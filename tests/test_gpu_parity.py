@@ -19,7 +19,19 @@ pytestmark = pytest.mark.gpu
 def client_root(served):
     return served[3]
 
-PRECISIONS = {"fp32": knn.PREC_FP32, "scan": knn.PREC_EXACT_SCAN}
+# "fp32": the library's own routing (a handful of queries over a small shard take the single-launch direct scan);
+# "fp32_tc": the same exact mode with the direct scan switched off, so the tensor-core path answers; "scan": the checker
+PRECISIONS = {"fp32": knn.PREC_FP32, "fp32_tc": knn.PREC_FP32, "scan": knn.PREC_EXACT_SCAN}
+
+
+def search_as(ctx, c, prec, queries, metric, k, **kw):
+    if prec != "fp32_tc":
+        return c.search(queries, metric, k, PRECISIONS[prec], **kw)
+    ctx.set_option("FENIX_DIRECT", 0)
+    try:
+        return c.search(queries, metric, k, PRECISIONS[prec], **kw)
+    finally:
+        ctx.set_option("FENIX_DIRECT", None)
 
 
 @pytest.fixture(scope="module")
@@ -45,7 +57,7 @@ def test_topk_matches_live_reference_outputs(ctx, case, metric, prec):
     g = load_golden(case)
     corpus, queries, k = g["corpus"], g["queries"], int(g["k"])
     c = make_corpus(ctx, corpus)
-    rows, dist = c.search(queries, metric, k, PRECISIONS[prec])
+    rows, dist = search_as(ctx, c, prec, queries, metric, k)
     for qi in range(len(queries)):
         assert_same_neighbours(rows[qi], dist[qi], g[f"{metric}:{qi}:id"], g[f"{metric}:{qi}:dist"],
                                corpus, queries[qi], metric)
@@ -90,7 +102,7 @@ def test_seeded_parity_with_oracle(ctx, shape, metric, prec):
     corpus = rng.standard_normal((n, d), dtype=np.float32)
     queries = rng.standard_normal((nq, d), dtype=np.float32)
     c = make_corpus(ctx, corpus)
-    rows, dist = c.search(queries, metric, k, PRECISIONS[prec])
+    rows, dist = search_as(ctx, c, prec, queries, metric, k)
     table = table_of(corpus, 4096)
     for qi in range(0, nq, max(1, nq // 6)):  # the oracle is O(N*D) per query
         ref_rows, ref_dist = search_rows(table, "vector", queries[qi], metric, k)
@@ -108,7 +120,7 @@ def test_duplicates_are_ordered_by_row(ctx, prec):
     corpus[1000:1400] = corpus[17]  # 400 copies of the winner
     c = make_corpus(ctx, corpus)
     for metric in ("l2", "cosine", "dot"):
-        rows, dist = c.search(corpus[17], metric, 10, PRECISIONS[prec])
+        rows, dist = search_as(ctx, c, prec, corpus[17], metric, 10)
         want_rows, want_dist = brute_force_f64(corpus, corpus[17], metric, 10)
         assert np.array_equal(rows, want_rows), metric
         np.testing.assert_allclose(dist, want_dist, rtol=2e-6, atol=1e-6)
@@ -573,6 +585,7 @@ def test_small_searches_replay_a_cuda_graph(ctx, metric, nq):
     n, d, k = 100_000, 128, 10
     corpus = rng.standard_normal((n, d), dtype=np.float32)
     c = make_corpus(ctx, corpus)
+    ctx.set_option("FENIX_DIRECT_MAX_MB", 16)   # (a shard this small would take the direct scan: no graph, nothing to replay)
     launches = []
     for call in range(6):
         q = rng.standard_normal((nq, d), dtype=np.float32)
@@ -596,6 +609,7 @@ def test_small_searches_replay_a_cuda_graph(ctx, metric, nq):
     for _ in range(3):
         r1, d1 = c.search(q, metric, k)
         assert np.array_equal(r0, r1) and np.array_equal(d0, d1)
+    ctx.set_option("FENIX_DIRECT_MAX_MB", None)
     c.close()
 
 
@@ -605,7 +619,7 @@ def test_each_shadow_is_built_by_the_first_search_that_streams_it(ctx):
     rng = np.random.default_rng(8)
     n, d = 16_384, 128
     corpus = rng.standard_normal((n, d), dtype=np.float32)
-    queries = rng.standard_normal((8, d), dtype=np.float32)
+    queries = rng.standard_normal((9, d), dtype=np.float32)    # (<= 8 queries would take the direct scan: no shadow at all)
     c = make_corpus(ctx, corpus)
     rows_bytes = c.stats().device_bytes
     assert rows_bytes == n * (d + 2) * 4                       # rows + the two cached norm terms, no shadow yet
@@ -619,6 +633,83 @@ def test_each_shadow_is_built_by_the_first_search_that_streams_it(ctx):
     assert plain_shadow == n * (d + 64) * 2                    # data blocks + one block per tile for the augmented columns
     c.search(queries, "l2", 5)
     assert c.stats().device_bytes == rows_bytes + norm_shadow + plain_shadow
+    c.close()
+
+
+# ---- the latency path: single-launch direct scan (direct_scan.cuh) ------------------------------------------
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+@pytest.mark.parametrize("shape", [(100_000, 128, 1, 10), (100_000, 128, 8, 10), (20_011, 100, 3, 37), (5_000, 768, 5, 128),
+                                   (70_000, 7, 2, 5), (333, 36, 4, 64), (40, 24, 2, 64), (1, 16, 1, 3)])
+def test_direct_scan_equals_scan_tensor_path_and_oracle(ctx, shape, metric):
+    """<= 8 queries over a small shard are ONE launch (last_path 3): ids and distances bit-equal to the fp64 scan and to
+    the tensor-core path (same fp64 summation order as its rerank), neighbours as the oracle's."""
+    n, d, nq, k = shape
+    rng = np.random.default_rng(n * 7 + d)
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    queries = rng.standard_normal((nq, d), dtype=np.float32)
+    c = make_corpus(ctx, corpus)
+    before = c.stats().kernel_launches
+    rows, dist = c.search(queries, metric, k)
+    st = c.stats()
+    assert st.last_path == 3 and st.kernel_launches - before == 1, (st.last_path, st.kernel_launches - before)
+    rows_s, dist_s = c.search(queries, metric, k, knn.PREC_EXACT_SCAN)
+    assert c.stats().last_path == 0
+    assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
+    rows_t, dist_t = search_as(ctx, c, "fp32_tc", queries, metric, k)
+    assert c.stats().last_path != 3
+    assert np.array_equal(rows, rows_t) and np.array_equal(dist, dist_t)
+    if n >= k:
+        want_rows, want_dist = brute_force_f64(corpus, queries, metric, k)
+        assert np.array_equal(rows, want_rows)
+        table = table_of(corpus, 4096)
+        ref_rows, ref_dist = search_rows(table, "vector", queries[nq - 1], metric, k)
+        assert_same_neighbours(rows[nq - 1], dist[nq - 1], ref_rows, ref_dist, corpus, queries[nq - 1], metric)
+    else:
+        assert (rows[:, n:] == -1).all() and np.isinf(dist[:, n:]).all() and (rows[:, :n] >= 0).all()
+    c.close()
+
+
+def test_direct_scan_masks_duplicates_and_trims(ctx):
+    """Row mask, ties broken by row, and a shard large enough per CTA that the candidate buffers are cut back: 300k rows /
+    148 CTAs = 2k rows each, ordered so that the rows get closer to query 0 as the row number grows - every row passes the
+    running threshold, the worst case for a running top-k."""
+    rng = np.random.default_rng(21)
+    n, d, k = 300_000, 32, 100
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    queries = rng.standard_normal((3, d), dtype=np.float32)
+    far_first = np.argsort(-np.linalg.norm(corpus.astype(np.float64) - queries[0].astype(np.float64), axis=1), kind="stable")
+    corpus = np.ascontiguousarray(corpus[far_first])
+    corpus[1000:1400] = corpus[-1]                      # 400 copies of the best row
+    c = make_corpus(ctx, corpus)
+    for metric in ("l2", "dot"):
+        rows, dist = c.search(queries, metric, k)
+        assert c.stats().last_path == 3
+        rows_s, dist_s = c.search(queries, metric, k, knn.PREC_EXACT_SCAN)
+        assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s), metric
+    mask = (rng.random(n) < 0.05).astype(np.uint8)
+    mask[:5000] = 0
+    rows, dist = c.search(queries, "l2", k, row_mask=mask)
+    assert c.stats().last_path == 3 and mask[rows].all()
+    rows_s, dist_s = c.search(queries, "l2", k, knn.PREC_EXACT_SCAN, row_mask=mask)
+    assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
+    few = np.zeros(n, np.uint8)
+    few[[5, 77, 190_000]] = 1
+    rows, dist = c.search(queries[:1], "l2", 10, row_mask=few)
+    assert sorted(rows[0, :3].tolist()) == [5, 77, 190_000] and (rows[0, 3:] == -1).all() and np.isinf(dist[0, 3:]).all()
+    # knobs: off, and the size bound
+    ctx.set_option("FENIX_DIRECT", 0)
+    c.search(queries, "l2", k)
+    assert c.stats().last_path != 3
+    ctx.set_option("FENIX_DIRECT", None)
+    ctx.set_option("FENIX_DIRECT_MAX_MB", 8)
+    c.search(queries, "l2", k)
+    assert c.stats().last_path != 3
+    ctx.set_option("FENIX_DIRECT_MAX_MB", None)
+    # nine queries, or k > 128: the other paths
+    c.search(np.repeat(queries, 3, axis=0), "l2", k)
+    assert c.stats().last_path != 3
+    c.search(queries, "l2", 129)
+    assert c.stats().last_path != 3
     c.close()
 
 
