@@ -2,27 +2,31 @@
 //
 // A single query against a 100k x 128 shard (BASELINE C1) is 51 MB of fp32 rows that live in L2: the tensor-core
 // pipeline (prep, sample prepass, threshold pick, filter, finish: six launches, ~55 us of device time for ~12 us of
-// filter) is all fixed cost there. This kernel reads the fp32 rows themselves once (coalesced, eight lanes per row),
-// accumulates q.x and |x|^2 in fp64 from exact fp32 products - the arithmetic of the finish kernel's rerank, in the
-// same summation order, so the distances are bit-identical to the tensor-core path's - collects (distance, row) keys
-// per CTA in shared memory, selects each CTA's k smallest with warp-level sorted lists held in registers (shuffle
-// bitonic networks, a handful of barriers; block-wide shared-memory bitonic sorts measured 17 us here), and the last
-// CTA to finish joins the per-CTA lists the same way and writes the result. No shadow, no certificate, no second launch. A small query block (<= 896 floats) travels in the kernel
+// filter) is all fixed cost there. This kernel reads the fp32 rows themselves once (coalesced, eight lanes per row,
+// three row chunks in flight per lane), accumulates q.x and |x|^2 in fp64 from exact fp32 products - the arithmetic of
+// the finish kernel's rerank, in the same summation order, so the distances are bit-identical to the tensor-core
+// path's - and parks the raw sums of up to DS_CAP_STEPS * 64 rows in shared memory. A flush turns them into (distance,
+// row) keys with every lane busy (one row per thread), and every warp folds its 32 keys into a sorted list of its 32 R
+// best held in registers (shuffle bitonic networks: no atomics, no key buffers, no thresholds to maintain). A tree over
+// the warps' lists gives the CTA's k best; the last CTA to finish joins the per-CTA lists the same way and writes the
+// result. No shadow, no certificate, no second launch. A small query block (<= 896 floats) travels in the kernel
 // parameters and the results may be written straight to mapped pinned host memory, so fx_search issues no copies.
-// (Reading the queries from mapped host memory instead was measured: every CTA fetches them over PCIe, ~30 us per query.) Replaces index.py:162-168 (distance column + select_k + take indices) like the rest
-// of the library; HBM/L2-bound byte work, deliberately kept off the tensor cores.
+// Measured dead ends (B200, C1): queries read from mapped host memory (every CTA fetches them over PCIe: ~30 us per
+// query), block-wide shared-memory bitonic sorts (17 us), finishing each row inside the scan loop (a sqrt + append chain
+// per step that four lanes of 32 execute: 11-15 us of scan).
+// Replaces index.py:162-168 (distance column + select_k + take indices) like the rest of the library; HBM/L2-bound
+// byte work, deliberately kept off the tensor cores.
 #pragma once
 #include "common.cuh"
 #include "exact_scan.cuh"
 
 namespace fx {
 
-constexpr int DS_THREADS = 512;          // 16 warps: 64 rows in flight per CTA and load round
+constexpr int DS_THREADS = 512;          // 16 warps: 64 rows per CTA and step, three steps in flight
 constexpr int DS_MAX_Q = 8;              // queries per launch
 constexpr int DS_MAX_K = 128;
-constexpr int DS_BUF = 1024;             // candidate keys per (CTA, query) between trims
-constexpr int DS_ROWS_PER_STEP = (DS_THREADS / 8) * 2;   // 8 lanes per row, two rows per lane group and step
-constexpr int DS_CHECK_STEPS = 4;        // steps between overflow checks: 4 * 128 = 512 appends at most, BUF - K >= 896
+constexpr int DS_ROWS_PER_STEP = DS_THREADS / 8;         // 8 lanes per row, one row per lane group and step
+constexpr int DS_CAP_STEPS = 16;         // steps whose raw sums are parked in shared memory between flushes (at most)
 constexpr int DS_INLINE_FLOATS = 896;    // query floats carried in the kernel parameters (3.5 KB of the 4 KB parameter space)
 
 struct DirectParams {
@@ -32,7 +36,9 @@ struct DirectParams {
   const uint8_t* mask;       // [n_rows] or null
   uint64_t* partial;         // [gridDim.x][n_q][k] sorted keys of every CTA
   unsigned int* ticket;      // zero on entry; the last CTA leaves it zero again
+  int cap_steps;             // steps between flushes (1 .. DS_CAP_STEPS; shared-memory budget)
   int64_t* out_rows; float* out_dist;   // [n_q][k]; device memory or mapped pinned host memory
+  unsigned long long* dbg;   // FENIX_DEBUG_DIRECT: globaltimer stamps ([0..7] phases of the last CTA, [8 + cta] end of each CTA's scan) or null
   float q_inline[DS_INLINE_FLOATS];
 };
 
@@ -87,197 +93,287 @@ __device__ __forceinline__ void warp_merge_keep_low(uint64_t (&best)[R], const u
   warp_stage<R, 32 * R, 16 * R>(best, lane);
 }
 
-// The CTA's 32 R smallest keys of `cnt` keys, sorted, left in lists[0, 32 R). get(i) returns key i. Every warp sorts
-// chunks of 32 R keys in registers and folds them into its running best list; a tree over the warps' lists (shared
-// memory, log2(warps) barriers) joins them. All threads of the CTA call it.
-template <int R, typename Get>
-__device__ __forceinline__ void cta_select(Get get, int cnt, uint64_t* lists) {
+// Tree over the warps' sorted lists (wl[warp][32 R], shared memory): after log2(warps) rounds wl[0] holds the CTA's
+// 32 R smallest keys, sorted. All threads of the CTA call it (barriers inside); it ends with a barrier.
+template <int R>
+__device__ __forceinline__ void cta_join_lists(uint64_t* wl) {
   constexpr int L = 32 * R;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  uint64_t best[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) best[r] = KEY_PAD;
-  for (int c0 = warp * L; c0 < cnt; c0 += n_warps * L) {
-    uint64_t v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { const int i = c0 + r * 32 + lane; v[r] = i < cnt ? get(i) : KEY_PAD; }
-    warp_sort<R>(v, lane);
-    warp_merge_keep_low<R>(best, v, lane);
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) lists[warp * L + r * 32 + lane] = best[r];
-  __syncthreads();
   for (int span = 1; span < n_warps; span <<= 1) {
     if ((warp & (2 * span - 1)) == 0 && warp + span < n_warps) {
-      uint64_t v[R];
+      uint64_t best[R], v[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = lists[(warp + span) * L + r * 32 + lane];
+      for (int r = 0; r < R; ++r) { best[r] = wl[warp * L + r * 32 + lane]; v[r] = wl[(warp + span) * L + r * 32 + lane]; }
       warp_merge_keep_low<R>(best, v, lane);
 #pragma unroll
-      for (int r = 0; r < R; ++r) lists[warp * L + r * 32 + lane] = best[r];
+      for (int r = 0; r < R; ++r) wl[warp * L + r * 32 + lane] = best[r];
     }
     __syncthreads();
   }
 }
 
-template <int NQ, int R>
+__device__ __forceinline__ unsigned long long ds_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// QREG (one query, rows of <= 128 floats): the lane's sixteen query values live in registers, the multiply loop reads
+// no shared memory at all.
+template <int NQ, int R, bool QREG>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 knn_direct_kernel(DirectParams p) {
+  unsigned long long t_start = 0, t_staged = 0, t_scanned = 0, t_published = 0;
+  if (p.dbg != nullptr) t_start = ds_now();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // double qs[NQ][pitch] | u64 buf[NQ][DS_BUF] | u64 lists[warps][32 R]
+  // double qs[NQ][pitch_q] (rows zero-padded to whole 128-float chunks) | u64 wl[NQ][warps][32 R] (the warps' sorted
+  // lists) | double sums[cap_rows][NQ + 1] (|x|^2, q.x per query) | int rowid[cap_rows] (-1: masked / past the end)
+  constexpr int L = 32 * R;
+  constexpr int NW = DS_THREADS / 32;
+  const int pitch_q = (p.pitch + 127) & ~127;
+  const int cap_rows = p.cap_steps * DS_ROWS_PER_STEP;
   double* qs = reinterpret_cast<double*>(smem_raw);
-  uint64_t* buf = reinterpret_cast<uint64_t*>(qs + size_t(NQ) * p.pitch);
-  uint64_t* lists = buf + size_t(NQ) * DS_BUF;
+  uint64_t* wl = reinterpret_cast<uint64_t*>(qs + size_t(NQ) * pitch_q);
+  double* sums = reinterpret_cast<double*>(wl + size_t(NQ) * NW * L);
+  int* rowid = reinterpret_cast<int*>(sums + size_t(cap_rows) * (NQ + 1));
   __shared__ double s_qq[NQ];
-  __shared__ uint64_t s_tau[NQ];
-  __shared__ int s_cnt[NQ];
   __shared__ unsigned int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sub = lane & 7, grp = lane >> 3;
+  // lane = grp + 4 * sub: row `grp` of the warp's four, float4 slot `sub` of eight. A quarter-warp (the unit a 128-bit
+  // shared-memory load is served in) then reads TWO query addresses, 64 contiguous bytes, instead of eight 32 B apart
+  // (sub-major lanes: 8 wavefronts per load, the query reads alone cost ~6 us per query on C1).
+  const int grp = lane & 3, sub = lane >> 2;
 
   for (int q = 0; q < NQ; ++q) {
-    for (int d = tid; d < p.pitch; d += DS_THREADS) {
+    for (int d = tid; d < pitch_q; d += DS_THREADS) {
       float v = 0.f;
       if (q < p.n_q && d < p.dim) v = p.Q != nullptr ? p.Q[size_t(q) * p.dim + d] : p.q_inline[q * p.dim + d];
-      qs[size_t(q) * p.pitch + d] = double(v);
+      qs[size_t(q) * pitch_q + d] = double(v);
     }
   }
-  if (tid < NQ) { s_cnt[tid] = 0; s_tau[tid] = KEY_PAD; }
+  for (int i = tid; i < NQ * NW * L; i += DS_THREADS) wl[i] = KEY_PAD;
   __syncthreads();
   if (warp < NQ) {   // |q|^2, summed as the finish kernel sums it (lane-strided, xor tree)
     double s = 0.0;
-    const double* qv = qs + size_t(warp) * p.pitch;
+    const double* qv = qs + size_t(warp) * pitch_q;
     for (int d = lane; d < p.pitch; d += 32) s = fma(qv[d], qv[d], s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) s_qq[warp] = s;
   }
   __syncthreads();
+  if (p.dbg != nullptr) t_staged = ds_now();
 
+  // The scan is a stream of work items (row of this lane group, chunk of 128 floats of that row): every lane holds four
+  // float4 of the item, three items rotate through registers so that the loads of items t + 1 and t + 2 are in flight
+  // while item t is multiplied. Summation order per accumulator = the finish kernel's: j = sub, sub + 8, ... then the xor
+  // tree over the 8 lanes.
   const int n4 = p.pitch >> 2;
+  const int C = (n4 + 31) >> 5;                       // chunks per row
   const int64_t n_steps = (p.n_rows + DS_ROWS_PER_STEP - 1) / DS_ROWS_PER_STEP;
-  int since_check = 0;
-  for (int64_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
-    // rows of this lane group: two of the warp's eight
-    const int64_t r0 = step * DS_ROWS_PER_STEP + warp * 8 + grp, r1 = r0 + 4;
-    bool live0 = r0 < p.n_rows, live1 = r1 < p.n_rows;
-    if (p.mask != nullptr) { live0 = live0 && p.mask[r0] != 0; live1 = live1 && p.mask[r1] != 0; }
-    const float4* x0p = reinterpret_cast<const float4*>(p.X + size_t(live0 ? r0 : 0) * p.pitch);
-    const float4* x1p = reinterpret_cast<const float4*>(p.X + size_t(live1 ? r1 : 0) * p.pitch);
-    double xx0 = 0.0, xx1 = 0.0, qx0[NQ], qx1[NQ];
+  const int my_steps = int64_t(blockIdx.x) < n_steps ? int((n_steps - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  const int total = my_steps * C;
+  int parked = 0;                                     // steps parked in `sums` since the last flush
+  double xx = 0.0, qx[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { qx0[q] = 0.0; qx1[q] = 0.0; }
-    if (__any_sync(0xffffffffu, live0 || live1)) {
-#pragma unroll 4
-      for (int j = sub; j < n4; j += 8) {
-        const float4 a = live0 ? __ldg(x0p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 b = live1 ? __ldg(x1p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const double a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w, b0 = b.x, b1 = b.y, b2 = b.z, b3 = b.w;
-        xx0 = fma(a0, a0, xx0); xx1 = fma(b0, b0, xx1);
-        xx0 = fma(a1, a1, xx0); xx1 = fma(b1, b1, xx1);
-        xx0 = fma(a2, a2, xx0); xx1 = fma(b2, b2, xx1);
-        xx0 = fma(a3, a3, xx0); xx1 = fma(b3, b3, xx1);
+  for (int q = 0; q < NQ; ++q) qx[q] = 0.0;
+  double qreg[QREG ? 16 : 1];
+  if constexpr (QREG) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const double2* qp = reinterpret_cast<const double2*>(qs + size_t(q) * p.pitch + 4 * j);
-          const double2 u = qp[0], v = qp[1];
-          qx0[q] = fma(a0, u.x, qx0[q]); qx1[q] = fma(b0, u.x, qx1[q]);
-          qx0[q] = fma(a1, u.y, qx0[q]); qx1[q] = fma(b1, u.y, qx1[q]);
-          qx0[q] = fma(a2, v.x, qx0[q]); qx1[q] = fma(b2, v.x, qx1[q]);
-          qx0[q] = fma(a3, v.y, qx0[q]); qx1[q] = fma(b3, v.y, qx1[q]);
-        }
-      }
+    for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        xx0 += __shfl_xor_sync(0xffffffffu, xx0, o); xx1 += __shfl_xor_sync(0xffffffffu, xx1, o);
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          qx0[q] += __shfl_xor_sync(0xffffffffu, qx0[q], o); qx1[q] += __shfl_xor_sync(0xffffffffu, qx1[q], o);
-        }
-      }
-      // every lane of a group holds the group's sums: lane `sub` finishes query `sub` (all lanes busy at NQ = 8)
-      if (sub < p.n_q) {
-        double d0 = qx0[0], d1 = qx1[0];
-#pragma unroll
-        for (int q = 1; q < NQ; ++q) { if (sub == q) { d0 = qx0[q]; d1 = qx1[q]; } }
-        const uint64_t tau = s_tau[sub];
-        const double qq = s_qq[sub];
-        if (live0) {
-          const uint64_t key = make_key(finish_distance(p.metric, qq, xx0, d0), uint32_t(r0));
-          if (key < tau) buf[size_t(sub) * DS_BUF + atomicAdd(&s_cnt[sub], 1)] = key;
-        }
-        if (live1) {
-          const uint64_t key = make_key(finish_distance(p.metric, qq, xx1, d1), uint32_t(r1));
-          if (key < tau) buf[size_t(sub) * DS_BUF + atomicAdd(&s_cnt[sub], 1)] = key;
-        }
-      }
-    }
-    if (++since_check < DS_CHECK_STEPS) continue;
-    since_check = 0;
-    // a buffer that the next DS_CHECK_STEPS steps could overflow is cut back to its 32 R (>= k) best, whose k-th key
-    // becomes the admission threshold (a CTA sees n / gridDim rows: C1 never gets here)
-    __syncthreads();
-    unsigned need = 0;
-    for (int q = 0; q < p.n_q; ++q) need |= (s_cnt[q] > DS_BUF - DS_CHECK_STEPS * DS_ROWS_PER_STEP) ? (1u << q) : 0u;
-    __syncthreads();
-    for (int q = 0; q < p.n_q; ++q) {
-      if (!(need >> q & 1u)) continue;
-      const int c = s_cnt[q];
-      uint64_t* b = buf + size_t(q) * DS_BUF;
-      cta_select<R>([b](int i) { return b[i]; }, c, lists);
-      for (int i = tid; i < p.k; i += DS_THREADS) b[i] = lists[i];
-      if (tid == 0) { s_cnt[q] = min(c, p.k); s_tau[q] = (c >= p.k) ? lists[p.k - 1] : KEY_PAD; }
-      __syncthreads();
+      for (int e = 0; e < 4; ++e) qreg[4 * u + e] = qs[4 * (sub + 8 * u) + e];
     }
   }
-  __syncthreads();
+
+  auto row_of = [&](int st) { return (int64_t(blockIdx.x) + int64_t(st) * gridDim.x) * DS_ROWS_PER_STEP + warp * 4 + grp; };
+  auto load = [&](float4 (&x)[4], bool& live, int st, int ch) {
+    const int64_t row = row_of(st);
+    live = st < my_steps && row < p.n_rows;
+    if (live && p.mask != nullptr) live = p.mask[row] != 0;
+    const float4* xp = reinterpret_cast<const float4*>(p.X + size_t(live ? row : 0) * p.pitch);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = ch * 32 + sub + 8 * u;
+      x[u] = (live && j < n4) ? __ldg(xp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  // parked sums -> keys (one row per thread, every lane busy), every warp folds its 32 R keys into its sorted list
+  auto flush = [&](int n_parked_steps) {
+    __syncthreads();
+    const int n_slots = n_parked_steps * DS_ROWS_PER_STEP;
+    for (int q = 0; q < p.n_q; ++q) {
+      uint64_t best[R];
+      uint64_t* mine = wl + (size_t(q) * NW + warp) * L;
+#pragma unroll
+      for (int r = 0; r < R; ++r) best[r] = mine[r * 32 + lane];
+      const double qq = s_qq[q];
+      for (int base = warp * L; base < n_slots; base += NW * L) {
+        uint64_t v[R];
+        bool any = false;
+        const uint64_t worst = __shfl_sync(0xffffffffu, best[R - 1], 31);   // the list's largest entry
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          // (no divergence around the distance arithmetic: dead slots compute on slot 0 and are discarded)
+          const int slot = base + r * 32 + lane;
+          const bool in = slot < n_slots;
+          const int sl = in ? slot : 0;
+          const int row = rowid[sl];
+          const uint64_t key = make_key(finish_distance(p.metric, qq, sums[size_t(sl) * (NQ + 1)], sums[size_t(sl) * (NQ + 1) + 1 + q]), uint32_t(row));
+          v[r] = (in && row >= 0) ? key : KEY_PAD;
+          any = any || v[r] < worst;
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, any)) continue;
+        warp_sort<R>(v, lane);
+        warp_merge_keep_low<R>(best, v, lane);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) mine[r * 32 + lane] = best[r];
+    }
+    __syncthreads();
+  };
+  auto compute = [&](const float4 (&x)[4], bool live, int st, int ch) {
+    if (__any_sync(0xffffffffu, live)) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = ch * 32 + sub + 8 * u;           // (j >= n4: x is zero, the query row is zero-padded to whole chunks)
+        const double a0 = x[u].x, a1 = x[u].y, a2 = x[u].z, a3 = x[u].w;
+        xx = fma(a0, a0, xx); xx = fma(a1, a1, xx); xx = fma(a2, a2, xx); xx = fma(a3, a3, xx);
+        if constexpr (QREG) {
+          qx[0] = fma(a0, qreg[4 * u], qx[0]); qx[0] = fma(a1, qreg[4 * u + 1], qx[0]);
+          qx[0] = fma(a2, qreg[4 * u + 2], qx[0]); qx[0] = fma(a3, qreg[4 * u + 3], qx[0]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const double2* qp = reinterpret_cast<const double2*>(qs + size_t(q) * pitch_q + 4 * j);
+            const double2 v0 = qp[0], v1 = qp[1];
+            qx[q] = fma(a0, v0.x, qx[q]); qx[q] = fma(a1, v0.y, qx[q]); qx[q] = fma(a2, v1.x, qx[q]); qx[q] = fma(a3, v1.y, qx[q]);
+          }
+        }
+      }
+    }
+    if (ch != C - 1) return;
+    // the row is complete: reduce over the group's 8 lanes and park the raw sums (lane `sub` stores q.x of query `sub`)
+    const int slot = parked * DS_ROWS_PER_STEP + warp * 4 + grp;
+    if (__any_sync(0xffffffffu, live)) {
+#pragma unroll
+      for (int o = 16; o > 2; o >>= 1) {   // sub ^ 4, sub ^ 2, sub ^ 1: the finish kernel's tree
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) qx[q] += __shfl_xor_sync(0xffffffffu, qx[q], o);
+      }
+      double dq = qx[0];
+#pragma unroll
+      for (int q = 1; q < NQ; ++q) { if (sub == q) dq = qx[q]; }
+      if (sub < NQ) sums[size_t(slot) * (NQ + 1) + 1 + sub] = dq;
+      if (sub == 0) sums[size_t(slot) * (NQ + 1)] = xx;
+    }
+    if (sub == 0) rowid[slot] = live ? int(row_of(st)) : -1;
+    xx = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) qx[q] = 0.0;
+    if (++parked == p.cap_steps) { flush(parked); parked = 0; }
+  };
+  {
+    float4 x0[4], x1[4], x2[4];
+    bool l0 = false, l1 = false, l2 = false;
+    int ls = 0, lc = 0, cs = 0, cc = 0;                 // next item to load / to compute: (step, chunk)
+    auto adv = [&](int& st, int& ch) { if (++ch == C) { ch = 0; ++st; } };
+    load(x0, l0, ls, lc); adv(ls, lc);
+    load(x1, l1, ls, lc); adv(ls, lc);
+    for (int t = 0; t < total; t += 3) {
+      load(x2, l2, ls, lc); adv(ls, lc);
+      compute(x0, l0, cs, cc); adv(cs, cc);
+      if (t + 1 < total) {
+        load(x0, l0, ls, lc); adv(ls, lc);
+        compute(x1, l1, cs, cc); adv(cs, cc);
+      }
+      if (t + 2 < total) {
+        load(x1, l1, ls, lc); adv(ls, lc);
+        compute(x2, l2, cs, cc); adv(cs, cc);
+      }
+    }
+  }
+  if (p.dbg != nullptr) { t_scanned = ds_now(); if (tid == 0) p.dbg[8 + blockIdx.x] = t_scanned; }
+  flush(parked);   // (barriers on both sides; also when nothing is parked)
 
   // ---- this CTA's k best per query, published ----
   for (int q = 0; q < p.n_q; ++q) {
-    const uint64_t* b = buf + size_t(q) * DS_BUF;
-    cta_select<R>([b](int i) { return b[i]; }, s_cnt[q], lists);
-    for (int i = tid; i < p.k; i += DS_THREADS) p.partial[(size_t(blockIdx.x) * p.n_q + q) * p.k + i] = lists[i];
-    __syncthreads();
+    uint64_t* w0 = wl + size_t(q) * NW * L;
+    cta_join_lists<R>(w0);
+    for (int i = tid; i < p.k; i += DS_THREADS) p.partial[(size_t(blockIdx.x) * p.n_q + q) * p.k + i] = w0[i];
   }
   __threadfence();
   __syncthreads();
+  if (p.dbg != nullptr) t_published = ds_now();
   if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
   if (s_last == 0u) return;
   __threadfence();
+  unsigned long long t_ticket = 0, t_joined = 0;
+  if (p.dbg != nullptr) t_ticket = ds_now();
 
-  // ---- the last CTA joins gridDim.x lists of k keys per query ----
-  const int total = int(gridDim.x) * p.k;
+  // ---- the last CTA joins gridDim.x sorted lists of k keys per query: every warp folds chunks of 32 R keys (the next
+  // chunk's loads in flight while one is sorted), then the same tree ----
+  const int n_keys = int(gridDim.x) * p.k;
+  const unsigned k_magic = p.k > 1 ? unsigned((0x100000000ull + unsigned(p.k) - 1u) / unsigned(p.k)) : 0u;   // i / k = umulhi(i, magic), i < 2^15
   for (int q = 0; q < p.n_q; ++q) {
-    const uint64_t* src = p.partial;
-    const int n_q = p.n_q, k = p.k;
-    cta_select<R>([src, n_q, k, q](int i) { const int cta = i / k, e = i - cta * k; return __ldcg(src + (size_t(cta) * n_q + q) * k + e); },
-                  total, lists);
+    auto get = [&](int i) {
+      if (i >= n_keys) return KEY_PAD;
+      const int cta = p.k > 1 ? int(__umulhi(unsigned(i), k_magic)) : i, e = i - cta * p.k;
+      return __ldcg(p.partial + (size_t(cta) * p.n_q + q) * p.k + e);
+    };
+    uint64_t best[R], v[R], nv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { best[r] = KEY_PAD; v[r] = get(warp * L + r * 32 + lane); }
+    for (int c0 = warp * L; c0 < n_keys; c0 += NW * L) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) nv[r] = get(c0 + NW * L + r * 32 + lane);
+      warp_sort<R>(v, lane);
+      warp_merge_keep_low<R>(best, v, lane);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = nv[r];
+    }
+    uint64_t* w0 = wl + size_t(q) * NW * L;
+#pragma unroll
+    for (int r = 0; r < R; ++r) w0[warp * L + r * 32 + lane] = best[r];
+    __syncthreads();
+    cta_join_lists<R>(w0);
     for (int i = tid; i < p.k; i += DS_THREADS) {
-      const uint64_t key = lists[i];
+      const uint64_t key = w0[i];
       const bool pad = key == KEY_PAD;
       p.out_rows[size_t(q) * p.k + i] = pad ? int64_t(-1) : p.row_base + int64_t(key & 0xffffffffull);
       p.out_dist[size_t(q) * p.k + i] = pad ? __int_as_float(0x7f800000) : ord2f(uint32_t(key >> 32));
     }
-    __syncthreads();
   }
-  if (tid == 0) *p.ticket = 0u;
-  __threadfence_system();   // results may live in mapped host memory
+  if (p.dbg != nullptr) t_joined = ds_now();
+  if (tid == 0) *p.ticket = 0u;   // (results in mapped host memory are visible to the host once the kernel has completed)
+  if (p.dbg != nullptr && tid == 0) {
+    p.dbg[0] = t_start; p.dbg[1] = t_staged; p.dbg[2] = t_scanned; p.dbg[3] = t_published; p.dbg[4] = t_ticket; p.dbg[5] = t_joined;
+    p.dbg[6] = ds_now(); p.dbg[7] = gridDim.x;
+  }
 }
 
 // ---- host side ----
-struct DirectPlan { bool ok = false; int nq_t = 0; int r = 0; int grid = 0; size_t smem = 0; size_t partial_bytes = 0; };
+struct DirectPlan { bool ok = false; int nq_t = 0; int r = 0; int grid = 0; int cap_steps = 0; size_t smem = 0; size_t partial_bytes = 0; };
 
-// Shapes the kernel takes: a handful of queries, k <= 128, queries and candidate buffers within shared memory.
+// Shapes the kernel takes: a handful of queries, k <= 128, queries + the warps' lists + at least one step of parked
+// sums within shared memory.
 inline DirectPlan direct_plan(int64_t n_rows, int pitch, int64_t n_q, int k, int sm_count) {
   DirectPlan pl;
-  if (n_rows < 1 || n_q < 1 || n_q > DS_MAX_Q || k < 1 || k > DS_MAX_K) return pl;
+  if (n_rows < 1 || n_rows > (int64_t(1) << 31) - 1 || n_q < 1 || n_q > DS_MAX_Q || k < 1 || k > DS_MAX_K) return pl;
   pl.nq_t = n_q <= 1 ? 1 : n_q <= 2 ? 2 : n_q <= 4 ? 4 : 8;
   pl.r = k <= 32 ? 1 : k <= 64 ? 2 : 4;
   const int64_t n_steps = (n_rows + DS_ROWS_PER_STEP - 1) / DS_ROWS_PER_STEP;
   pl.grid = int(std::max<int64_t>(1, std::min<int64_t>(sm_count, n_steps)));
-  pl.smem = size_t(pl.nq_t) * pitch * 8 + size_t(pl.nq_t) * DS_BUF * 8 + size_t(DS_THREADS / 32) * 32 * pl.r * 8;
-  if (pl.smem > size_t(200) * 1024) return pl;
+  const size_t fixed = size_t(pl.nq_t) * ((pitch + 127) & ~127) * 8 + size_t(pl.nq_t) * (DS_THREADS / 32) * 32 * pl.r * 8;
+  const size_t per_step = size_t(DS_ROWS_PER_STEP) * ((pl.nq_t + 1) * 8 + 4);
+  const size_t budget = size_t(200) * 1024;
+  if (fixed + per_step > budget) return pl;
+  const int64_t steps_per_cta = (n_steps + pl.grid - 1) / pl.grid;
+  pl.cap_steps = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(DS_CAP_STEPS, steps_per_cta), int64_t((budget - fixed) / per_step))));
+  pl.smem = fixed + per_step * pl.cap_steps + 16;
   pl.partial_bytes = size_t(pl.grid) * n_q * k * 8;
   pl.ok = true;
   return pl;
@@ -285,7 +381,9 @@ inline DirectPlan direct_plan(int64_t n_rows, int pitch, int64_t n_q, int k, int
 
 template <int NQ, int R>
 inline cudaError_t direct_attr() {
-  return cudaFuncSetAttribute(knn_direct_kernel<NQ, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(knn_direct_kernel<NQ, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (NQ == 1 && e == cudaSuccess) e = cudaFuncSetAttribute(knn_direct_kernel<1, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return e;
 }
 template <int NQ>
 inline cudaError_t direct_attr_q() {
@@ -302,12 +400,17 @@ inline cudaError_t direct_set_attributes() {
   return e;
 }
 
+template <int NQ, int R>
+inline void direct_launch_qr(const DirectPlan& pl, const DirectParams& p, cudaStream_t stream) {
+  if (NQ == 1 && p.pitch <= 128) knn_direct_kernel<1, R, true><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p);
+  else knn_direct_kernel<NQ, R, false><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p);
+}
 template <int NQ>
 inline void direct_launch_q(const DirectPlan& pl, const DirectParams& p, cudaStream_t stream) {
   switch (pl.r) {
-    case 1: knn_direct_kernel<NQ, 1><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p); break;
-    case 2: knn_direct_kernel<NQ, 2><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p); break;
-    default: knn_direct_kernel<NQ, 4><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p); break;
+    case 1: direct_launch_qr<NQ, 1>(pl, p, stream); break;
+    case 2: direct_launch_qr<NQ, 2>(pl, p, stream); break;
+    default: direct_launch_qr<NQ, 4>(pl, p, stream); break;
   }
 }
 inline cudaError_t direct_launch(const DirectPlan& pl, const DirectParams& p, cudaStream_t stream) {

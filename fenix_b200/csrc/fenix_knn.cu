@@ -9,6 +9,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -726,9 +727,28 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
     p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.row_base = c->row_base;
     p.Q = d_q; p.n_q = int(n_q); p.metric = metric; p.k = k; p.mask = d_mask;
     if (run->inline_q != nullptr) { p.Q = nullptr; std::memcpy(p.q_inline, run->inline_q, size_t(n_q) * c->dim * sizeof(float)); }
-    p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.ticket = ctx->d_ticket;
+    p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.ticket = ctx->d_ticket; p.cap_steps = dpl.cap_steps;
     p.out_rows = d_out_rows; p.out_dist = d_out_dist;
+    if (ctx->tc.knobs.debug_direct) {
+      FX_TRY(ctx->h_flags.ensure(size_t(512) * 8));
+      std::memset(ctx->h_flags.p, 0, 512 * 8);
+      p.dbg = static_cast<unsigned long long*>(ctx->h_flags.p);
+    }
     FX_CUDA(fx::direct_launch(dpl, p, ctx->stream));
+    if (ctx->tc.knobs.debug_direct) {
+      // watchdog: a kernel that has not finished after 3 s is reported (last source line each warp of CTA 0 reached) and the process ends
+      const unsigned long long* t = static_cast<const unsigned long long*>(ctx->h_flags.p);
+      volatile unsigned long long* done = static_cast<volatile unsigned long long*>(ctx->h_flags.p) + 500;
+      std::thread([t, done]() {
+        std::this_thread::sleep_for(std::chrono::seconds(3));
+        if (*done) return;
+        fprintf(stderr, "[fenix direct] kernel still running after 3 s; last source line reached per warp of CTA 0:");
+        for (int w = 0; w < 16; ++w) fprintf(stderr, " %llu", t[400 + w]);
+        fprintf(stderr, "\n");
+        fflush(stderr);
+        _exit(3);
+      }).detach();
+    }
     ctx->launches++; c->stats.kernel_launches++;
     run->path = 3;
   } else if (want_tc) {
@@ -1009,6 +1029,17 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
     std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
     std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
     search_account(c, run);
+    if (ctx->tc.knobs.debug_direct && ctx->h_flags.p) {
+      static_cast<volatile unsigned long long*>(ctx->h_flags.p)[500] = 1;
+      const int grid = direct_plan_for(c, n_q, k, precision).grid;
+      const unsigned long long* t = static_cast<const unsigned long long*>(ctx->h_flags.p);
+      unsigned long long lo = ~0ull, hi = 0;
+      for (int i = 0; i < grid; ++i) { lo = std::min(lo, t[8 + i]); hi = std::max(hi, t[8 + i]); }
+      fprintf(stderr, "[fenix direct] last CTA: start 0, staged %llu, scanned %llu, published %llu, ticket %llu, joined %llu, end %llu ns; "
+                      "scan ends over all %d CTAs: first %lld, last %lld ns after that start; event time %.1f us\n",
+              t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0], t[6] - t[0], grid,
+              (long long)(lo - t[0]), (long long)(hi - t[0]), c->stats.last_search_ms * 1e3);
+    }
     return FX_OK;
   }
   // ---- small searches: replay (or capture) the whole call as one CUDA graph ----

@@ -10,3 +10,8 @@ for nq in (1, 8):
         for _ in range(5):
             c.search(q[:nq], "l2", 10, prec)
         print(name, nq, "queries: device", c.stats().last_search_ms * 1e3, "us")
+ctx.set_option("FENIX_DEBUG_DIRECT", 1)
+for i in range(4):
+    c.search(q[:1], "l2", 10)
+c.search(q[:8], "l2", 10)
+ctx.set_option("FENIX_DEBUG_DIRECT", None)
