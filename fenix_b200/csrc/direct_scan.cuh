@@ -38,6 +38,8 @@ struct DirectParams {
   unsigned int* ticket;      // zero on entry; the last CTA leaves it zero again
   int cap_steps;             // steps between flushes (1 .. DS_CAP_STEPS; shared-memory budget)
   int64_t* out_rows; float* out_dist;   // [n_q][k]; device memory or mapped pinned host memory
+  unsigned long long* done;  // mapped pinned host words or null: [1] = kernel time (ns), then [0] = seq once the results are in host memory
+  unsigned long long seq;
   unsigned long long* dbg;   // FENIX_DEBUG_DIRECT: globaltimer stamps ([0..7] phases of the last CTA, [8 + cta] end of each CTA's scan) or null
   float q_inline[DS_INLINE_FLOATS];
 };
@@ -123,8 +125,8 @@ __device__ __forceinline__ unsigned long long ds_now() {
 template <int NQ, int R, bool QREG>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 knn_direct_kernel(DirectParams p) {
-  unsigned long long t_start = 0, t_staged = 0, t_scanned = 0, t_published = 0;
-  if (p.dbg != nullptr) t_start = ds_now();
+  unsigned long long t_staged = 0, t_scanned = 0, t_published = 0;
+  const unsigned long long t_start = ds_now();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // double qs[NQ][pitch_q] (rows zero-padded to whole 128-float chunks) | u64 wl[NQ][warps][32 R] (the warps' sorted
   // lists) | double sums[cap_rows][NQ + 1] (|x|^2, q.x per query) | int rowid[cap_rows] (-1: masked / past the end)
@@ -348,7 +350,15 @@ knn_direct_kernel(DirectParams p) {
     }
   }
   if (p.dbg != nullptr) t_joined = ds_now();
-  if (tid == 0) *p.ticket = 0u;   // (results in mapped host memory are visible to the host once the kernel has completed)
+  if (tid == 0) *p.ticket = 0u;
+  if (p.done != nullptr) {
+    // the host spins on done[0] instead of waiting for the stream (saves the driver's completion latency): results first,
+    // system-wide fence, then the sequence number - writes of one GPU reach host memory in order
+    if (tid == 0) { volatile unsigned long long* d = p.done; d[1] = ds_now() - t_start; }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) { volatile unsigned long long* d = p.done; d[0] = p.seq; }
+  }
   if (p.dbg != nullptr && tid == 0) {
     p.dbg[0] = t_start; p.dbg[1] = t_staged; p.dbg[2] = t_scanned; p.dbg[3] = t_published; p.dbg[4] = t_ticket; p.dbg[5] = t_joined;
     p.dbg[6] = ds_now(); p.dbg[7] = gridDim.x;

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -114,6 +115,8 @@ struct fx_ctx {
   DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref, d_maskn, d_floor, d_xchg, d_hdr;
   HostBuf h_q, h_rows, h_dist, h_flags;
   unsigned int* d_ticket = nullptr;   // direct scan: "last CTA merges" counter (zero between launches)
+  unsigned long long* h_done = nullptr;   // pinned: direct scan completion word [0] = sequence number, [1] = kernel ns
+  unsigned long long direct_seq = 0;
   int* h_word = nullptr;           // pinned: [0] flagged-query count of the last main pass, [1..] gathered per-rank counts
   int64_t launches = 0;
   fx::TcState tc;                  // driver entry points / kernel attributes / tuning knobs of the TC path
@@ -238,6 +241,8 @@ extern "C" int fx_init(int device, fx_ctx** out) {
   FX_CUDA(cudaEventCreate(&ctx->ev_x1));
   FX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_word), H_WORDS * sizeof(int)));
   std::memset(ctx->h_word, 0, H_WORDS * sizeof(int));
+  FX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_done), 64));
+  std::memset(ctx->h_done, 0, 64);
   FX_CUDA(cudaFuncSetAttribute(fx::exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -266,6 +271,7 @@ extern "C" int fx_shutdown(fx_ctx* ctx) {
   ctx->h_q.release(); ctx->h_rows.release(); ctx->h_dist.release(); ctx->h_flags.release();
   if (ctx->h_word) cudaFreeHost(ctx->h_word);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->h_done) cudaFreeHost(ctx->h_done);
   cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_stop);
   cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
   cudaEventDestroy(ctx->ev_x0); cudaEventDestroy(ctx->ev_x1);
@@ -699,6 +705,8 @@ struct SearchRun {
   const float* d_q = nullptr; int64_t n_q = 0; int metric = 0, k = 0;
   const uint8_t* d_mask = nullptr; int64_t* d_out_rows = nullptr; float* d_out_dist = nullptr;
   const float* inline_q = nullptr;   // set by the caller: HOST queries small enough to ride in the direct scan's kernel parameters
+  bool spin = false;                 // set by the caller: results go to mapped host memory and the host spins on the kernel's completion word
+                                     // (no events are recorded around the launch)
 };
 
 static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metric, int k, int precision,
@@ -708,8 +716,9 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
   run->d_mask = d_mask; run->d_out_rows = d_out_rows; run->d_out_dist = d_out_dist;
   ctx->h_word[0] = 0;
   const unsigned ev_flags = ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
-  FX_CUDA(cudaEventRecordWithFlags(ctx->ev_start, ctx->stream, ev_flags));
   const fx::DirectPlan dpl = direct_plan_for(c, n_q, k, precision);
+  const bool spin = run->spin && dpl.ok && c->n > 0;
+  if (!spin) FX_CUDA(cudaEventRecordWithFlags(ctx->ev_start, ctx->stream, ev_flags));
   const bool want_tc = !dpl.ok && precision != FX_PREC_EXACT_SCAN &&
                        fx::tc_supported(&ctx->tc, &c->tc, c->n, c->dim, k, int(n_q));
   if (c->n == 0) {
@@ -729,6 +738,7 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
     if (run->inline_q != nullptr) { p.Q = nullptr; std::memcpy(p.q_inline, run->inline_q, size_t(n_q) * c->dim * sizeof(float)); }
     p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.ticket = ctx->d_ticket; p.cap_steps = dpl.cap_steps;
     p.out_rows = d_out_rows; p.out_dist = d_out_dist;
+    if (spin) { p.done = ctx->h_done; p.seq = ++ctx->direct_seq; }
     if (ctx->tc.knobs.debug_direct) {
       FX_TRY(ctx->h_flags.ensure(size_t(512) * 8));
       std::memset(ctx->h_flags.p, 0, 512 * 8);
@@ -780,7 +790,7 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
     FX_TRY(run_exact_scan(c, d_q, int(n_q), nullptr, int(n_q), metric, k, d_mask, d_out_rows, d_out_dist));
     FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k1, ctx->stream, ev_flags));
   }
-  FX_CUDA(cudaEventRecordWithFlags(ctx->ev_stop, ctx->stream, ev_flags));
+  if (!spin) FX_CUDA(cudaEventRecordWithFlags(ctx->ev_stop, ctx->stream, ev_flags));
   return FX_OK;
 }
 
@@ -897,7 +907,8 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
 static void search_account(fx_corpus* c, const SearchRun& run) {
   fx_ctx* ctx = c->ctx;
   float ms = 0.f, kms = 0.f;
-  cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+  if (run.spin && run.path == 3) ms = float(double(ctx->h_done[1]) * 1e-6);   // the kernel's own globaltimer stamps
+  else cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
   if (run.path == 3) kms = ms;   // the direct scan is its one kernel (no inner events: they cost host time on the latency path)
   else cudaEventElapsedTime(&kms, ctx->ev_k0, ctx->ev_k1);
   c->stats.last_search_ms = ms; c->stats.last_main_kernel_ms = kms; c->stats.last_path = run.path;
@@ -1010,6 +1021,7 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
     FX_TRY(ctx->h_rows.ensure(r_bytes));
     FX_TRY(ctx->h_dist.ensure(d_bytes));
     SearchRun run;
+    run.spin = ctx->tc.knobs.direct_spin != 0 && !ctx->tc.knobs.debug_direct;
     if (n_q * int64_t(c->dim) <= fx::DS_INLINE_FLOATS) {
       run.inline_q = queries;
     } else {
@@ -1025,7 +1037,21 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
     }
     FX_TRY(search_enqueue(c, static_cast<const float*>(ctx->d_q.p), n_q, metric, k, precision, d_mask,
                           static_cast<int64_t*>(ctx->h_rows.p), static_cast<float*>(ctx->h_dist.p), &run));
-    FX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (run.spin) {
+      // the last CTA writes the results, then the sequence number, into mapped host memory: spinning on that word skips the
+      // driver's stream-completion latency. A kernel that does not report within 2 ms (a fault) falls back to the stream wait.
+      volatile unsigned long long* done = ctx->h_done;
+      const auto t0 = std::chrono::steady_clock::now();
+      for (unsigned it = 1; done[0] != ctx->direct_seq; ++it) {
+        if ((it & 0x3ff) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) {
+          FX_CUDA(cudaStreamSynchronize(ctx->stream));
+          break;
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+      FX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
     std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
     search_account(c, run);

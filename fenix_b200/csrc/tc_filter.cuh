@@ -119,6 +119,8 @@ struct TcKnobs {
   int debug_tiers = 0;     // FENIX_DEBUG_TIERS    stderr trace of the certificate-failure tiers (counts, host-clock times)
   int direct = 1;          // FENIX_DIRECT         0: never take the single-launch direct scan (direct_scan.cuh: <= 8 queries, small shards)
   int direct_mb = 256;     // FENIX_DIRECT_MAX_MB  largest shard (MB of fp32 rows) the direct scan takes
+  int direct_spin = 1;     // FENIX_DIRECT_SPIN    fx_search waits for a direct scan by spinning on the kernel's completion word in mapped
+                           //                      host memory (0: cudaStreamSynchronize, events around the launch)
   int debug_direct = 0;    // FENIX_DEBUG_DIRECT   stderr timeline (globaltimer stamps) of every direct scan launched by fx_search
 };
 // name = the environment variable's name; value = its text, or null to restore the default. False: unknown name.
@@ -155,6 +157,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_DIRECT") k->direct = as_int(d.direct);
   else if (n == "FENIX_DIRECT_MAX_MB") k->direct_mb = as_int(d.direct_mb);
   else if (n == "FENIX_DEBUG_DIRECT") k->debug_direct = as_flag();
+  else if (n == "FENIX_DIRECT_SPIN") k->direct_spin = as_int(d.direct_spin);
   else return false;
   return true;
 }
@@ -163,7 +166,7 @@ inline void tc_knobs_from_env(TcKnobs* k) {
       "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_MAX_WAVES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
       "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SMALL", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
       "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
-      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH", "FENIX_DIRECT", "FENIX_DIRECT_MAX_MB", "FENIX_DEBUG_DIRECT"};
+      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH", "FENIX_DIRECT", "FENIX_DIRECT_MAX_MB", "FENIX_DEBUG_DIRECT", "FENIX_DIRECT_SPIN"};
   for (const char* name : names) {
     if (const char* v = std::getenv(name)) tc_set_knob(k, name, v);
   }
