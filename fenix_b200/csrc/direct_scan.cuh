@@ -27,6 +27,7 @@ constexpr int DS_MAX_Q = 8;              // queries per launch
 constexpr int DS_MAX_K = 128;
 constexpr int DS_ROWS_PER_STEP = DS_THREADS / 8;         // 8 lanes per row, one row per lane group and step
 constexpr int DS_CAP_STEPS = 16;         // steps whose raw sums are parked in shared memory between flushes (at most)
+constexpr int DS_MAX_PROBES = 512;       // posting lists one query may probe (LISTS mode; prefix sums in shared memory)
 constexpr int DS_INLINE_FLOATS = 896;    // query floats carried in the kernel parameters (3.5 KB of the 4 KB parameter space)
 
 struct DirectParams {
@@ -38,6 +39,10 @@ struct DirectParams {
   unsigned int* ticket;      // zero on entry; the last CTA leaves it zero again
   int cap_steps;             // steps between flushes (1 .. DS_CAP_STEPS; shared-memory budget)
   int64_t* out_rows; float* out_dist;   // [n_q][k]; device memory or mapped pinned host memory
+  // LISTS mode (batched IVF, fx_search_cells): blockIdx.y = query; the query scans only the rows of the posting lists it
+  // probes. inv_rows: local rows grouped by cell, cell_off[c .. c + 1): cell c's slice of it, probes[q][n_probe]: the
+  // query's cells (-1: none); ticket then points at one counter per query and partial is [query][cta][k]
+  const int* inv_rows; const long long* cell_off; const int* probes; int n_probe;
   unsigned long long* done;  // mapped pinned host words or null: [1] = kernel time (ns), then [0] = seq once the results are in host memory
   unsigned long long seq;
   unsigned long long* dbg;   // FENIX_DEBUG_DIRECT: globaltimer stamps ([0..7] phases of the last CTA, [8 + cta] end of each CTA's scan) or null
@@ -122,9 +127,11 @@ __device__ __forceinline__ unsigned long long ds_now() {
 
 // QREG (one query, rows of <= 128 floats): the lane's sixteen query values live in registers, the multiply loop reads
 // no shared memory at all.
-template <int NQ, int R, bool QREG>
+// LISTS (batched IVF): one query per CTA column (blockIdx.y), rows come from the query's probed posting lists.
+template <int NQ, int R, bool QREG, bool LISTS = false>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 knn_direct_kernel(DirectParams p) {
+  static_assert(!LISTS || NQ == 1, "LISTS mode scans one query per CTA");
   unsigned long long t_staged = 0, t_scanned = 0, t_published = 0;
   const unsigned long long t_start = ds_now();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,7 +147,11 @@ knn_direct_kernel(DirectParams p) {
   int* rowid = reinterpret_cast<int*>(sums + size_t(cap_rows) * (NQ + 1));
   __shared__ double s_qq[NQ];
   __shared__ unsigned int s_last;
+  __shared__ int s_pre[LISTS ? DS_MAX_PROBES + 1 : 1];          // LISTS: rows before posting list t of this query
+  __shared__ long long s_lst[LISTS ? DS_MAX_PROBES : 1];        // LISTS: where list t starts in inv_rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qbase = LISTS ? int(blockIdx.y) : 0;                // first query of this CTA
+  const int nq_here = LISTS ? 1 : p.n_q;
   // lane = grp + 4 * sub: row `grp` of the warp's four, float4 slot `sub` of eight. A quarter-warp (the unit a 128-bit
   // shared-memory load is served in) then reads TWO query addresses, 64 contiguous bytes, instead of eight 32 B apart
   // (sub-major lanes: 8 wavefronts per load, the query reads alone cost ~6 us per query on C1).
@@ -149,11 +160,20 @@ knn_direct_kernel(DirectParams p) {
   for (int q = 0; q < NQ; ++q) {
     for (int d = tid; d < pitch_q; d += DS_THREADS) {
       float v = 0.f;
-      if (q < p.n_q && d < p.dim) v = p.Q != nullptr ? p.Q[size_t(q) * p.dim + d] : p.q_inline[q * p.dim + d];
+      if (q < nq_here && d < p.dim) v = p.Q != nullptr ? p.Q[size_t(qbase + q) * p.dim + d] : p.q_inline[q * p.dim + d];
       qs[size_t(q) * pitch_q + d] = double(v);
     }
   }
   for (int i = tid; i < NQ * NW * L; i += DS_THREADS) wl[i] = KEY_PAD;
+  if constexpr (LISTS) {
+    for (int t = tid; t < p.n_probe; t += DS_THREADS) {
+      const int cell = p.probes[size_t(qbase) * p.n_probe + t];
+      const long long lo = cell >= 0 ? p.cell_off[cell] : 0, hi = cell >= 0 ? p.cell_off[cell + 1] : 0;
+      s_lst[t] = lo; s_pre[t + 1] = int(hi - lo);
+    }
+    __syncthreads();
+    if (tid == 0) { s_pre[0] = 0; for (int t = 0; t < p.n_probe; ++t) s_pre[t + 1] += s_pre[t]; }
+  }
   __syncthreads();
   if (warp < NQ) {   // |q|^2, summed as the finish kernel sums it (lane-strided, xor tree)
     double s = 0.0;
@@ -172,7 +192,8 @@ knn_direct_kernel(DirectParams p) {
   // tree over the 8 lanes.
   const int n4 = p.pitch >> 2;
   const int C = (n4 + 31) >> 5;                       // chunks per row
-  const int64_t n_steps = (p.n_rows + DS_ROWS_PER_STEP - 1) / DS_ROWS_PER_STEP;
+  const int64_t n_items = LISTS ? int64_t(s_pre[p.n_probe]) : p.n_rows;   // rows this CTA column scans
+  const int64_t n_steps = (n_items + DS_ROWS_PER_STEP - 1) / DS_ROWS_PER_STEP;
   const int my_steps = int64_t(blockIdx.x) < n_steps ? int((n_steps - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
   const int total = my_steps * C;
   int parked = 0;                                     // steps parked in `sums` since the last flush
@@ -188,9 +209,19 @@ knn_direct_kernel(DirectParams p) {
     }
   }
 
-  auto row_of = [&](int st) { return (int64_t(blockIdx.x) + int64_t(st) * gridDim.x) * DS_ROWS_PER_STEP + warp * 4 + grp; };
-  auto load = [&](float4 (&x)[4], bool& live, int st, int ch) {
-    const int64_t row = row_of(st);
+  auto item_of = [&](int st) { return (int64_t(blockIdx.x) + int64_t(st) * gridDim.x) * DS_ROWS_PER_STEP + warp * 4 + grp; };
+  // the shard row behind an item: the item itself, or (LISTS) entry `item` of the query's concatenated posting lists
+  auto row_of = [&](int st) -> int64_t {
+    const int64_t item = item_of(st);
+    if constexpr (!LISTS) return item;
+    if (item >= n_items) return p.n_rows;   // (past the end: not live)
+    int lo = 0, hi = p.n_probe;             // last list t with s_pre[t] <= item
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (int64_t(s_pre[mid]) <= item) lo = mid; else hi = mid; }
+    return int64_t(p.inv_rows[s_lst[lo] + (item - s_pre[lo])]);
+  };
+  auto load = [&](float4 (&x)[4], bool& live, int& rowreg, int st, int ch) {
+    const int64_t row = st < my_steps ? row_of(st) : p.n_rows;
+    rowreg = int(row);
     live = st < my_steps && row < p.n_rows;
     if (live && p.mask != nullptr) live = p.mask[row] != 0;
     const float4* xp = reinterpret_cast<const float4*>(p.X + size_t(live ? row : 0) * p.pitch);
@@ -204,7 +235,7 @@ knn_direct_kernel(DirectParams p) {
   auto flush = [&](int n_parked_steps) {
     __syncthreads();
     const int n_slots = n_parked_steps * DS_ROWS_PER_STEP;
-    for (int q = 0; q < p.n_q; ++q) {
+    for (int q = 0; q < nq_here; ++q) {
       uint64_t best[R];
       uint64_t* mine = wl + (size_t(q) * NW + warp) * L;
 #pragma unroll
@@ -235,7 +266,7 @@ knn_direct_kernel(DirectParams p) {
     }
     __syncthreads();
   };
-  auto compute = [&](const float4 (&x)[4], bool live, int st, int ch) {
+  auto compute = [&](const float4 (&x)[4], bool live, int rowreg, int ch) {
     if (__any_sync(0xffffffffu, live)) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -271,7 +302,7 @@ knn_direct_kernel(DirectParams p) {
       if (sub < NQ) sums[size_t(slot) * (NQ + 1) + 1 + sub] = dq;
       if (sub == 0) sums[size_t(slot) * (NQ + 1)] = xx;
     }
-    if (sub == 0) rowid[slot] = live ? int(row_of(st)) : -1;
+    if (sub == 0) rowid[slot] = live ? rowreg : -1;
     xx = 0.0;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) qx[q] = 0.0;
@@ -280,20 +311,22 @@ knn_direct_kernel(DirectParams p) {
   {
     float4 x0[4], x1[4], x2[4];
     bool l0 = false, l1 = false, l2 = false;
-    int ls = 0, lc = 0, cs = 0, cc = 0;                 // next item to load / to compute: (step, chunk)
+    int r0 = 0, r1 = 0, r2 = 0;                         // shard row of the item in each buffer
+    int ls = 0, lc = 0, cc = 0;                         // next item to load: (step, chunk); chunk of the next item to compute
     auto adv = [&](int& st, int& ch) { if (++ch == C) { ch = 0; ++st; } };
-    load(x0, l0, ls, lc); adv(ls, lc);
-    load(x1, l1, ls, lc); adv(ls, lc);
+    auto advc = [&](int& ch) { if (++ch == C) ch = 0; };
+    load(x0, l0, r0, ls, lc); adv(ls, lc);
+    load(x1, l1, r1, ls, lc); adv(ls, lc);
     for (int t = 0; t < total; t += 3) {
-      load(x2, l2, ls, lc); adv(ls, lc);
-      compute(x0, l0, cs, cc); adv(cs, cc);
+      load(x2, l2, r2, ls, lc); adv(ls, lc);
+      compute(x0, l0, r0, cc); advc(cc);
       if (t + 1 < total) {
-        load(x0, l0, ls, lc); adv(ls, lc);
-        compute(x1, l1, cs, cc); adv(cs, cc);
+        load(x0, l0, r0, ls, lc); adv(ls, lc);
+        compute(x1, l1, r1, cc); advc(cc);
       }
       if (t + 2 < total) {
-        load(x1, l1, ls, lc); adv(ls, lc);
-        compute(x2, l2, cs, cc); adv(cs, cc);
+        load(x1, l1, r1, ls, lc); adv(ls, lc);
+        compute(x2, l2, r2, cc); advc(cc);
       }
     }
   }
@@ -301,15 +334,19 @@ knn_direct_kernel(DirectParams p) {
   flush(parked);   // (barriers on both sides; also when nothing is parked)
 
   // ---- this CTA's k best per query, published ----
-  for (int q = 0; q < p.n_q; ++q) {
+  // published lists: [cta][query][k]; LISTS: [query][cta][k]
+  uint64_t* const part = LISTS ? p.partial + size_t(qbase) * gridDim.x * p.k : p.partial;
+  const int part_nq = LISTS ? 1 : p.n_q;
+  for (int q = 0; q < nq_here; ++q) {
     uint64_t* w0 = wl + size_t(q) * NW * L;
     cta_join_lists<R>(w0);
-    for (int i = tid; i < p.k; i += DS_THREADS) p.partial[(size_t(blockIdx.x) * p.n_q + q) * p.k + i] = w0[i];
+    for (int i = tid; i < p.k; i += DS_THREADS) part[(size_t(blockIdx.x) * part_nq + q) * p.k + i] = w0[i];
   }
   __threadfence();
   __syncthreads();
   if (p.dbg != nullptr) t_published = ds_now();
-  if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  unsigned int* const ticket = p.ticket + (LISTS ? qbase : 0);
+  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
   if (s_last == 0u) return;
   __threadfence();
@@ -320,11 +357,11 @@ knn_direct_kernel(DirectParams p) {
   // chunk's loads in flight while one is sorted), then the same tree ----
   const int n_keys = int(gridDim.x) * p.k;
   const unsigned k_magic = p.k > 1 ? unsigned((0x100000000ull + unsigned(p.k) - 1u) / unsigned(p.k)) : 0u;   // i / k = umulhi(i, magic), i < 2^15
-  for (int q = 0; q < p.n_q; ++q) {
+  for (int q = 0; q < nq_here; ++q) {
     auto get = [&](int i) {
       if (i >= n_keys) return KEY_PAD;
       const int cta = p.k > 1 ? int(__umulhi(unsigned(i), k_magic)) : i, e = i - cta * p.k;
-      return __ldcg(p.partial + (size_t(cta) * p.n_q + q) * p.k + e);
+      return __ldcg(part + (size_t(cta) * part_nq + q) * p.k + e);
     };
     uint64_t best[R], v[R], nv[R];
 #pragma unroll
@@ -345,12 +382,12 @@ knn_direct_kernel(DirectParams p) {
     for (int i = tid; i < p.k; i += DS_THREADS) {
       const uint64_t key = w0[i];
       const bool pad = key == KEY_PAD;
-      p.out_rows[size_t(q) * p.k + i] = pad ? int64_t(-1) : p.row_base + int64_t(key & 0xffffffffull);
-      p.out_dist[size_t(q) * p.k + i] = pad ? __int_as_float(0x7f800000) : ord2f(uint32_t(key >> 32));
+      p.out_rows[size_t(qbase + q) * p.k + i] = pad ? int64_t(-1) : p.row_base + int64_t(key & 0xffffffffull);
+      p.out_dist[size_t(qbase + q) * p.k + i] = pad ? __int_as_float(0x7f800000) : ord2f(uint32_t(key >> 32));
     }
   }
   if (p.dbg != nullptr) t_joined = ds_now();
-  if (tid == 0) *p.ticket = 0u;
+  if (tid == 0) *ticket = 0u;
   if (p.done != nullptr) {
     // the host spins on done[0] instead of waiting for the stream (saves the driver's completion latency): results first,
     // system-wide fence, then the sequence number - writes of one GPU reach host memory in order
@@ -429,6 +466,56 @@ inline cudaError_t direct_launch(const DirectPlan& pl, const DirectParams& p, cu
     case 2: direct_launch_q<2>(pl, p, stream); break;
     case 4: direct_launch_q<4>(pl, p, stream); break;
     default: direct_launch_q<8>(pl, p, stream); break;
+  }
+  return cudaGetLastError();
+}
+
+// ---- LISTS mode (batched IVF): grid = (CTAs per query, queries) ----
+struct CellsPlan { bool ok = false; int r = 0; int ctas = 0; int cap_steps = 0; size_t smem = 0; size_t partial_bytes = 0; };
+
+// max_items: the longest concatenated posting list any query of the batch scans
+inline CellsPlan cells_plan(int pitch, int64_t n_q, int k, int n_probe, int64_t max_items, int sm_count) {
+  CellsPlan pl;
+  if (n_q < 1 || n_q > 65535 || k < 1 || k > DS_MAX_K || n_probe < 1 || n_probe > DS_MAX_PROBES) return pl;
+  pl.r = k <= 32 ? 1 : k <= 64 ? 2 : 4;
+  const int64_t n_steps = std::max<int64_t>(1, (max_items + DS_ROWS_PER_STEP - 1) / DS_ROWS_PER_STEP);
+  // enough CTAs to fill the GPU twice over, but at least four steps each (a CTA's fixed cost is ~3 us)
+  pl.ctas = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((2 * int64_t(sm_count) + n_q - 1) / n_q, (n_steps + 3) / 4), sm_count)));
+  const size_t fixed = size_t((pitch + 127) & ~127) * 8 + size_t(DS_THREADS / 32) * 32 * pl.r * 8;
+  const size_t per_step = size_t(DS_ROWS_PER_STEP) * (2 * 8 + 4);
+  const size_t budget = size_t(200) * 1024;
+  if (fixed + per_step > budget) return pl;
+  const int64_t steps_per_cta = (n_steps + pl.ctas - 1) / pl.ctas;
+  pl.cap_steps = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(DS_CAP_STEPS, steps_per_cta), int64_t((budget - fixed) / per_step))));
+  pl.smem = fixed + per_step * pl.cap_steps + 16;
+  pl.partial_bytes = size_t(n_q) * pl.ctas * k * 8;
+  pl.ok = true;
+  return pl;
+}
+
+template <int R>
+inline cudaError_t cells_attr() {
+  cudaError_t e = cudaFuncSetAttribute(knn_direct_kernel<1, R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(knn_direct_kernel<1, R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return e;
+}
+inline cudaError_t cells_set_attributes() {
+  cudaError_t e = cells_attr<1>();
+  if (e == cudaSuccess) e = cells_attr<2>();
+  if (e == cudaSuccess) e = cells_attr<4>();
+  return e;
+}
+template <int R>
+inline void cells_launch_r(const CellsPlan& pl, const DirectParams& p, int n_q, cudaStream_t stream) {
+  const dim3 grid(pl.ctas, n_q);
+  if (p.pitch <= 128) knn_direct_kernel<1, R, true, true><<<grid, DS_THREADS, pl.smem, stream>>>(p);
+  else knn_direct_kernel<1, R, false, true><<<grid, DS_THREADS, pl.smem, stream>>>(p);
+}
+inline cudaError_t cells_launch(const CellsPlan& pl, const DirectParams& p, int n_q, cudaStream_t stream) {
+  switch (pl.r) {
+    case 1: cells_launch_r<1>(pl, p, n_q, stream); break;
+    case 2: cells_launch_r<2>(pl, p, n_q, stream); break;
+    default: cells_launch_r<4>(pl, p, n_q, stream); break;
   }
   return cudaGetLastError();
 }

@@ -112,7 +112,7 @@ struct fx_ctx {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   std::mutex mu;                   // one search at a time per device context
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;   // exchange (all-gather + merge) of a sharded search
-  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref, d_maskn, d_floor, d_xchg, d_hdr;
+  DevBuf d_q, d_rows, d_dist, d_mask, d_partial, d_qlist, d_tc, d_ref, d_maskn, d_floor, d_xchg, d_hdr, d_tickets;
   HostBuf h_q, h_rows, h_dist, h_flags;
   unsigned int* d_ticket = nullptr;   // direct scan: "last CTA merges" counter (zero between launches)
   unsigned long long* h_done = nullptr;   // pinned: direct scan completion word [0] = sequence number, [1] = kernel ns
@@ -158,6 +158,10 @@ struct fx_corpus {
     int path = 0, variant = 0, launches = 0;
   };
   std::vector<GraphEntry> graphs;
+  // inverted index for batched IVF searches (fx_corpus_set_cells): local rows grouped by cell
+  int* d_inv = nullptr; long long* d_cell_off = nullptr;
+  std::vector<long long> h_cell_off;
+  int64_t n_inv = 0, n_cells = 0;
 };
 
 static int bind(fx_ctx* ctx) {
@@ -247,6 +251,7 @@ extern "C" int fx_init(int device, fx_ctx** out) {
   FX_CUDA(cudaFuncSetAttribute(fx::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   FX_CUDA(fx::direct_set_attributes());
+  FX_CUDA(fx::cells_set_attributes());
   FX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_ticket), 256));
   FX_CUDA(cudaMemset(ctx->d_ticket, 0, 256));
   {
@@ -267,7 +272,7 @@ extern "C" int fx_shutdown(fx_ctx* ctx) {
   cudaStreamSynchronize(ctx->upload);
   ctx->d_q.release(); ctx->d_rows.release(); ctx->d_dist.release(); ctx->d_mask.release();
   ctx->d_partial.release(); ctx->d_qlist.release(); ctx->d_tc.release(); ctx->d_ref.release(); ctx->d_maskn.release();
-  ctx->d_floor.release(); ctx->d_xchg.release(); ctx->d_hdr.release();
+  ctx->d_floor.release(); ctx->d_xchg.release(); ctx->d_hdr.release(); ctx->d_tickets.release();
   ctx->h_q.release(); ctx->h_rows.release(); ctx->h_dist.release(); ctx->h_flags.release();
   if (ctx->h_word) cudaFreeHost(ctx->h_word);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
@@ -466,6 +471,8 @@ extern "C" int fx_corpus_destroy(fx_corpus* c) {
   if (c->hx) cudaFree(c->hx);
   if (c->rx) cudaFree(c->rx);
   if (c->max_n2_bits) cudaFree(c->max_n2_bits);
+  if (c->d_inv) cudaFree(c->d_inv);
+  if (c->d_cell_off) cudaFree(c->d_cell_off);
   delete c;
   return FX_OK;
 }
@@ -1152,6 +1159,104 @@ extern "C" int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_
     std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
     std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
   }
+  search_account(c, run);
+  return FX_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// batched IVF: an inverted index per shard, one launch per query batch (direct_scan.cuh, LISTS mode)
+// ----------------------------------------------------------------------------------------
+extern "C" int fx_corpus_set_cells(fx_corpus* c, const int32_t* inv_rows, int64_t n_inv, const int64_t* cell_off, int64_t n_cells) {
+  FX_LEASE(c, "fx_corpus_set_cells");
+  if (!c->finalized) return fail(FX_ESTATE, "fx_corpus_set_cells: corpus is not finalized");
+  if (n_inv < 0 || n_cells < 0 || (n_inv > 0 && !inv_rows) || !cell_off) return fail(FX_EINVAL, "fx_corpus_set_cells: bad arguments");
+  if (cell_off[0] != 0 || cell_off[n_cells] != n_inv) return fail(FX_EINVAL, "fx_corpus_set_cells: cell_off must run from 0 to n_inv");
+  for (int64_t i = 0; i < n_cells; ++i) if (cell_off[i + 1] < cell_off[i]) return fail(FX_EINVAL, "fx_corpus_set_cells: cell_off must not decrease");
+  for (int64_t i = 0; i < n_inv; ++i) if (inv_rows[i] < 0 || inv_rows[i] >= c->n) return fail(FX_EINVAL, "fx_corpus_set_cells: row %d out of range", inv_rows[i]);
+  fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (c->d_inv) { cudaFree(c->d_inv); c->d_inv = nullptr; }
+  if (c->d_cell_off) { cudaFree(c->d_cell_off); c->d_cell_off = nullptr; }
+  c->n_inv = 0; c->n_cells = 0; c->h_cell_off.clear();
+  if (cudaMalloc(reinterpret_cast<void**>(&c->d_inv), size_t(std::max<int64_t>(n_inv, 1)) * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&c->d_cell_off), size_t(n_cells + 1) * sizeof(long long)) != cudaSuccess) {
+    cudaGetLastError();
+    if (c->d_inv) { cudaFree(c->d_inv); c->d_inv = nullptr; }
+    return fail(FX_ENOMEM, "fx_corpus_set_cells: no device memory for %lld rows in %lld cells", (long long)n_inv, (long long)n_cells);
+  }
+  FX_CUDA(cudaMemcpy(c->d_inv, inv_rows, size_t(n_inv) * sizeof(int), cudaMemcpyHostToDevice));
+  FX_CUDA(cudaMemcpy(c->d_cell_off, cell_off, size_t(n_cells + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+  c->h_cell_off.assign(cell_off, cell_off + n_cells + 1);
+  c->n_inv = n_inv; c->n_cells = n_cells;
+  return FX_OK;
+}
+
+extern "C" int fx_search_cells(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, int32_t k, const int32_t* probes,
+                               int32_t n_probe, const uint8_t* row_mask, int64_t* out_rows, float* out_dist) {
+  FX_LEASE(c, "fx_search_cells");
+  NvtxRange nvtx("fenix:search_cells");
+  FX_TRY(check_search_args(c, queries, n_q, metric, k, FX_PREC_FP32, out_rows, out_dist));
+  if (n_q == 0) return FX_OK;
+  if (!probes || n_probe < 1) return fail(FX_EINVAL, "fx_search_cells: no probes");
+  if (!c->d_cell_off) return fail(FX_ESTATE, "fx_search_cells: the shard has no cells (fx_corpus_set_cells)");
+  fx_ctx* ctx = c->ctx;
+  // the longest candidate list of the batch sizes the grid; cell numbers are validated on the way
+  int64_t max_items = 0;
+  for (int64_t q = 0; q < n_q; ++q) {
+    int64_t items = 0;
+    for (int t = 0; t < n_probe; ++t) {
+      const int cell = probes[q * n_probe + t];
+      if (cell >= c->n_cells) return fail(FX_EINVAL, "fx_search_cells: cell %d out of range [0, %lld)", cell, (long long)c->n_cells);
+      if (cell >= 0) items += c->h_cell_off[cell + 1] - c->h_cell_off[cell];
+    }
+    if (items > (int64_t(1) << 31) - 1) return fail(FX_EUNSUP, "fx_search_cells: a query probes more than 2^31 rows");
+    max_items = std::max(max_items, items);
+  }
+  const fx::CellsPlan pl = fx::cells_plan(c->pitch, n_q, k, n_probe, max_items, ctx->sm_count);
+  if (!pl.ok) return fail(FX_EUNSUP, "fx_search_cells: shape not supported by the one-launch path (k %d <= 128, probes %d <= 512, queries %lld <= 65535, dim %d)",
+                          k, n_probe, (long long)n_q, c->dim);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  FX_TRY(bind(ctx));
+  const size_t q_bytes = size_t(n_q) * c->dim * sizeof(float), p_bytes = size_t(n_q) * n_probe * sizeof(int);
+  const size_t r_bytes = size_t(n_q) * k * sizeof(int64_t), d_bytes = size_t(n_q) * k * sizeof(float);
+  FX_TRY(ctx->d_q.ensure(q_bytes));
+  FX_TRY(ctx->d_rows.ensure(r_bytes));
+  FX_TRY(ctx->d_dist.ensure(d_bytes));
+  FX_TRY(ctx->d_qlist.ensure(p_bytes));
+  FX_TRY(ctx->d_tickets.ensure(size_t(n_q) * sizeof(unsigned int)));
+  FX_TRY(ctx->d_partial.ensure(pl.partial_bytes));
+  FX_TRY(ctx->h_q.ensure(q_bytes + p_bytes));
+  FX_TRY(ctx->h_rows.ensure(r_bytes));
+  FX_TRY(ctx->h_dist.ensure(d_bytes));
+  std::memcpy(ctx->h_q.p, queries, q_bytes);
+  std::memcpy(static_cast<char*>(ctx->h_q.p) + q_bytes, probes, p_bytes);
+  FX_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+  FX_CUDA(cudaMemcpyAsync(ctx->d_q.p, ctx->h_q.p, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, static_cast<char*>(ctx->h_q.p) + q_bytes, p_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  FX_CUDA(cudaMemsetAsync(ctx->d_tickets.p, 0, size_t(n_q) * sizeof(unsigned int), ctx->stream));
+  const uint8_t* d_mask = nullptr;
+  if (row_mask) {
+    FX_TRY(ctx->d_mask.ensure(size_t(c->n)));
+    FX_CUDA(cudaMemcpyAsync(ctx->d_mask.p, row_mask, size_t(c->n), cudaMemcpyHostToDevice, ctx->stream));
+    d_mask = static_cast<const uint8_t*>(ctx->d_mask.p);
+  }
+  fx::DirectParams p{};
+  p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.row_base = c->row_base;
+  p.Q = static_cast<const float*>(ctx->d_q.p); p.n_q = int(n_q); p.metric = metric; p.k = k; p.mask = d_mask;
+  p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.ticket = static_cast<unsigned int*>(ctx->d_tickets.p); p.cap_steps = pl.cap_steps;
+  p.out_rows = static_cast<int64_t*>(ctx->d_rows.p); p.out_dist = static_cast<float*>(ctx->d_dist.p);
+  p.inv_rows = c->d_inv; p.cell_off = c->d_cell_off; p.probes = static_cast<const int*>(ctx->d_qlist.p); p.n_probe = n_probe;
+  FX_CUDA(fx::cells_launch(pl, p, int(n_q), ctx->stream));
+  ctx->launches++; c->stats.kernel_launches++;
+  FX_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+  FX_CUDA(cudaMemcpyAsync(ctx->h_rows.p, ctx->d_rows.p, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  FX_CUDA(cudaMemcpyAsync(ctx->h_dist.p, ctx->d_dist.p, d_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  FX_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out_rows, ctx->h_rows.p, r_bytes);
+  std::memcpy(out_dist, ctx->h_dist.p, d_bytes);
+  SearchRun run; run.path = 3; run.n_q = n_q;
   search_account(c, run);
   return FX_OK;
 }

@@ -174,9 +174,20 @@ def call(
         mask = _row_mask(data, column, filter) if filter is not None else None
 
         if probe_codes is not None and batched:
-            # Batched IVF: every query has its own probe cells, i.e. its own row mask. The shard, the predicate mask and
-            # the code column are prepared once; each query is one masked search on the resident shard.
+            # Batched IVF: every query has its own probe cells, i.e. its own row mask (index.py:113-126 per query).
             codes = data.column(CODE_COL).to_numpy()
+            # One launch for the batch when the shard is on one device and the shape fits (k <= 128, <= 512 probes): the
+            # shard keeps its rows grouped by cell and query q scans only the posting lists of its probe codes.
+            fast = _search_cells(shard, coding, codes, queries, metric, maxval, probe_codes, mask, precision)
+            if fast is not None:
+                rows, dist = fast
+                keep = rows.reshape(-1) >= 0
+                out = take_rows(data, out_cols, rows.reshape(-1)[keep])
+                out = out.append_column(DIST_COL, _distance_array(dist.reshape(-1)[keep], typ.value_type))
+                qid = np.repeat(np.arange(rows.shape[0], dtype=np.int32), rows.shape[1])[keep]
+                return out.append_column(QUERY_COL, pa.array(qid, type=pa.int32())).combine_chunks()
+            # otherwise: the shard, the predicate mask and the code column are prepared once; each query is one masked
+            # search on the resident shard.
             parts = []
             for qi in range(queries.shape[0]):
                 cell = np.isin(codes, probe_codes[qi]).astype(np.uint8)
@@ -236,6 +247,39 @@ def call(
             shard.close()
         else:
             shard.release()   # the lease taken by shards.get
+
+
+def _search_cells(shard, coding, codes: np.ndarray, queries: np.ndarray, metric: str, maxval, probe_codes: np.ndarray,
+                  mask, precision):
+    """fx_search_cells for a batched IVF search, or None when the one-launch path does not apply (several devices, maxval
+    None or > 128, too many probes, an approximate precision mode)."""
+    if len(shard.corpora) != 1 or maxval is None or int(maxval) < 1 or precision != knn.PREC_FP32:
+        return None
+    corpus = shard.corpora[0]
+    if corpus.n_rows == 0 or corpus.n_rows != len(codes):
+        return None
+    with shard._cells_lock:
+        cells = shard._cells
+        if cells is None or cells[0] != coding:
+            uniq, dense = np.unique(codes, return_inverse=True)      # composite codes present in the sidecar -> 0 .. n_cells - 1
+            corpus.set_cells(dense)
+            cells = shard._cells = (coding, uniq)
+        uniq = cells[1]
+        # probe codes -> dense cell numbers; codes no row carries and repeated codes become -1
+        pc_ = np.asarray(probe_codes, dtype=np.int64)
+        pos_c = np.minimum(np.searchsorted(uniq, pc_), len(uniq) - 1)
+        dense_p = np.where(uniq[pos_c] == pc_, pos_c, -1).astype(np.int32)
+        srt = np.sort(dense_p, axis=1)
+        if ((srt[:, 1:] == srt[:, :-1]) & (srt[:, 1:] >= 0)).any():
+            for qi in range(dense_p.shape[0]):
+                _, first = np.unique(dense_p[qi], return_index=True)
+                dup = np.ones(dense_p.shape[1], dtype=bool)
+                dup[first] = False
+                dense_p[qi, dup] = -1
+        try:
+            return corpus.search_cells(queries, metric, min(int(maxval), corpus.n_rows), dense_p, mask)
+        except NotImplementedError:
+            return None
 
 
 def _batched_input(target) -> bool:

@@ -92,6 +92,10 @@ class ShardSet:
     _users: int = 0
     _retired: bool = False
     _guard: threading.Lock = field(default_factory=threading.Lock)
+    # batched IVF: the coding whose cells the (single) corpus currently holds as its inverted index + the sorted composite
+    # codes behind the dense cell numbers; `_cells_lock` spans "install the cells, then search them" (io/index.py)
+    _cells: Optional[tuple] = None
+    _cells_lock: threading.Lock = field(default_factory=threading.Lock)
 
     # ---- leases ----
     def lease(self) -> "ShardSet":

@@ -25,7 +25,7 @@ __all__ = [
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libfenix_knn.so"
 COMM_ID_BYTES = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FX_OK = 0
 FX_EINVAL, FX_ECUDA, FX_ENOMEM, FX_ESTATE, FX_EUNSUP = -1, -2, -3, -4, -5
@@ -41,6 +41,7 @@ ABI_SYMBOLS = (
     "fx_merge_topk", "fx_get_stats", "fx_debug_scores", "fx_last_error", "fx_abi_version", "fx_set_option",
     "fx_comm_unique_id", "fx_comm_init_rank", "fx_comm_destroy", "fx_search_sharded", "fx_search_sharded_device",
     "fx_group_create", "fx_group_size", "fx_group_ctx", "fx_group_search", "fx_group_destroy",
+    "fx_corpus_set_cells", "fx_search_cells",
 )
 
 
@@ -137,6 +138,8 @@ def load_library() -> ctypes.CDLL:
         lib.fx_group_ctx.argtypes = [vp, i32]
         lib.fx_group_search.argtypes = [vp, ctypes.POINTER(vp), vp, i64, i32, i32, i32, vp, vp, vp]
         lib.fx_group_destroy.argtypes = [vp]
+        lib.fx_corpus_set_cells.argtypes = [vp, vp, i64, vp, i64]
+        lib.fx_search_cells.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, vp, vp]
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
             if name not in ("fx_last_error", "fx_group_ctx"):
@@ -305,6 +308,44 @@ class Corpus:
         search, candidate all-gather, merge and result copy on one stream, one host synchronisation)."""
         fn = self._lib.fx_search_sharded_device if on_device else self._lib.fx_search_sharded
         _check(self._lib, fn(self._h, comm._h, q_ptr, n_q, metric, k, precision, mask_ptr, out_rows_ptr, out_dist_ptr))
+
+    # ---- batched IVF (index.py:113-126 for a whole query batch): rows grouped by cell, one launch per batch ----
+    def set_cells(self, cell_of_row: np.ndarray) -> int:
+        """Give the shard its inverted index: `cell_of_row[r]` = dense cell number (0 .. n_cells - 1) of local row r.
+        Returns n_cells."""
+        cells = np.ascontiguousarray(cell_of_row, dtype=np.int64)
+        if cells.shape != (self.n_rows,):
+            raise ValueError(f"cell_of_row must have shape ({self.n_rows},), got {cells.shape}")
+        n_cells = int(cells.max()) + 1 if cells.size else 0
+        inv = np.argsort(cells, kind="stable").astype(np.int32)          # rows grouped by cell, ascending row inside a cell
+        off = np.zeros(n_cells + 1, dtype=np.int64)
+        np.cumsum(np.bincount(cells, minlength=n_cells), out=off[1:])
+        _check(self._lib, self._lib.fx_corpus_set_cells(self._h, inv.ctypes.data, inv.size, off.ctypes.data, n_cells))
+        return n_cells
+
+    def search_cells(self, queries: np.ndarray, metric: str | int, k: int, probes: np.ndarray,
+                     row_mask: Optional[np.ndarray] = None) -> tuple[np.ndarray, np.ndarray]:
+        """Exact k-NN of every query among the rows of the cells it probes (`probes[q]`: cell numbers, -1 = unused, no
+        duplicates), ANDed with `row_mask`. One launch for the batch; NotImplementedError for shapes it does not take."""
+        m = metric if isinstance(metric, int) else metric_code(metric)
+        q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries)), dtype=np.float32)
+        if q.shape[1] != self.dim:
+            raise ValueError(f"expected queries of shape (*, {self.dim}), got {q.shape}")
+        pr = np.ascontiguousarray(np.atleast_2d(np.asarray(probes)), dtype=np.int32)
+        if pr.shape[0] != q.shape[0]:
+            raise ValueError(f"expected one probe list per query, got {pr.shape} for {q.shape[0]} queries")
+        n_q, k = q.shape[0], int(k)
+        out_rows = np.empty((n_q, max(k, 0)), dtype=np.int64)
+        out_dist = np.empty((n_q, max(k, 0)), dtype=np.float32)
+        mask_ptr = None
+        if row_mask is not None:
+            row_mask = np.ascontiguousarray(row_mask, dtype=np.uint8)
+            if row_mask.shape != (self.n_rows,):
+                raise ValueError(f"row_mask must have shape ({self.n_rows},), got {row_mask.shape}")
+            mask_ptr = row_mask.ctypes.data
+        _check(self._lib, self._lib.fx_search_cells(self._h, q.ctypes.data, n_q, m, k, pr.ctypes.data, pr.shape[1], mask_ptr,
+                                                    out_rows.ctypes.data, out_dist.ctypes.data))
+        return out_rows, out_dist
 
     def distances(self, query: np.ndarray, metric: str | int) -> np.ndarray:
         """Distance of one query to every row (the reference's maxval=None branch)."""

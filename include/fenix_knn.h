@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FX_ABI_VERSION 2
+#define FX_ABI_VERSION 3
 
 /* error codes */
 #define FX_OK 0
@@ -152,6 +152,21 @@ int fx_search(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, i
 int fx_search_device(fx_corpus* c, const float* d_queries, int64_t n_q, int32_t metric,
                      int32_t k, int32_t precision, const uint8_t* d_row_mask,
                      int64_t* d_out_rows, float* d_out_dist);
+
+/* ---- batched IVF: every query scans only the rows of the cells it probes -------------------------------------------
+ * The reference builds `__CODED_ID__ isin(probe codes)` per query and filters the table before the distance step
+ * (index.py:113-126, 161); a batch of Q queries is Q such filters. Here the shard keeps an inverted index - its rows
+ * grouped by cell - and ONE launch answers the whole batch: query q reads the posting lists of probes[q][*] (exact fp64
+ * distances, the direct scan's arithmetic), so the bytes read are the probed rows, not Q passes over the shard.
+ *   fx_corpus_set_cells: inv_rows [n_inv] LOCAL row positions grouped by cell (HOST), cell_off [n_cells + 1] offsets of
+ *                        every cell's slice (HOST). Replaces the shard's previous cell structure.
+ *   fx_search_cells:     probes [n_q * n_probe] cell numbers per query, -1 = unused slot, no cell twice in one query
+ *                        (HOST); row_mask as in fx_search (ANDed: index.py:119-126). k <= 128, n_probe <= 512, else
+ *                        FX_EUNSUP (the caller runs one masked fx_search per query instead). Lists shorter than k are
+ *                        padded with (-1, +inf). */
+int fx_corpus_set_cells(fx_corpus* c, const int32_t* inv_rows, int64_t n_inv, const int64_t* cell_off, int64_t n_cells);
+int fx_search_cells(fx_corpus* c, const float* queries, int64_t n_q, int32_t metric, int32_t k, const int32_t* probes,
+                    int32_t n_probe, const uint8_t* row_mask, int64_t* out_rows, float* out_dist);
 
 /* Full distance column of ONE query against every shard row (HOST in / HOST out,
  * out_dist[n_rows]). This is the `maxval is None or len(data) <= maxval` branch of

@@ -713,6 +713,47 @@ def test_direct_scan_masks_duplicates_and_trims(ctx):
     c.close()
 
 
+@pytest.mark.parametrize("shape", [(50_000, 64, 37, 10, 5, 300), (20_000, 200, 3, 100, 40, 64), (30_000, 128, 2, 33, 8, 16),
+                                   (5_000, 36, 400, 7, 3, 1000)])
+def test_search_cells_equals_per_query_masked_searches(ctx, shape):
+    """fx_search_cells (batched IVF in one launch: query q scans the posting lists of its probe cells) against one masked
+    fp64 scan per query with the mask the reference would build (`cell isin probes` AND the predicate, index.py:119-126):
+    ids and distances bit-equal, short lists padded."""
+    n, d, nq, k, n_probe, n_cells = shape
+    rng = np.random.default_rng(n + d + nq)
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    queries = rng.standard_normal((nq, d), dtype=np.float32)
+    cell = (rng.random(n) ** 2 * n_cells).astype(np.int64)              # uneven cells; some stay empty
+    cell[rng.integers(0, n, 5)] = n_cells - 1
+    pred = (rng.random(n) < 0.7).astype(np.uint8)
+    probes = np.stack([rng.choice(n_cells, n_probe, replace=False) for _ in range(nq)]).astype(np.int32)
+    probes[rng.random(probes.shape) < 0.15] = -1                        # unused slots
+    c = make_corpus(ctx, corpus)
+    assert c.set_cells(cell) == n_cells
+    for metric in ("l2", "cosine", "dot"):
+        for mask in (None, pred):
+            before = c.stats().kernel_launches
+            rows, dist = c.search_cells(queries, metric, k, probes, mask)
+            assert c.stats().kernel_launches - before == 1
+            for qi in range(0, nq, max(1, nq // 12)):
+                m_q = np.isin(cell, probes[qi][probes[qi] >= 0]).astype(np.uint8)
+                if mask is not None:
+                    m_q &= mask
+                want_rows, want_dist = c.search(queries[qi], metric, k, knn.PREC_EXACT_SCAN, row_mask=m_q)
+                assert np.array_equal(rows[qi], want_rows[0]) and np.array_equal(dist[qi], want_dist[0]), (metric, qi)
+                assert (rows[qi] >= 0).sum() == min(k, int(m_q.sum()))
+    # a second cell structure replaces the first; errors
+    assert c.set_cells(np.zeros(n, np.int64)) == 1
+    rows, dist = c.search_cells(queries[:2], "l2", k, np.zeros((2, 1), np.int32))
+    want_rows, want_dist = c.search(queries[:2], "l2", k, knn.PREC_EXACT_SCAN)
+    assert np.array_equal(rows, want_rows) and np.array_equal(dist, want_dist)
+    with pytest.raises(ValueError):
+        c.search_cells(queries[:2], "l2", k, np.full((2, 1), 7, np.int32))       # no such cell
+    with pytest.raises(NotImplementedError):
+        c.search_cells(queries[:2], "l2", 129, np.zeros((2, 1), np.int32))       # k > 128: the caller loops masked searches
+    c.close()
+
+
 def test_tensor_core_path_runs_and_certifies(ctx):
     """fp32 mode must take the tcgen05 path on ordinary data (no silent fallback to the scan) and the
     certificate must hold for (nearly) every query; tf32 mode reports its recall."""
@@ -917,6 +958,18 @@ def test_ivf_search_matches_live_reference_outputs(built_library, case, tmp_path
                     key = f"{m or 'default'}:{qi}:{int(p)}"
                     assert res.column_names == ["id", "__DISTANCE__"]
                     assert_same_neighbours(res.column("id").to_numpy(), res.column("__DISTANCE__").to_numpy(),
+                                           g[key + ":id"], g[key + ":dist"], g["corpus"], q, m or metric)
+        # the whole query batch in ONE call (batched wire extension; one fx_search_cells launch): per query the answer the
+        # live reference gave for that query alone
+        for p in g["probes"]:
+            for m in (None, "l2", "cosine", "dot"):
+                res = fenix.io.index.call(root, "cb", "t", "vector", g["queries"], metric=m, select=["id"], filter=flt,
+                                          maxval=int(g["k"]), probes=int(p))
+                assert res.column_names == ["id", "__DISTANCE__", "__QUERY__"]
+                for qi, q in enumerate(g["queries"]):
+                    sel = res.filter(pc.field("__QUERY__") == qi)
+                    key = f"{m or 'default'}:{qi}:{int(p)}"
+                    assert_same_neighbours(sel.column("id").to_numpy(), sel.column("__DISTANCE__").to_numpy(),
                                            g[key + ":id"], g[key + ":dist"], g["corpus"], q, m or metric)
         # default projection carries the code column, as the joined table does in the reference (index.py:128)
         res = fenix.io.index.call(root, "cb", "t", "vector", g["queries"][0], metric=metric, maxval=3, probes=2)
