@@ -206,6 +206,18 @@ def call(
                 return empty.append_column(QUERY_COL, pa.array([], type=pa.int32())).combine_chunks()
             return pa.concat_tables(parts).combine_chunks()
 
+        if probe_codes is not None and mask is None and maxval is not None:
+            # one query, no predicate: the probed cells' sizes say whether more than maxval rows survive; if so the search
+            # reads just those cells' rows (fx_search_cells) instead of building an N-byte mask on the host and passing
+            # over the whole shard
+            fast = _search_cells(shard, coding, data.column(CODE_COL).to_numpy(), queries, metric, maxval, probe_codes, None,
+                                 precision, more_than=int(maxval))
+            if fast is not None:
+                rows, dist = fast
+                keep = rows[0] >= 0
+                out = take_rows(data, out_cols, rows[0][keep])
+                return out.append_column(DIST_COL, _distance_array(dist[0][keep], typ.value_type)).combine_chunks()
+
         if probe_codes is not None:
             # `__CODED_ID__ isin(probe codes)` AND the caller's predicate (index.py:119-126)
             cell = np.isin(data.column(CODE_COL).to_numpy(), probe_codes[0]).astype(np.uint8)
@@ -250,9 +262,10 @@ def call(
 
 
 def _search_cells(shard, coding, codes: np.ndarray, queries: np.ndarray, metric: str, maxval, probe_codes: np.ndarray,
-                  mask, precision):
-    """fx_search_cells for a batched IVF search, or None when the one-launch path does not apply (several devices, maxval
-    None or > 128, too many probes, an approximate precision mode)."""
+                  mask, precision, more_than: int | None = None):
+    """fx_search_cells for an IVF search, or None when the one-launch path does not apply (several devices, maxval None or
+    > 128, too many probes, an approximate precision mode; `more_than`: the first query's probed cells hold no more rows
+    than that - the caller then returns every surviving row instead, index.py:162-165)."""
     if len(shard.corpora) != 1 or maxval is None or int(maxval) < 1 or precision != knn.PREC_FP32:
         return None
     corpus = shard.corpora[0]
@@ -263,7 +276,7 @@ def _search_cells(shard, coding, codes: np.ndarray, queries: np.ndarray, metric:
         if cells is None or cells[0] != coding:
             uniq, dense = np.unique(codes, return_inverse=True)      # composite codes present in the sidecar -> 0 .. n_cells - 1
             corpus.set_cells(dense)
-            cells = shard._cells = (coding, uniq)
+            cells = shard._cells = (coding, uniq, np.bincount(dense, minlength=len(uniq)))
         uniq = cells[1]
         # probe codes -> dense cell numbers; codes no row carries and repeated codes become -1
         pc_ = np.asarray(probe_codes, dtype=np.int64)
@@ -276,6 +289,8 @@ def _search_cells(shard, coding, codes: np.ndarray, queries: np.ndarray, metric:
                 dup = np.ones(dense_p.shape[1], dtype=bool)
                 dup[first] = False
                 dense_p[qi, dup] = -1
+        if more_than is not None and int(cells[2][dense_p[0][dense_p[0] >= 0]].sum()) <= more_than:
+            return None
         try:
             return corpus.search_cells(queries, metric, min(int(maxval), corpus.n_rows), dense_p, mask)
         except NotImplementedError:

@@ -45,6 +45,16 @@ for metric, k in (("l2", 10), ("cosine", 100), ("dot", 10), ("l2", 1500)):
               f"exchange {st.last_exchange_ms:.3f} ms", flush=True)
         ok &= same_dev and same_host
     print(f"  rank {rank}: fallback_queries={st.fallback_queries} refined_queries={st.refined_queries}", flush=True)
+# a handful of queries: every rank answers its shard with ONE direct-scan launch (direct_scan.cuh), then the same exchange
+for nq_small in (1, 5):
+    m = knn.metric_code("l2")
+    rows, dist = searcher.search_device(d_q[:nq_small].contiguous(), m, 10)
+    st = shard.stats()
+    if rank == 0:
+        want_rows, want_dist = whole.search(queries[:nq_small], "l2", 10)
+        same = np.array_equal(rows.cpu().numpy(), want_rows) and np.array_equal(dist.cpu().numpy(), want_dist)
+        print(f"world={world} l2 k=10, {nq_small} queries (shard path {st.last_path}): == unsharded: {same}", flush=True)
+        ok &= same and st.last_path == 3
 td.barrier()
 if rank == 0:
     whole.close()
