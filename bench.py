@@ -491,6 +491,59 @@ def time_single_gpu(corpus, ctx, cfg, device, steps, warmup, pk, label, variant=
     return out
 
 
+def ivf_block(corpus, cfg: dict, device, n_cells=1024, n_probe=8, n_q=256, k=10) -> dict:
+    """SURVEY section 8f rank 4 at C2 scale: a batch of IVF searches (coding + probes; here: cells = nearest of 1024 random
+    centroids, probes = a query's 8 nearest centroids) as ONE fx_search_cells launch, against the loop of per-query masked
+    searches it replaces (the reference's per-query `isin` filter, index.py:119-126), same answers required."""
+    import torch
+
+    from fenix_b200 import knn
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(4242)
+    cent = torch.randn((n_cells, cfg["d"]), generator=gen, device=device, dtype=torch.float32)
+    cells = []
+    for ci in range((cfg["n"] + GEN_CHUNK - 1) // GEN_CHUNK):
+        block = gen_chunk(cfg, ci, device)[: min(GEN_CHUNK, cfg["n"] - ci * GEN_CHUNK)]
+        cells.append(torch.cdist(block, cent).argmin(dim=1).cpu().numpy())
+    cell = np.concatenate(cells).astype(np.int64)
+    h_q = query_batch(cfg)[:n_q]
+    probes = torch.cdist(torch.from_numpy(h_q).to(device), cent).topk(n_probe, dim=1, largest=False).indices.cpu().numpy().astype(np.int32)
+    corpus.set_cells(cell)
+    sizes = np.bincount(cell, minlength=n_cells)
+    probed = float(sizes[probes].sum(1).mean())
+    for _ in range(3):
+        rows, dist = corpus.search_cells(h_q, cfg["metric"], k, probes)
+    t, dev_ms = [], []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        rows, dist = corpus.search_cells(h_q, cfg["metric"], k, probes)
+        t.append(time.perf_counter() - t0)
+        dev_ms.append(corpus.stats().last_search_ms)
+    one = float(np.median(t))
+    n_loop, same = 8, True
+    masks = [np.isin(cell, probes[i]).astype(np.uint8) for i in range(n_loop)]
+    corpus.search(h_q[0], cfg["metric"], k, knn.PREC_FP32, row_mask=masks[0])
+    t0 = time.perf_counter()
+    for i in range(n_loop):
+        r, dd = corpus.search(h_q[i], cfg["metric"], k, knn.PREC_FP32, row_mask=masks[i])
+        same = same and np.array_equal(r[0], rows[i]) and np.array_equal(dd[0], dist[i])
+    loop = (time.perf_counter() - t0) / n_loop * n_q
+    r_s, d_s = corpus.search(h_q[n_loop], cfg["metric"], k, knn.PREC_EXACT_SCAN, row_mask=np.isin(cell, probes[n_loop]).astype(np.uint8))
+    same = same and np.array_equal(r_s[0], rows[n_loop]) and np.array_equal(d_s[0], dist[n_loop])
+    return {
+        "workload": f"batched IVF over the C2 corpus: {n_cells} cells, {n_probe} probes, k={k}, {n_q} queries per call (host buffers in and out)",
+        "probed_rows_per_query": probed, "ms_per_step": one * 1e3, "value": n_q / one, "unit": "queries/s",
+        "kernel": "knn_direct_kernel<LISTS> (one launch per batch: query q scans the posting lists of its probe cells)",
+        "kernel_ms": float(np.mean(dev_ms)),
+        "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": probed * cfg["d"] * 4 * n_q / (float(np.mean(dev_ms)) * 1e-3) / 1e9,
+                     "note": "bytes of the probed rows (gathered 512-byte rows) / device time of the call incl. its copies"},
+        "masked_loop_ms_per_step": loop * 1e3, "masked_loop_note": f"one masked fx_search per query, extrapolated from {n_loop} queries",
+        "speedup_over_masked_loop": loop / one,
+        "parity": {"checked_queries": n_loop + 1, "ok": bool(same), "how": "bit-equal to the per-query masked searches (tensor-core path) and to a masked fp64 scan"},
+    }
+
+
 def also_block(args, ctx, c3_corpus, device, pk) -> dict:
     """The other BASELINE configs that fit one GPU and SURVEY section 8d's stress inputs, as compact lines (N = 1 only)."""
     import torch
@@ -505,6 +558,8 @@ def also_block(args, ctx, c3_corpus, device, pk) -> dict:
         cfg = dict(CONFIGS[name])
         corpus = build_shard(cfg, ctx, 0, cfg["n"], device)
         out[name] = time_single_gpu(corpus, ctx, cfg, device, steps, warmup, pk, cfg["label"])
+        if name == "c2":
+            out["ivf_batched"] = ivf_block(corpus, cfg, device)
         corpus.close()
     # C1 shape, one query per search: the latency path. The 51 MB shard is L2-resident in steady state (that IS the
     # serving regime of a shard this small; nothing is flushed between searches and the line says so).
