@@ -23,7 +23,8 @@
 namespace fx {
 
 constexpr int DS_THREADS = 512;          // 16 warps: 64 rows per CTA and step, three steps in flight
-constexpr int DS_MAX_Q = 8;              // queries per launch
+constexpr int DS_MAX_Q = 8;              // queries per search (four per launch)
+constexpr int DS_LAUNCH_Q = 4;
 constexpr int DS_MAX_K = 128;
 constexpr int DS_ROWS_PER_STEP = DS_THREADS / 8;         // 8 lanes per row, one row per lane group and step
 constexpr int DS_CAP_STEPS = 16;         // steps whose raw sums are parked in shared memory between flushes (at most)
@@ -197,9 +198,11 @@ knn_direct_kernel(DirectParams p) {
   const int my_steps = int64_t(blockIdx.x) < n_steps ? int((n_steps - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
   const int total = my_steps * C;
   int parked = 0;                                     // steps parked in `sums` since the last flush
-  double xx = 0.0, qx[NQ];
+  // one accumulator per float4 component and sum (four independent fp64 chains each): the library's canonical order,
+  // see the finish kernel's rerank (tc_filter.cuh)
+  double xa[4] = {0.0, 0.0, 0.0, 0.0}, qa[NQ][4];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) qx[q] = 0.0;
+  for (int q = 0; q < NQ; ++q) { qa[q][0] = 0.0; qa[q][1] = 0.0; qa[q][2] = 0.0; qa[q][3] = 0.0; }
   double qreg[QREG ? 16 : 1];
   if constexpr (QREG) {
 #pragma unroll
@@ -272,16 +275,17 @@ knn_direct_kernel(DirectParams p) {
       for (int u = 0; u < 4; ++u) {
         const int j = ch * 32 + sub + 8 * u;           // (j >= n4: x is zero, the query row is zero-padded to whole chunks)
         const double a0 = x[u].x, a1 = x[u].y, a2 = x[u].z, a3 = x[u].w;
-        xx = fma(a0, a0, xx); xx = fma(a1, a1, xx); xx = fma(a2, a2, xx); xx = fma(a3, a3, xx);
+        xa[0] = fma(a0, a0, xa[0]); xa[1] = fma(a1, a1, xa[1]); xa[2] = fma(a2, a2, xa[2]); xa[3] = fma(a3, a3, xa[3]);
         if constexpr (QREG) {
-          qx[0] = fma(a0, qreg[4 * u], qx[0]); qx[0] = fma(a1, qreg[4 * u + 1], qx[0]);
-          qx[0] = fma(a2, qreg[4 * u + 2], qx[0]); qx[0] = fma(a3, qreg[4 * u + 3], qx[0]);
+          qa[0][0] = fma(a0, qreg[4 * u], qa[0][0]); qa[0][1] = fma(a1, qreg[4 * u + 1], qa[0][1]);
+          qa[0][2] = fma(a2, qreg[4 * u + 2], qa[0][2]); qa[0][3] = fma(a3, qreg[4 * u + 3], qa[0][3]);
         } else {
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
             const double2* qp = reinterpret_cast<const double2*>(qs + size_t(q) * pitch_q + 4 * j);
             const double2 v0 = qp[0], v1 = qp[1];
-            qx[q] = fma(a0, v0.x, qx[q]); qx[q] = fma(a1, v0.y, qx[q]); qx[q] = fma(a2, v1.x, qx[q]); qx[q] = fma(a3, v1.y, qx[q]);
+            qa[q][0] = fma(a0, v0.x, qa[q][0]); qa[q][1] = fma(a1, v0.y, qa[q][1]);
+            qa[q][2] = fma(a2, v1.x, qa[q][2]); qa[q][3] = fma(a3, v1.y, qa[q][3]);
           }
         }
       }
@@ -290,6 +294,9 @@ knn_direct_kernel(DirectParams p) {
     // the row is complete: reduce over the group's 8 lanes and park the raw sums (lane `sub` stores q.x of query `sub`)
     const int slot = parked * DS_ROWS_PER_STEP + warp * 4 + grp;
     if (__any_sync(0xffffffffu, live)) {
+      double xx = (xa[0] + xa[1]) + (xa[2] + xa[3]), qx[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) qx[q] = (qa[q][0] + qa[q][1]) + (qa[q][2] + qa[q][3]);
 #pragma unroll
       for (int o = 16; o > 2; o >>= 1) {   // sub ^ 4, sub ^ 2, sub ^ 1: the finish kernel's tree
         xx += __shfl_xor_sync(0xffffffffu, xx, o);
@@ -303,9 +310,12 @@ knn_direct_kernel(DirectParams p) {
       if (sub == 0) sums[size_t(slot) * (NQ + 1)] = xx;
     }
     if (sub == 0) rowid[slot] = live ? rowreg : -1;
-    xx = 0.0;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) qx[q] = 0.0;
+    for (int e = 0; e < 4; ++e) {
+      xa[e] = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) qa[q][e] = 0.0;
+    }
     if (++parked == p.cap_steps) { flush(parked); parked = 0; }
   };
   {
@@ -403,14 +413,14 @@ knn_direct_kernel(DirectParams p) {
 }
 
 // ---- host side ----
-struct DirectPlan { bool ok = false; int nq_t = 0; int r = 0; int grid = 0; int cap_steps = 0; size_t smem = 0; size_t partial_bytes = 0; };
+struct DirectPlan { bool ok = false; bool qreg = true; int nq_t = 0; int r = 0; int grid = 0; int cap_steps = 0; size_t smem = 0; size_t partial_bytes = 0; };
 
 // Shapes the kernel takes: a handful of queries, k <= 128, queries + the warps' lists + at least one step of parked
 // sums within shared memory.
 inline DirectPlan direct_plan(int64_t n_rows, int pitch, int64_t n_q, int k, int sm_count) {
   DirectPlan pl;
   if (n_rows < 1 || n_rows > (int64_t(1) << 31) - 1 || n_q < 1 || n_q > DS_MAX_Q || k < 1 || k > DS_MAX_K) return pl;
-  pl.nq_t = n_q <= 1 ? 1 : n_q <= 2 ? 2 : n_q <= 4 ? 4 : 8;
+  pl.nq_t = n_q <= 1 ? 1 : n_q <= 2 ? 2 : 4;     // more than four queries: two launches (the caller splits the batch)
   pl.r = k <= 32 ? 1 : k <= 64 ? 2 : 4;
   const int64_t n_steps = (n_rows + DS_ROWS_PER_STEP - 1) / DS_ROWS_PER_STEP;
   pl.grid = int(std::max<int64_t>(1, std::min<int64_t>(sm_count, n_steps)));
@@ -443,13 +453,12 @@ inline cudaError_t direct_set_attributes() {
   cudaError_t e = direct_attr_q<1>();
   if (e == cudaSuccess) e = direct_attr_q<2>();
   if (e == cudaSuccess) e = direct_attr_q<4>();
-  if (e == cudaSuccess) e = direct_attr_q<8>();
   return e;
 }
 
 template <int NQ, int R>
 inline void direct_launch_qr(const DirectPlan& pl, const DirectParams& p, cudaStream_t stream) {
-  if (NQ == 1 && p.pitch <= 128) knn_direct_kernel<1, R, true><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p);
+  if (NQ == 1 && p.pitch <= 128 && pl.qreg) knn_direct_kernel<1, R, true><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p);
   else knn_direct_kernel<NQ, R, false><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p);
 }
 template <int NQ>
@@ -464,8 +473,7 @@ inline cudaError_t direct_launch(const DirectPlan& pl, const DirectParams& p, cu
   switch (pl.nq_t) {
     case 1: direct_launch_q<1>(pl, p, stream); break;
     case 2: direct_launch_q<2>(pl, p, stream); break;
-    case 4: direct_launch_q<4>(pl, p, stream); break;
-    default: direct_launch_q<8>(pl, p, stream); break;
+    default: direct_launch_q<4>(pl, p, stream); break;
   }
   return cudaGetLastError();
 }

@@ -736,37 +736,35 @@ static int search_enqueue(fx_corpus* c, const float* d_q, int64_t n_q, int metri
     FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k0, ctx->stream, ev_flags));
     FX_CUDA(cudaEventRecordWithFlags(ctx->ev_k1, ctx->stream, ev_flags));
   } else if (dpl.ok) {
-    // one kernel: fp64 distances of every (live) row, per-CTA top-k, merge by the last CTA. d_out_* may be mapped pinned
-    // host memory (fx_search passes its staging buffers and, for small query blocks, the queries by value: no copies)
+    // one kernel per four queries: fp64 distances of every (live) row, per-CTA top-k, join by the last CTA. d_out_* may be
+    // mapped pinned host memory (fx_search passes its staging buffers and, for small query blocks, the queries by value:
+    // no copies)
     FX_TRY(ctx->d_partial.ensure(dpl.partial_bytes));
-    fx::DirectParams p{};
-    p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.row_base = c->row_base;
-    p.Q = d_q; p.n_q = int(n_q); p.metric = metric; p.k = k; p.mask = d_mask;
-    if (run->inline_q != nullptr) { p.Q = nullptr; std::memcpy(p.q_inline, run->inline_q, size_t(n_q) * c->dim * sizeof(float)); }
-    p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.ticket = ctx->d_ticket; p.cap_steps = dpl.cap_steps;
-    p.out_rows = d_out_rows; p.out_dist = d_out_dist;
-    if (spin) { p.done = ctx->h_done; p.seq = ++ctx->direct_seq; }
     if (ctx->tc.knobs.debug_direct) {
       FX_TRY(ctx->h_flags.ensure(size_t(512) * 8));
       std::memset(ctx->h_flags.p, 0, 512 * 8);
-      p.dbg = static_cast<unsigned long long*>(ctx->h_flags.p);
     }
-    FX_CUDA(fx::direct_launch(dpl, p, ctx->stream));
-    if (ctx->tc.knobs.debug_direct) {
-      // watchdog: a kernel that has not finished after 3 s is reported (last source line each warp of CTA 0 reached) and the process ends
-      const unsigned long long* t = static_cast<const unsigned long long*>(ctx->h_flags.p);
-      volatile unsigned long long* done = static_cast<volatile unsigned long long*>(ctx->h_flags.p) + 500;
-      std::thread([t, done]() {
-        std::this_thread::sleep_for(std::chrono::seconds(3));
-        if (*done) return;
-        fprintf(stderr, "[fenix direct] kernel still running after 3 s; last source line reached per warp of CTA 0:");
-        for (int w = 0; w < 16; ++w) fprintf(stderr, " %llu", t[400 + w]);
-        fprintf(stderr, "\n");
-        fflush(stderr);
-        _exit(3);
-      }).detach();
+    for (int64_t q0 = 0; q0 < n_q; q0 += fx::DS_LAUNCH_Q) {
+      const int64_t nq_l = std::min<int64_t>(fx::DS_LAUNCH_Q, n_q - q0);
+      fx::DirectPlan pl = fx::direct_plan(c->n, c->pitch, nq_l, k, ctx->sm_count);
+      pl.qreg = ctx->tc.knobs.direct_qreg != 0;
+      fx::DirectParams p{};
+      p.X = c->X; p.n_rows = c->n; p.pitch = c->pitch; p.dim = c->dim; p.row_base = c->row_base;
+      p.Q = d_q + q0 * c->dim; p.n_q = int(nq_l); p.metric = metric; p.k = k; p.mask = d_mask;
+      if (run->inline_q != nullptr) { p.Q = nullptr; std::memcpy(p.q_inline, run->inline_q + q0 * c->dim, size_t(nq_l) * c->dim * sizeof(float)); }
+      p.partial = static_cast<uint64_t*>(ctx->d_partial.p); p.ticket = ctx->d_ticket; p.cap_steps = pl.cap_steps;
+      p.out_rows = d_out_rows + q0 * k; p.out_dist = d_out_dist + q0 * k;
+      const bool last = q0 + fx::DS_LAUNCH_Q >= n_q;
+      // (launches of one stream complete in order: the host waits for the last one's word; the first one leaves its time in [3])
+      if (spin) {
+        if (q0 == 0) ctx->h_done[3] = 0;
+        p.done = last ? ctx->h_done : ctx->h_done + 2;
+        p.seq = last ? ++ctx->direct_seq : 0;
+      }
+      if (ctx->tc.knobs.debug_direct && last) p.dbg = static_cast<unsigned long long*>(ctx->h_flags.p);
+      FX_CUDA(fx::direct_launch(pl, p, ctx->stream));
+      ctx->launches++; c->stats.kernel_launches++;
     }
-    ctx->launches++; c->stats.kernel_launches++;
     run->path = 3;
   } else if (want_tc) {
     fx::TcSearch& s = run->s;
@@ -914,7 +912,7 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
 static void search_account(fx_corpus* c, const SearchRun& run) {
   fx_ctx* ctx = c->ctx;
   float ms = 0.f, kms = 0.f;
-  if (run.spin && run.path == 3) ms = float(double(ctx->h_done[1]) * 1e-6);   // the kernel's own globaltimer stamps
+  if (run.spin && run.path == 3) ms = float(double(ctx->h_done[1] + ctx->h_done[3]) * 1e-6);   // the kernels' own globaltimer stamps
   else cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
   if (run.path == 3) kms = ms;   // the direct scan is its one kernel (no inner events: they cost host time on the latency path)
   else cudaEventElapsedTime(&kms, ctx->ev_k0, ctx->ev_k1);

@@ -121,6 +121,8 @@ struct TcKnobs {
   int direct_mb = 256;     // FENIX_DIRECT_MAX_MB  largest shard (MB of fp32 rows) the direct scan takes
   int direct_spin = 1;     // FENIX_DIRECT_SPIN    fx_search waits for a direct scan by spinning on the kernel's completion word in mapped
                            //                      host memory (0: cudaStreamSynchronize, events around the launch)
+  int direct_qreg = 0;     // FENIX_DIRECT_QREG    1: the direct scan keeps a single narrow query in registers instead of shared memory (measured
+                           //                      slower: the 32 extra registers spill)
   int debug_direct = 0;    // FENIX_DEBUG_DIRECT   stderr timeline (globaltimer stamps) of every direct scan launched by fx_search
 };
 // name = the environment variable's name; value = its text, or null to restore the default. False: unknown name.
@@ -158,6 +160,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_DIRECT_MAX_MB") k->direct_mb = as_int(d.direct_mb);
   else if (n == "FENIX_DEBUG_DIRECT") k->debug_direct = as_flag();
   else if (n == "FENIX_DIRECT_SPIN") k->direct_spin = as_int(d.direct_spin);
+  else if (n == "FENIX_DIRECT_QREG") k->direct_qreg = as_int(d.direct_qreg);
   else return false;
   return true;
 }
@@ -166,7 +169,7 @@ inline void tc_knobs_from_env(TcKnobs* k) {
       "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_MAX_WAVES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
       "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SMALL", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
       "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
-      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH", "FENIX_DIRECT", "FENIX_DIRECT_MAX_MB", "FENIX_DEBUG_DIRECT", "FENIX_DIRECT_SPIN"};
+      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH", "FENIX_DIRECT", "FENIX_DIRECT_MAX_MB", "FENIX_DEBUG_DIRECT", "FENIX_DIRECT_SPIN", "FENIX_DIRECT_QREG"};
   for (const char* name : names) {
     if (const char* v = std::getenv(name)) tc_set_knob(k, name, v);
   }
@@ -1381,16 +1384,21 @@ knn_tc_finish_kernel(FinishParams p) {
       const bool live = c < n_gt || (!keep_all && c >= p.kp - n_tie_kept && c < p.kp);
       const uint32_t row = live ? cand[c] : 0u;
       const float4* xp = reinterpret_cast<const float4*>(p.X + size_t(row) * p.pitch);
-      double xx = 0.0, qx = 0.0;
+      // THE summation order of every exact distance this library reports from 8-lane groups (here and in
+      // direct_scan.cuh, bit for bit): per lane one accumulator per float4 component over j = sub, sub + 8, ...; lane
+      // total = (x + y) + (z + w); then the xor tree over the 8 lanes. Four independent chains per sum: the fp64 pipe's
+      // latency, not its rate, bounded the single-chain form.
+      double xa[4] = {0.0, 0.0, 0.0, 0.0}, qa[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
       for (int j = sub; j < n4; j += 8) {
         const float4 xv = live ? __ldg(xp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 qv = *reinterpret_cast<const float4*>(qs + 4 * j);
-        xx = fma(double(xv.x), double(xv.x), xx); qx = fma(double(xv.x), double(qv.x), qx);
-        xx = fma(double(xv.y), double(xv.y), xx); qx = fma(double(xv.y), double(qv.y), qx);
-        xx = fma(double(xv.z), double(xv.z), xx); qx = fma(double(xv.z), double(qv.z), qx);
-        xx = fma(double(xv.w), double(xv.w), xx); qx = fma(double(xv.w), double(qv.w), qx);
+        xa[0] = fma(double(xv.x), double(xv.x), xa[0]); qa[0] = fma(double(xv.x), double(qv.x), qa[0]);
+        xa[1] = fma(double(xv.y), double(xv.y), xa[1]); qa[1] = fma(double(xv.y), double(qv.y), qa[1]);
+        xa[2] = fma(double(xv.z), double(xv.z), xa[2]); qa[2] = fma(double(xv.z), double(qv.z), qa[2]);
+        xa[3] = fma(double(xv.w), double(xv.w), xa[3]); qa[3] = fma(double(xv.w), double(qv.w), qa[3]);
       }
+      double xx = (xa[0] + xa[1]) + (xa[2] + xa[3]), qx = (qa[0] + qa[1]) + (qa[2] + qa[3]);
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
         xx += __shfl_xor_sync(0xffffffffu, xx, o);
