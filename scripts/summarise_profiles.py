@@ -25,6 +25,9 @@ METRICS = [
     "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__cluster_dim_x", "launch__cluster_size",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__inst_executed.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
+    "smsp__pcsamp_warps_issue_stalled_short_scoreboard", "smsp__pcsamp_warps_issue_stalled_long_scoreboard",
+    "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle",
 ]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
@@ -36,6 +39,7 @@ CAPTURES = {
     "r02_prof_c4s.ncu-rep": ("r02_ncu_full_c4s_rq_main", "c4s", "python bench.py --config c4s ...; resident-query filter, main pass"),
     "r02_prof_c5_8.ncu-rep": ("r02_ncu_full_c5_8", "c5_8", "python bench.py --config c5_8 ...; one-CTA streaming filter, batch 8, main pass"),
     "r2i_c2_rq.ncu-rep": ("r02_ncu_full_c2_rq_main", "c2", "python bench.py --config c2 ...; resident-query filter, main pass"),
+    "r3n_direct.ncu-rep": ("r02_ncu_full_c1_direct", None, "python scripts/ubench/c1_one.py (100k x 128, one query, L2 k=10); single-launch direct scan, warm L2 (--cache-control none)"),
     # round 2, experiments that decided the design (before the sample prepass became the default for wide rows)
     "r2b_eighth_pair.ncu-rep": ("r02_ncu_full_c3_eighth_pair_noprepass", None, "one 8-GPU shard of C3, CTA-pair kernel, adaptive thresholds only (FENIX_TC_PRE_WIDE=0)"),
     "r2b_eighth_one.ncu-rep": ("r02_ncu_full_c3_eighth_onecta_noprepass", None, "one 8-GPU shard of C3, one-CTA kernel (FENIX_TC_PAIR=0), adaptive thresholds only"),
