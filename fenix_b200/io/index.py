@@ -178,7 +178,8 @@ def call(
             codes = data.column(CODE_COL).to_numpy()
             # One launch for the batch when the shard is on one device and the shape fits (k <= 128, <= 512 probes): the
             # shard keeps its rows grouped by cell and query q scans only the posting lists of its probe codes.
-            fast = _search_cells(shard, coding, codes, queries, metric, maxval, probe_codes, mask, precision)
+            # (a table passed in directly has no cached shard: grouping its rows by cell would be paid on every call)
+            fast = None if owned and queries.shape[0] < 16 else _search_cells(shard, coding, codes, queries, metric, maxval, probe_codes, mask, precision)
             if fast is not None:
                 rows, dist = fast
                 keep = rows.reshape(-1) >= 0
@@ -206,7 +207,7 @@ def call(
                 return empty.append_column(QUERY_COL, pa.array([], type=pa.int32())).combine_chunks()
             return pa.concat_tables(parts).combine_chunks()
 
-        if probe_codes is not None and mask is None and maxval is not None:
+        if probe_codes is not None and mask is None and maxval is not None and not owned:
             # one query, no predicate: the probed cells' sizes say whether more than maxval rows survive; if so the search
             # reads just those cells' rows (fx_search_cells) instead of building an N-byte mask on the host and passing
             # over the whole shard
