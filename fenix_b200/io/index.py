@@ -179,7 +179,8 @@ def call(
             # One launch for the batch when the shard is on one device and the shape fits (k <= 128, <= 512 probes): the
             # shard keeps its rows grouped by cell and query q scans only the posting lists of its probe codes.
             # (a table passed in directly has no cached shard: grouping its rows by cell would be paid on every call)
-            fast = None if owned and queries.shape[0] < 16 else _search_cells(shard, coding, codes, queries, metric, maxval, probe_codes, mask, precision)
+            fast = None if owned and queries.shape[0] < 16 else _search_cells(
+                shard, _cells_key(root, coding, source, column), codes, queries, metric, maxval, probe_codes, mask, precision)
             if fast is not None:
                 rows, dist = fast
                 keep = rows.reshape(-1) >= 0
@@ -211,8 +212,8 @@ def call(
             # one query, no predicate: the probed cells' sizes say whether more than maxval rows survive; if so the search
             # reads just those cells' rows (fx_search_cells) instead of building an N-byte mask on the host and passing
             # over the whole shard
-            fast = _search_cells(shard, coding, data.column(CODE_COL).to_numpy(), queries, metric, maxval, probe_codes, None,
-                                 precision, more_than=int(maxval))
+            fast = _search_cells(shard, _cells_key(root, coding, source, column), data.column(CODE_COL).to_numpy(), queries, metric,
+                                 maxval, probe_codes, None, precision, more_than=int(maxval))
             if fast is not None:
                 rows, dist = fast
                 keep = rows[0] >= 0
@@ -260,6 +261,22 @@ def call(
             shard.close()
         else:
             shard.release()   # the lease taken by shards.get
+
+
+def _cells_key(root: str, coding: str, source, column: str) -> tuple:
+    """Identity of the code column an inverted index was built from: the coding's name and the version (mtime, size) of
+    every sidecar file - `make_index` under the same name replaces the cells."""
+    if isinstance(source, pa.Table):
+        return (coding, id(source))
+    names = [source] if isinstance(source, str) else [*source]
+    sig = []
+    for one in names:
+        try:
+            st = os.stat(sidecar_path(root, coding, one, column))
+            sig.append((one, st.st_mtime_ns, st.st_size))
+        except OSError:
+            sig.append((one, None, None))
+    return (coding, tuple(sig))
 
 
 def _search_cells(shard, coding, codes: np.ndarray, queries: np.ndarray, metric: str, maxval, probe_codes: np.ndarray,
