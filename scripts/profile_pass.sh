@@ -12,4 +12,12 @@ ncu --set full --clock-control none --import-source on -k regex:knn_rq_filter_ke
 ncu --set full --clock-control none --import-source on -k regex:knn_tc_filter_kernel -s 5 -c 1 -o gpurun_out/${R}_prof_c5_8 $B --config c5_8 > gpurun_out/${R}_ncu_c5_8.log 2>&1; echo "ncu c5_8 rc=$?"
 timeout 300 python scripts/bench_flight.py > gpurun_out/${R}_flight_c1.txt 2> gpurun_out/${R}_flight_c1.err; echo "flight rc=$?"
 timeout 300 python scripts/latency_c1.py --c5 > gpurun_out/${R}_latency_c1.txt 2>&1; echo "latency rc=$?"
+# launch lists (every kernel of a short bench run, serialised): the dominant kernel's share of the step
+L="ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv"
+$L --log-file gpurun_out/${R}_launches_c3.csv python bench.py --steps 2 --warmup 1 --no-also --no-cpu-baseline --no-parity > /dev/null 2>&1; echo "launches c3 rc=$?"
+$L --log-file gpurun_out/${R}_launches_c2.csv python bench.py --steps 2 --warmup 1 --no-also --no-cpu-baseline --no-parity --config c2 > /dev/null 2>&1; echo "launches c2 rc=$?"
+$L --log-file gpurun_out/${R}_launches_c1.csv python scripts/ubench/c1_one.py > /dev/null 2>&1; echo "launches c1 rc=$?"
+# the latency path and batched IVF
+ncu --set full --cache-control none --clock-control none --import-source on -k regex:knn_direct -s 4 -c 1 -o gpurun_out/${R}_prof_c1_direct python scripts/ubench/c1_one.py > gpurun_out/${R}_ncu_c1.log 2>&1; echo "ncu c1 rc=$?"
+timeout 300 python scripts/bench_ivf.py > gpurun_out/${R}_ivf_batched.json 2>&1; echo "ivf rc=$?"
 ls -la gpurun_out/${R}_*
