@@ -1198,8 +1198,9 @@ extern "C" int fx_search_cells(fx_corpus* c, const float* queries, int64_t n_q, 
   FX_TRY(check_search_args(c, queries, n_q, metric, k, FX_PREC_FP32, out_rows, out_dist));
   if (n_q == 0) return FX_OK;
   if (!probes || n_probe < 1) return fail(FX_EINVAL, "fx_search_cells: no probes");
-  if (!c->d_cell_off) return fail(FX_ESTATE, "fx_search_cells: the shard has no cells (fx_corpus_set_cells)");
   fx_ctx* ctx = c->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);   // (also against a concurrent fx_corpus_set_cells on this shard)
+  if (!c->d_cell_off) return fail(FX_ESTATE, "fx_search_cells: the shard has no cells (fx_corpus_set_cells)");
   // the longest candidate list of the batch sizes the grid; cell numbers are validated on the way
   int64_t max_items = 0;
   for (int64_t q = 0; q < n_q; ++q) {
@@ -1215,7 +1216,6 @@ extern "C" int fx_search_cells(fx_corpus* c, const float* queries, int64_t n_q, 
   const fx::CellsPlan pl = fx::cells_plan(c->pitch, n_q, k, n_probe, max_items, ctx->sm_count);
   if (!pl.ok) return fail(FX_EUNSUP, "fx_search_cells: shape not supported by the one-launch path (k %d <= 128, probes %d <= 512, queries %lld <= 65535, dim %d)",
                           k, n_probe, (long long)n_q, c->dim);
-  std::lock_guard<std::mutex> lock(ctx->mu);
   FX_TRY(bind(ctx));
   const size_t q_bytes = size_t(n_q) * c->dim * sizeof(float), p_bytes = size_t(n_q) * n_probe * sizeof(int);
   const size_t r_bytes = size_t(n_q) * k * sizeof(int64_t), d_bytes = size_t(n_q) * k * sizeof(float);
