@@ -436,30 +436,18 @@ inline DirectPlan direct_plan(int64_t n_rows, int pitch, int64_t n_q, int k, int
   return pl;
 }
 
-template <int NQ, int R>
-inline cudaError_t direct_attr() {
-  cudaError_t e = cudaFuncSetAttribute(knn_direct_kernel<NQ, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (NQ == 1 && e == cudaSuccess) e = cudaFuncSetAttribute(knn_direct_kernel<1, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  return e;
-}
-template <int NQ>
-inline cudaError_t direct_attr_q() {
-  cudaError_t e = direct_attr<NQ, 1>();
-  if (e == cudaSuccess) e = direct_attr<NQ, 2>();
-  if (e == cudaSuccess) e = direct_attr<NQ, 4>();
-  return e;
-}
-inline cudaError_t direct_set_attributes() {
-  cudaError_t e = direct_attr_q<1>();
-  if (e == cudaSuccess) e = direct_attr_q<2>();
-  if (e == cudaSuccess) e = direct_attr_q<4>();
-  return e;
+// More than 48 KB of dynamic shared memory needs the opt-in attribute; it is set at the launch that needs it (wide rows,
+// several queries with k > 64) rather than for all 24 instantiations at fx_init, which cost a second of module loading.
+template <typename K>
+inline void ds_launch(K kernel, dim3 grid, size_t smem, cudaStream_t stream, const DirectParams& p) {
+  if (smem > size_t(48) * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  kernel<<<grid, DS_THREADS, smem, stream>>>(p);
 }
 
 template <int NQ, int R>
 inline void direct_launch_qr(const DirectPlan& pl, const DirectParams& p, cudaStream_t stream) {
-  if (NQ == 1 && p.pitch <= 128 && pl.qreg) knn_direct_kernel<1, R, true><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p);
-  else knn_direct_kernel<NQ, R, false><<<pl.grid, DS_THREADS, pl.smem, stream>>>(p);
+  if (NQ == 1 && p.pitch <= 128 && pl.qreg) ds_launch(knn_direct_kernel<1, R, true, false>, dim3(pl.grid), pl.smem, stream, p);
+  else ds_launch(knn_direct_kernel<NQ, R, false, false>, dim3(pl.grid), pl.smem, stream, p);
 }
 template <int NQ>
 inline void direct_launch_q(const DirectPlan& pl, const DirectParams& p, cudaStream_t stream) {
@@ -502,22 +490,9 @@ inline CellsPlan cells_plan(int pitch, int64_t n_q, int k, int n_probe, int64_t 
 }
 
 template <int R>
-inline cudaError_t cells_attr() {
-  cudaError_t e = cudaFuncSetAttribute(knn_direct_kernel<1, R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(knn_direct_kernel<1, R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  return e;
-}
-inline cudaError_t cells_set_attributes() {
-  cudaError_t e = cells_attr<1>();
-  if (e == cudaSuccess) e = cells_attr<2>();
-  if (e == cudaSuccess) e = cells_attr<4>();
-  return e;
-}
-template <int R>
 inline void cells_launch_r(const CellsPlan& pl, const DirectParams& p, int n_q, cudaStream_t stream) {
   const dim3 grid(pl.ctas, n_q);
-  if (p.pitch <= 128) knn_direct_kernel<1, R, true, true><<<grid, DS_THREADS, pl.smem, stream>>>(p);
-  else knn_direct_kernel<1, R, false, true><<<grid, DS_THREADS, pl.smem, stream>>>(p);
+  ds_launch(knn_direct_kernel<1, R, false, true>, grid, pl.smem, stream, p);
 }
 inline cudaError_t cells_launch(const CellsPlan& pl, const DirectParams& p, int n_q, cudaStream_t stream) {
   switch (pl.r) {

@@ -250,8 +250,6 @@ extern "C" int fx_init(int device, fx_ctx** out) {
   FX_CUDA(cudaFuncSetAttribute(fx::exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   FX_CUDA(cudaFuncSetAttribute(fx::merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  FX_CUDA(fx::direct_set_attributes());
-  FX_CUDA(fx::cells_set_attributes());
   FX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_ticket), 256));
   FX_CUDA(cudaMemset(ctx->d_ticket, 0, 256));
   {

@@ -88,7 +88,7 @@ class MicroBatcher:
                     promoted.error = _PROMOTED
                     promoted.done.set()
                 try:
-                    rows, dist = runner(np.stack([r.query for r in batch]))
+                    rows, dist = runner(batch[0].query[None, :] if len(batch) == 1 else np.stack([r.query for r in batch]))
                     for i, r in enumerate(batch):
                         r.result = (rows[i], dist[i])
                 except BaseException as exc:  # every member of the batch sees the failure

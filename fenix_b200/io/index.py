@@ -61,6 +61,31 @@ def _chunk_bounds(data: pa.Table, name: str) -> np.ndarray:
     return bounds
 
 
+def _chunk_views(data: pa.Table, name: str):
+    """Zero-copy numpy views of the column's chunks (1-D for primitive values, (rows, D) for fixed-size lists of them),
+    cached with the chunk bounds; None when the column cannot be viewed (nulls, strings, nested types)."""
+    _chunk_bounds(data, name)
+    slot = _bounds_cache[id(data)][1]
+    key = ("views", name)
+    if key in slot:
+        return slot[key]
+    col = data.column(name)
+    typ = col.type
+    views = None
+    try:
+        if pa.types.is_fixed_size_list(typ) and (pa.types.is_floating(typ.value_type) or pa.types.is_integer(typ.value_type)):
+            d = typ.list_size
+            if all(c.null_count == 0 and c.values.null_count == 0 for c in col.chunks):
+                views = [c.values.to_numpy(zero_copy_only=True)[c.offset * d: (c.offset + len(c)) * d].reshape(len(c), d) for c in col.chunks]
+        elif pa.types.is_floating(typ) or pa.types.is_integer(typ):
+            if all(c.null_count == 0 for c in col.chunks):
+                views = [c.to_numpy(zero_copy_only=True) for c in col.chunks]
+    except (pa.ArrowInvalid, pa.ArrowNotImplementedError, ValueError):
+        views = None
+    slot[key] = views
+    return views
+
+
 def take_rows(data: pa.Table, columns: Sequence[str], rows: np.ndarray) -> pa.Table:
     """`data.select(columns).take(rows)` (index.py:163-166) for a FEW rows of a table with MANY chunks: every row is
     resolved to its chunk by bisection over chunk bounds cached per table and gathered there (one-row slices, one
@@ -80,6 +105,16 @@ def take_rows(data: pa.Table, columns: Sequence[str], rows: np.ndarray) -> pa.Ta
         bounds = _chunk_bounds(data, name)
         which = np.searchsorted(bounds, rows, side="right") - 1
         local = rows - bounds[which]
+        views = _chunk_views(data, name)
+        if views is not None:
+            # numeric columns: gather straight out of the chunks' buffers (a tenth of the cost of ten one-row slices)
+            if views[0].ndim == 2:
+                vals = np.stack([views[c][i] for c, i in zip(which.tolist(), local.tolist())])
+                out.append(pa.FixedSizeListArray.from_arrays(pa.array(vals.reshape(-1), type=col.type.value_type), col.type.list_size))
+            else:
+                vals = np.fromiter((views[c][i] for c, i in zip(which.tolist(), local.tolist())), dtype=views[0].dtype, count=len(rows))
+                out.append(pa.array(vals, type=col.type))
+            continue
         out.append(pa.concat_arrays([col.chunk(int(c)).slice(int(i), 1) for c, i in zip(which, local)]))
     return pa.Table.from_arrays(out, schema=sub.schema)
 
@@ -149,8 +184,8 @@ def call(
         shard = _shards.from_chunks(data.column(column))
         owned = True
     else:
-        base = _shards.load_table(root, source)   # raises like table.load when the file is missing
-        shard = _shards.get(root, source, column, base)
+        base, sig = _shards.load_table(root, source, with_signature=True)   # raises like table.load when the file is missing
+        shard = _shards.get(root, source, column, base, sig)
         # with a coding the table carries its `__CODED_ID__` sidecar column (index.py:93-95)
         data = load(root, coding, source, column) if coding is not None else base
         owned = False

@@ -9,6 +9,7 @@ backing files, so do_put / drop-table / remove invalidate it (SURVEY.md §5, §8
 """
 from __future__ import annotations
 
+import functools
 import os
 import threading
 from dataclasses import dataclass, field
@@ -184,10 +185,21 @@ def from_chunks(column: pa.ChunkedArray, device_ids: Optional[Sequence[int]] = N
     return shard
 
 
+@functools.lru_cache(maxsize=256)
+def _abs(root: str) -> str:
+    return os.path.abspath(root)
+
+
+@functools.lru_cache(maxsize=1024)
+def _path(root: str, name: str) -> str:
+    return _table.path_of(root, name)
+
+
 def _signature(root: str, names: Sequence[str]) -> tuple:
+    """Version of the backing files: (name, mtime, size) each - one stat per file and request."""
     sig = []
     for n in names:
-        st = os.stat(_table.path_of(root, n))
+        st = os.stat(_path(root, n))
         sig.append((n, st.st_mtime_ns, st.st_size))
     return tuple(sig)
 
@@ -195,30 +207,31 @@ def _signature(root: str, names: Sequence[str]) -> tuple:
 _tables: dict[tuple, tuple] = {}
 
 
-def load_table(root: str, source: str | Sequence[str]) -> pa.Table:
+def load_table(root: str, source: str | Sequence[str], with_signature: bool = False):
     """`io.table.load` with the parsed (memory-mapped, zero-copy) Table cached per file version: the
     reference re-maps and re-parses the IPC stream on every search (index.py:93-97, ~3.5 % of its query
     time at 100 chunks, more with many chunks)."""
     names = (source,) if isinstance(source, str) else tuple(source)
-    key = (os.path.abspath(root), names)
+    key = (_abs(root), names)
     sig = _signature(root, names)
     with _lock:
         hit = _tables.get(key)
-        if hit is not None and hit[0] == sig:
-            return hit[1]
-    table = _table.load(root, source)
-    with _lock:
-        _tables[key] = (sig, table)
-    return table
+    if hit is None or hit[0] != sig:
+        table = _table.load(root, source)
+        with _lock:
+            _tables[key] = (sig, table)
+    else:
+        table = hit[1]
+    return (table, sig) if with_signature else table
 
 
-def get(root: str, source: str | Sequence[str], column: str, table: pa.Table) -> ShardSet:
+def get(root: str, source: str | Sequence[str], column: str, table: pa.Table, signature: Optional[tuple] = None) -> ShardSet:
     """LEASED shard set for `column` of the named table(s): `with shards.get(...) as shard:` (or release() it). Uploads
     on first use - one upload per key however many request threads miss at once (single-flight); a set replaced by a
     newer table version is retired, not closed under the searches still running on it."""
     names = (source,) if isinstance(source, str) else tuple(source)
-    key = (os.path.abspath(root), names, column, tuple(devices()))
-    sig = _signature(root, names)
+    key = (_abs(root), names, column, tuple(devices()))
+    sig = _signature(root, names) if signature is None else signature   # (`signature`: the one load_table just took)
     with _lock:
         hit = _cache.get(key)
         if hit is not None and hit.signature == sig:

@@ -13,7 +13,7 @@ for r in rows[hdr + 1:]:
     k = re.sub(r"\(.*", "", r[name_i]).replace("void ", "")
     ns = float(r[val_i].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}.get(r[unit_i], 1)
     tot[k] += ns; cnt[k] += 1
-build = {k for k in tot if "row_norms" in k or "to_bf16_tiled" in k or not k.startswith("fx::")}   # + torch's synthetic-data generator
+build = {k for k in tot if "row_norms" in k or "to_bf16_tiled" in k or k.startswith("at::")}   # + torch's synthetic-data generator
 search_total = sum(v for k, v in tot.items() if k not in build)
 shutil.copyfile(src, dst + ".csv")
 with open(dst + "_shares.txt", "w") as f:

@@ -34,12 +34,12 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 # capture file -> (summary name, config key for ncu_traffic.json or None, note)
 CAPTURES = {
     # round 2 (the code at HEAD): scripts/profile_pass.sh
-    "r02_prof_c3.ncu-rep": ("r02_ncu_full_c3_pair_main", "c3", "python bench.py --steps 2 --warmup 2 ...; CTA-pair (cta_group::2) streaming filter, main pass (after the sample prepass)"),
+    "r02f_prof_c3.ncu-rep": ("r02_ncu_full_c3_pair_main", "c3", "python bench.py --steps 2 --warmup 2 ...; CTA-pair (cta_group::2) streaming filter, main pass (after the sample prepass)"),
     "r02_prof_c3_eighth.ncu-rep": ("r02_ncu_full_c3_eighth_pair_main", None, "python bench.py --rows 1250000 ...: one 8-GPU shard of C3 on one GPU; CTA-pair streaming filter, main pass"),
-    "r02_prof_c4s.ncu-rep": ("r02_ncu_full_c4s_rq_main", "c4s", "python bench.py --config c4s ...; resident-query filter, main pass"),
-    "r02_prof_c5_8.ncu-rep": ("r02_ncu_full_c5_8", "c5_8", "python bench.py --config c5_8 ...; one-CTA streaming filter, batch 8, main pass"),
+    "r02f_prof_c4s.ncu-rep": ("r02_ncu_full_c4s_rq_main", "c4s", "python bench.py --config c4s ...; resident-query filter, main pass"),
+    "r02f_prof_c5_8.ncu-rep": ("r02_ncu_full_c5_8", "c5_8", "python bench.py --config c5_8 ...; one-CTA streaming filter, batch 8, main pass"),
     "r2i_c2_rq.ncu-rep": ("r02_ncu_full_c2_rq_main", "c2", "python bench.py --config c2 ...; resident-query filter, main pass"),
-    "r3n_direct.ncu-rep": ("r02_ncu_full_c1_direct", None, "python scripts/ubench/c1_one.py (100k x 128, one query, L2 k=10); single-launch direct scan, warm L2 (--cache-control none)"),
+    "r02f_prof_c1_direct.ncu-rep": ("r02_ncu_full_c1_direct", None, "python scripts/ubench/c1_one.py (100k x 128, one query, L2 k=10); single-launch direct scan, warm L2 (--cache-control none)"),
     # round 2, experiments that decided the design (before the sample prepass became the default for wide rows)
     "r2b_eighth_pair.ncu-rep": ("r02_ncu_full_c3_eighth_pair_noprepass", None, "one 8-GPU shard of C3, CTA-pair kernel, adaptive thresholds only (FENIX_TC_PRE_WIDE=0)"),
     "r2b_eighth_one.ncu-rep": ("r02_ncu_full_c3_eighth_onecta_noprepass", None, "one 8-GPU shard of C3, one-CTA kernel (FENIX_TC_PAIR=0), adaptive thresholds only"),
