@@ -83,6 +83,31 @@ def test_coerce_target_forms():
         ix.coerce_target(np.ones(5), 6)
 
 
+def test_take_rows_over_column_kinds_and_slices():
+    """The gather out of cached chunk views (numeric and fixed-size-list columns without nulls) and the one-row-slice
+    fallback (nulls, strings, nested lists) both equal Table.take - also on a sliced table, whose chunks carry offsets."""
+    rng = np.random.default_rng(3)
+    n, chunk = 900, 50
+    batches = []
+    for lo in range(0, n, chunk):
+        ids = np.arange(lo, lo + chunk, dtype=np.int64)
+        vec = pa.FixedSizeListArray.from_arrays(pa.array(rng.standard_normal(chunk * 4).astype(np.float32)), 4)
+        ivec = pa.FixedSizeListArray.from_arrays(pa.array(rng.integers(0, 9, chunk * 3).astype(np.int32)), 3)
+        nullable = pa.array([None if i % 7 == 0 else int(i) for i in ids], type=pa.int32())
+        text = pa.array([f"row{i}" for i in ids])
+        f64 = pa.array(rng.standard_normal(chunk))
+        ragged = pa.array([[int(i)] * (i % 3) for i in ids], type=pa.list_(pa.int64()))
+        batches.append(pa.record_batch([pa.array(ids), vec, ivec, nullable, text, f64, ragged],
+                                       names=["id", "vector", "ivec", "nullable", "text", "f64", "ragged"]))
+    full = pa.Table.from_batches(batches)
+    for t in (full, full.slice(37, 700)):
+        rows = np.array([0, 5, t.num_rows - 1, 49, 50, 51, 333, 5], dtype=np.int64)
+        got = ix.take_rows(t, t.column_names, rows)
+        want = t.take(pa.array(rows))
+        assert got.schema == want.schema
+        assert got.combine_chunks() == want.combine_chunks()
+
+
 def test_take_rows_equals_table_take():
     rng = np.random.default_rng(0)
     corpus = rng.standard_normal((1000, 6), dtype=np.float32)
