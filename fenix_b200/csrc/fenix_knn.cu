@@ -1330,7 +1330,10 @@ extern "C" int fx_debug_scores(fx_corpus* c, const float* queries, int64_t n_q, 
 static int enqueue_merge(fx_ctx* ctx, const int64_t* d_rows, const float* d_dist, int n_lists, int64_t n_q, int k,
                          int64_t rows_stride, int64_t dist_stride, int64_t* d_out_rows, float* d_out_dist) {
   const int64_t total = int64_t(n_lists) * k;
-  if (total <= 8192) {
+  // the lists arrive sorted: ranking every entry by binary searches over the other lists beats re-sorting them in shared
+  // memory from ~128 candidates per query on (C4's exchange, 8 x 100 per query: 0.59 -> 0.35 ms; scripts/ubench/merge_bench.py)
+  const int rank_min = ctx->tc.knobs.merge_rank_min > 0 ? ctx->tc.knobs.merge_rank_min : 128;
+  if (total < rank_min && total <= 8192) {
     const int n_sort = next_pow2(std::max(int(total), 2));
     fx::merge_pairs_kernel<<<unsigned(n_q), 256, size_t(n_sort) * 12, ctx->stream>>>(
         d_rows, d_dist, n_lists, n_q, k, n_sort, rows_stride, dist_stride, d_out_rows, d_out_dist);

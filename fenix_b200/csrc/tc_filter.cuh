@@ -123,6 +123,8 @@ struct TcKnobs {
                            //                      host memory (0: cudaStreamSynchronize, events around the launch)
   int direct_qreg = 0;     // FENIX_DIRECT_QREG    1: the direct scan keeps a single narrow query in registers instead of shared memory (measured
                            //                      slower: the 32 extra registers spill)
+  int merge_rank_min = 0;  // FENIX_MERGE_RANK_MIN candidates per query (lists x k) from which the exchange merges by rank (binary searches
+                           //                      over the sorted lists) instead of a shared-memory sort; 0: built-in default
   int debug_direct = 0;    // FENIX_DEBUG_DIRECT   stderr timeline (globaltimer stamps) of every direct scan launched by fx_search
 };
 // name = the environment variable's name; value = its text, or null to restore the default. False: unknown name.
@@ -161,6 +163,7 @@ inline bool tc_set_knob(TcKnobs* k, const char* name, const char* value) {
   else if (n == "FENIX_DEBUG_DIRECT") k->debug_direct = as_flag();
   else if (n == "FENIX_DIRECT_SPIN") k->direct_spin = as_int(d.direct_spin);
   else if (n == "FENIX_DIRECT_QREG") k->direct_qreg = as_int(d.direct_qreg);
+  else if (n == "FENIX_MERGE_RANK_MIN") k->merge_rank_min = as_int(d.merge_rank_min);
   else return false;
   return true;
 }
@@ -169,7 +172,7 @@ inline void tc_knobs_from_env(TcKnobs* k) {
       "FENIX_TC_KP", "FENIX_TC_FULLK", "FENIX_TC_NO_RQ", "FENIX_TC_SLICES", "FENIX_TC_MAX_WAVES", "FENIX_TC_ORDER", "FENIX_TC_KP_LIST",
       "FENIX_TC_PRE_WIDE", "FENIX_TC_PRE", "FENIX_TC_PRE_SMALL", "FENIX_TC_PRE_SAFETY", "FENIX_TC_PRE_M", "FENIX_TC_PF", "FENIX_RQ_STAGES",
       "FENIX_FIN_THREADS", "FENIX_TC_WARM", "FENIX_TC_PAIR", "FENIX_TC_ERRCOL", "FENIX_FP32_FILTER_TF32", "FENIX_NO_REFINE",
-      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH", "FENIX_DIRECT", "FENIX_DIRECT_MAX_MB", "FENIX_DEBUG_DIRECT", "FENIX_DIRECT_SPIN", "FENIX_DIRECT_QREG"};
+      "FENIX_NO_NORM_SHADOW", "FENIX_DEBUG_BF16", "FENIX_DEBUG_TIERS", "FENIX_GRAPH", "FENIX_DIRECT", "FENIX_DIRECT_MAX_MB", "FENIX_DEBUG_DIRECT", "FENIX_DIRECT_SPIN", "FENIX_DIRECT_QREG", "FENIX_MERGE_RANK_MIN"};
   for (const char* name : names) {
     if (const char* v = std::getenv(name)) tc_set_knob(k, name, v);
   }
