@@ -1774,7 +1774,10 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
   pl.n_qp = (pl.n_qt + 1) / 2;
   // wider rows and at least two query tiles: CTA pairs (cta_group::2) over the bf16 shadow - each SM stages half of
   // every corpus block, two thirds of the one-CTA kernel's L2 -> SM operand traffic at the same tensor work
-  pl.pair = (!pl.rq && s.kind == 1 && pl.n_qt >= 2 && s.dbg == nullptr && kn.pair != 0) ? 1 : 0;
+  // (auto: from 7 k-blocks per row on. A tile of D = 384 is 24 MMAs and the pair's cluster-wide hand-offs cost more than
+  // the halved B traffic saves - 1452 vs 1541 TFLOP/s at uncapped clocks; from D = 512 the pair wins, 1645 vs 1519 TFLOP/s at
+  // D = 768: scripts/ubench/width_sweep.py, profiles/r02_sweep_row_width.txt)
+  pl.pair = (!pl.rq && s.kind == 1 && pl.n_qt >= 2 && s.dbg == nullptr && (kn.pair == 1 || (kn.pair < 0 && pl.n_kblocks >= 7))) ? 1 : 0;
   pl.n_qt_lists = pl.pair ? 2 * pl.n_qp : pl.n_qt;
   const int n_tiles_full = pl.rq ? int((s.n_rows + RQ_BN - 1) / RQ_BN) : pl.n_tiles;   // tiles in the kernel's own unit
   pl.tile_stride = pre ? s.sample_stride : 1;

@@ -20,6 +20,7 @@ for n, d, nq, k, metric in [(20_000, 256, 300, 10, "dot"), (50_000, 768, 130, 10
     c = knn.Corpus(ctx, n, d)
     c.append(x)
     c.finalize()
+    ctx.set_option("FENIX_TC_PAIR", 1)
     t0 = time.perf_counter()
     rows, dist = c.search(q, metric, k)
     dt = time.perf_counter() - t0
@@ -32,7 +33,9 @@ for n, d, nq, k, metric in [(20_000, 256, 300, 10, "dot"), (50_000, 768, 130, 10
     same = np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
     same1 = np.array_equal(rows1, rows_s) and np.array_equal(dist1, dist_s)
     mask = (np.arange(n) % 3 != 0).astype(np.uint8)
+    ctx.set_option("FENIX_TC_PAIR", 1)
     rows_m, dist_m = c.search(q, metric, k, row_mask=mask)
+    ctx.set_option("FENIX_TC_PAIR", None)
     stm = c.stats()
     rows_ms, dist_ms = c.search(q, metric, k, knn.PREC_EXACT_SCAN, row_mask=mask)
     same_m = np.array_equal(rows_m, rows_ms) and np.array_equal(dist_m, dist_ms)

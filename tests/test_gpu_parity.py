@@ -273,9 +273,10 @@ def test_merge_of_many_long_lists(ctx):
 @pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
 @pytest.mark.parametrize("shape", [(20_000, 256, 300, 10), (50_000, 768, 130, 10), (30_000, 200, 257, 37), (12_345, 448, 129, 100)])
 def test_cta_pair_streaming_kernel(ctx, shape, metric):
-    """Wide rows and at least two query tiles take the CTA-pair (cta_group::2) streaming kernel: ragged query tiles (the
-    second CTA of a pair holds a near-empty tile), odd widths, a row mask, and cosine without the normalised shadow (the
-    multiplicative epilogue) - all against the fp64 scan, a few queries against the oracle."""
+    """Wide rows (from 7 k-blocks on; narrower ones here by FENIX_TC_PAIR=1) and at least two query tiles take the CTA-pair
+    (cta_group::2) streaming kernel: ragged query tiles (the second CTA of a pair holds a near-empty tile), odd widths, a
+    row mask, and cosine without the normalised shadow (the multiplicative epilogue) - all against the fp64 scan, a few
+    queries against the oracle."""
     from oracle import search_rows
 
     n, d, nq, k = shape
@@ -283,8 +284,12 @@ def test_cta_pair_streaming_kernel(ctx, shape, metric):
     corpus = rng.standard_normal((n, d), dtype=np.float32)
     queries = rng.standard_normal((nq, d), dtype=np.float32)
     c = make_corpus(ctx, corpus)
+    rows_auto, dist_auto = c.search(queries, metric, k)
+    assert bool(c.stats().last_variant & 4) == (d >= 448), "auto: CTA pairs from 7 k-blocks per row on"
+    ctx.set_option("FENIX_TC_PAIR", 1)
     rows, dist = c.search(queries, metric, k)
     assert c.stats().last_variant & 4, "expected the CTA-pair kernel"
+    assert np.array_equal(rows, rows_auto) and np.array_equal(dist, dist_auto)
     rows_s, dist_s = c.search(queries, metric, k, knn.PREC_EXACT_SCAN)
     assert np.array_equal(rows, rows_s) and np.array_equal(dist, dist_s)
     table = table_of(corpus, 4096)
@@ -306,6 +311,7 @@ def test_cta_pair_streaming_kernel(ctx, shape, metric):
         finally:
             ctx.set_option("FENIX_NO_NORM_SHADOW", None)
         assert np.array_equal(rows_e, rows_s) and np.array_equal(dist_e, dist_s)
+    ctx.set_option("FENIX_TC_PAIR", None)
     c.close()
 
 
