@@ -439,7 +439,7 @@ def test_resident_query_kernel_and_sample_prepass(ctx, metric, dim, k):
     # the same search through the other kernels (tuning knobs are per-context options; the environment is only read
     # once, at fx_init): adaptive thresholds, the streaming kernels (CTA pairs, one CTA per tile)
     variants = ({"FENIX_TC_PRE": "0"}, {"FENIX_TC_NO_RQ": "1"}, {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PRE": "0"},
-                {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PAIR": "0"})
+                {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PAIR": "1"}, {"FENIX_TC_NO_RQ": "1", "FENIX_TC_PAIR": "1", "FENIX_TC_PRE": "0"})
     for opts in variants:
         for key, value in opts.items():
             ctx.set_option(key, value)
@@ -451,7 +451,8 @@ def test_resident_query_kernel_and_sample_prepass(ctx, metric, dim, k):
                 ctx.set_option(key, None)
         assert np.array_equal(rows, rows_e) and np.array_equal(dist, dist_e), opts
         if "FENIX_TC_NO_RQ" in opts:
-            assert (variant & 1) == 0 and bool(variant & 4) == ("FENIX_TC_PAIR" not in opts), (opts, variant)
+            # (rows this narrow take the one-CTA streaming kernel unless CTA pairs are forced)
+            assert (variant & 1) == 0 and bool(variant & 4) == (opts.get("FENIX_TC_PAIR") == "1"), (opts, variant)
     c.close()
 
 
