@@ -106,6 +106,34 @@ concurrent("fenix_b200 Flight, 16 concurrent clients, micro-batching OFF")
 fio.index._batcher.max_wait = wait
 concurrent("fenix_b200 Flight, 16 concurrent clients, micro-batching ON (300 us window)")
 
+# The same with the 16 clients in their OWN processes: the threads above share this process's GIL with the server's
+# handler threads (client-side pickling / Arrow glue is ~150 us of Python per request), so they measure the interpreter, not
+# the server. Separate client processes leave the server's GIL to the server.
+import subprocess
+def concurrent_procs(label, n_procs=16, per_proc=250):
+    q_path = os.path.join(root, "_queries.npy")
+    np.save(q_path, queries)
+    b0, r0 = fio.index._batcher.batches, fio.index._batcher.requests
+    start = time.time() + 8.0           # (every child has imported pyarrow and warmed its connection by then)
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_flight_client.py")
+    procs = [subprocess.Popen([sys.executable, script, str(port), q_path, METRIC, str(K), str(per_proc), repr(start)],
+                              stdout=subprocess.PIPE, text=True) for _ in range(n_procs)]
+    spans = []
+    for p_ in procs:
+        out_, _ = p_.communicate(timeout=300)
+        a_, e_ = out_.split()[-2:]
+        spans.append((float(a_), float(e_)))
+    nb, nr = fio.index._batcher.batches - b0, fio.index._batcher.requests - r0
+    dt = max(e for _, e in spans) - min(s_ for s_, _ in spans)
+    print(json.dumps({"arm": label, "queries": n_procs * per_proc, "qps": n_procs * per_proc / dt,
+                      "gpu_batches": nb, "mean_batch": (nr / nb if nb else None),
+                      "late_starters": sum(1 for s_, _ in spans if s_ > start + 0.05)}), flush=True)
+
+fio.index._batcher.max_wait = 0.0
+concurrent_procs("fenix_b200 Flight, 16 client PROCESSES, micro-batching OFF")
+fio.index._batcher.max_wait = wait
+concurrent_procs("fenix_b200 Flight, 16 client PROCESSES, micro-batching ON (300 us window)")
+
 # reference arm: same server, CPU path of the reference (oracle port) behind io.index.call
 from oracle import call as oracle_call
 real_call = fio.index.call
