@@ -822,21 +822,25 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
   double t_mark = now_ms();
   if (trace) fprintf(stderr, "[fenix tiers] main pass: %zu certificate failures, %zu starved (of %lld queries, prepass %d)\n",
                      bad.size(), starved.size(), (long long)n_q, int(run->L.with_pre));
-  // Flagged queries are settled by up to two more filter passes over their own (small) batch:
-  //  tier 0 (queries left with fewer than k candidates): the adaptive search without prepass and with FULL candidate lists
-  //         (K' entries each). Two things starve a query: a sample threshold that came out too tight, and neighbours
-  //         concentrated in one candidate list (clustered rows in row order) when the lists keep fewer than k entries;
-  //         either way there is no k-th distance to refine from;
+  // Flagged queries are settled by further filter passes over their own (small) batch:
+  //  tier 0 (queries left with fewer than k candidates - there is no k-th distance to refine from): the search again with
+  //         FULL candidate lists (K' entries each). Stage a keeps the sample prepass: the small batch draws its own sample
+  //         (other tiles, other rank), which settles what starves on clustered rows - the sample statistic assumes rows
+  //         exchangeable across tiles, and the reference tests' batches of 1000 rows around a common offset are not: 8 % of
+  //         the queries of a C2-scale batch starve in the main pass, none after stage a (1.0 ms for ~800 queries; 1.1 ms
+  //         through the adaptive search). What stage a leaves starved runs adaptively, without prepass (stage b);
   //  tier 1: preset-threshold refinement: the admission threshold is the query's k-th distance minus the error
   //         bound and every survivor is reranked, so the result is exact.
-
-  for (int tier = starved.empty() ? 1 : 0; tier <= 1 && !ctx->tc.knobs.no_refine; ++tier) {
-    if (tier == 0) bad.swap(starved);                                    // tier 0 takes the starved queries only ...
-    else { bad.insert(bad.end(), starved.begin(), starved.end()); starved.clear(); }   // ... what it leaves flagged joins tier 1
-    if (bad.empty()) continue;
-    const int n_f = int(bad.size());
+  std::vector<int> to_refine;
+  to_refine.swap(bad);                 // certificate failures of the main pass: tier 1
+  bool adaptive_done = false;
+  for (int stage = starved.empty() ? 2 : 0; stage <= 2 && !ctx->tc.knobs.no_refine; ++stage) {
+    if (stage == 1 && adaptive_done) continue;
+    std::vector<int>& in = stage == 2 ? to_refine : starved;
+    if (in.empty()) continue;
+    const int n_f = int(in.size());
     FX_TRY(ctx->d_qlist.ensure(size_t(n_f) * sizeof(int)));
-    FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, bad.data(), size_t(n_f) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    FX_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, in.data(), size_t(n_f) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
     const size_t o_q = take(size_t(n_f) * c->dim * 4), o_tau = take(size_t(n_f) * 4);
@@ -855,9 +859,10 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
     FX_CUDA(cudaGetLastError());
     fx::TcSearch s2 = s;
     s2.Q = q_r; s2.n_q = n_f; s2.out_rows = rows2; s2.out_dist = dist2; s2.certify = true;
-    s2.tau_fixed = tier == 1 ? tau_fixed : nullptr; s2.no_prepass = 1; s2.full_lists = tier == 0 ? 1 : 0;
+    s2.tau_fixed = stage == 2 ? tau_fixed : nullptr; s2.no_prepass = stage == 0 ? 0 : 1; s2.full_lists = stage < 2 ? 1 : 0;
     s2.ev_k0 = nullptr; s2.ev_k1 = nullptr;   // keep the timing of the main pass
     const fx::TcLaunch L2 = fx::tc_prepare(&ctx->tc, s2);
+    if (stage == 0 && !L2.with_pre) adaptive_done = true;   // (no sample for this small batch: stage a already ran adaptively)
     FX_TRY(ctx->d_tc.ensure(L2.scratch_bytes));
     int launched2 = 0;
     if (!fx::tc_search(&ctx->tc, &c->tc, s2, L2, ctx->d_tc.p, &launched2, &err)) return fail(FX_ECUDA, "fx_search (refine): %s", err.c_str());
@@ -865,17 +870,31 @@ static int search_settle(fx_corpus* c, SearchRun* run, bool* changed) {
     // tier 0 results replace the first pass's in any case (they hold k real neighbours for tier 1 to refine from);
     // tier 1 results only where their certificate holds
     fx::refine_scatter_kernel<<<std::min((n_f * k + 255) / 256, 1024), 256, 0, ctx->stream>>>(
-        static_cast<const int*>(ctx->d_qlist.p), tier == 1 ? d_flags2 : nullptr, n_f, k, rows2, dist2, d_out_rows, d_out_dist);
+        static_cast<const int*>(ctx->d_qlist.p), stage == 2 ? d_flags2 : nullptr, n_f, k, rows2, dist2, d_out_rows, d_out_dist);
     FX_CUDA(cudaGetLastError());
     ctx->launches += launched2 + 2; c->stats.kernel_launches += launched2 + 2;
     FX_CUDA(cudaMemcpyAsync(h_flags, d_flags2, size_t(n_f) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     FX_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<int> still;
-    for (int i = 0; i < n_f; ++i) if (h_flags[i]) still.push_back(bad[i]);
-    c->stats.refined_queries += int64_t(n_f - int(still.size()));
-    if (trace) { const double t = now_ms(); fprintf(stderr, "[fenix tiers] tier %d: %d queries in, %zu still flagged, %.3f ms\n", tier, n_f, still.size(), t - t_mark); t_mark = t; }
-    bad.swap(still);
+    // stage a: still starved -> stage b, certificate failures -> tier 1; stage b: whatever is flagged -> tier 1;
+    // tier 1: whatever is flagged -> the fp64 scan
+    std::vector<int> still_starved, still;
+    for (int i = 0; i < n_f; ++i) {
+      if (h_flags[i] == 0) continue;
+      if (stage == 0 && h_flags[i] == 2 && !adaptive_done) still_starved.push_back(in[i]);
+      else still.push_back(in[i]);
+    }
+    c->stats.refined_queries += int64_t(n_f - int(still.size()) - int(still_starved.size()));
+    if (trace) {
+      const double t = now_ms();
+      fprintf(stderr, "[fenix tiers] tier %s: %d queries in, %zu still flagged, %.3f ms\n",
+              stage == 0 ? (L2.with_pre ? "0a (sample thresholds, full lists)" : "0 (adaptive, full lists)") : stage == 1 ? "0b (adaptive, full lists)" : "1 (refinement)",
+              n_f, still.size() + still_starved.size(), t - t_mark);
+      t_mark = t;
+    }
+    if (stage < 2) { starved.swap(still_starved); to_refine.insert(to_refine.end(), still.begin(), still.end()); }
+    else bad.swap(still);
   }
+  if (ctx->tc.knobs.no_refine) { bad.swap(to_refine); bad.insert(bad.end(), starved.begin(), starved.end()); }
   if (!bad.empty()) {
     // tier 2: the certificate-free fp64 scan
     std::vector<int64_t> before_rows; std::vector<float> before_dist;
