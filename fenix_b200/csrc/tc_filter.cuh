@@ -211,6 +211,7 @@ struct TcSearch {
   int sample_stride;         // > 1: threshold prepass over every sample_stride-th corpus tile (set by tc_search)
   int pre_m;                 // prepass: rank of the sample's block maximum that becomes the query's initial threshold
   int no_prepass;            // 1: adaptive thresholds only (re-run of queries the sample threshold failed)
+  int seeded;                // set by tc_prepare: this main pass starts from the sample prepass's thresholds (list quotas >= k, see tc_plan)
   int full_lists;            // 1: every candidate list keeps K' entries (re-run of starved queries: when a query's neighbours sit in
                              // ONE list - clustered rows in row order - a list that keeps fewer than k can never supply them)
 };
@@ -1826,6 +1827,11 @@ inline TcPlan tc_plan(const TcState* st, const TcSearch& s) {
     int m = std::max(32, (2 * s.k + lists - 1) / lists + 16);
     m = (m + 31) & ~31;
     pl.kp_list = (s.tau_fixed || pre || s.full_lists) ? pl.kp : std::min(pl.kp, m);   // prepass: every list keeps the m best it sees
+    // A pass seeded by the sample prepass selects only when a list overflows, so a quota below k buys nothing there -
+    // and it is what starves queries whose neighbours sit in ONE list (a list that publishes its m-th best score as the
+    // query's global threshold vouches for m candidates only): with quotas of k rounded up the reference tests' clustered
+    // rows at C2 scale lose their 800 starved queries per batch (4.5 -> 3.3 ms per step; Gaussian rows unchanged).
+    if (s.seeded && !pre && !s.full_lists && !s.tau_fixed) pl.kp_list = std::min(pl.kp, std::max(pl.kp_list, (s.k + 31) & ~31));
     if (!pre && !s.full_lists && kn.kp_list >= 32) pl.kp_list = std::min(pl.kp, (kn.kp_list + 31) & ~31);
     pl.cap = (s.tau_fixed || pre) ? pl.cap : tc_cap(pl.kp_list);
   }
@@ -1870,6 +1876,10 @@ inline TcLaunch tc_prepare(const TcState* st, const TcSearch& s) {
   L.scratch_bytes = L.pl.total;
   L.with_pre = tc_prepass_config(st, s, L.pl, &L.pre);
   if (L.with_pre) {
+    TcSearch seeded = s;
+    seeded.seeded = 1;
+    L.pl = tc_plan(st, seeded);          // (same kernel, units and slices; the list quotas - hence the scratch layout - differ)
+    L.scratch_bytes = L.pl.total;
     L.ppl = tc_plan(st, L.pre);
     L.scratch_bytes = std::max(L.scratch_bytes, L.ppl.total);
   }
