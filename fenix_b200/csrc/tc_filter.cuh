@@ -2066,7 +2066,7 @@ inline bool tc_run_pass(TcState* st, TcCorpus* tc, const TcSearch& s, const TcPl
   // many short lists per query (small batches split over all SMs): more warps sweep them in parallel
   // few lists, many candidates to rerank (K' >= 128: k = 100): 128-thread CTAs - more of them per SM cover the scattered
   // exact-row reads better (C2: 2.87 -> 2.78 ms per step; 512 threads: 3.04)
-  int fin_threads = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices > 32 ? 1024 : (pl.kp >= 128 ? 128 : 256);
+  int fin_threads = (pl.rq ? 1 : TC_SPLIT) * pl.n_slices > 32 ? 1024 : (pl.kp >= 128 && pl.kp <= 512 ? 128 : 256);   // (refinement passes rerank up to 1024 survivors: 256)
   { const int ft = st->knobs.fin_threads; if (ft == 128 || ft == 256 || ft == 512 || ft == 1024) fin_threads = ft; }
   knn_tc_finish_kernel<<<s.n_q, fin_threads, fin_smem, s.stream>>>(f);
   cudaError_t e = cudaGetLastError();
