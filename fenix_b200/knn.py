@@ -226,6 +226,20 @@ class Context:
         _check(self._lib, self._lib.fx_merge_topk(self._h, d_rows, d_dist, n_lists, n_q, k, d_out_rows, d_out_dist))
 
 
+def cells_csr(cell_of_row: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Inverted index of a dense cell assignment: (rows grouped by cell - ascending row inside a cell - as int32,
+    offsets[n_cells + 1] of every cell's slice as int64), the layout fx_corpus_set_cells takes."""
+    cells = np.ascontiguousarray(cell_of_row, dtype=np.int64)
+    if cells.size and cells.min() < 0:
+        raise ValueError("cell numbers must be >= 0")
+    n_cells = int(cells.max()) + 1 if cells.size else 0
+    inv = np.argsort(cells, kind="stable").astype(np.int32)
+    off = np.zeros(n_cells + 1, dtype=np.int64)
+    if n_cells:
+        np.cumsum(np.bincount(cells, minlength=n_cells), out=off[1:])
+    return inv, off
+
+
 class Corpus:
     """A device-resident row shard of a corpus (float32, row-major)."""
 
@@ -316,10 +330,8 @@ class Corpus:
         cells = np.ascontiguousarray(cell_of_row, dtype=np.int64)
         if cells.shape != (self.n_rows,):
             raise ValueError(f"cell_of_row must have shape ({self.n_rows},), got {cells.shape}")
-        n_cells = int(cells.max()) + 1 if cells.size else 0
-        inv = np.argsort(cells, kind="stable").astype(np.int32)          # rows grouped by cell, ascending row inside a cell
-        off = np.zeros(n_cells + 1, dtype=np.int64)
-        np.cumsum(np.bincount(cells, minlength=n_cells), out=off[1:])
+        inv, off = cells_csr(cells)
+        n_cells = len(off) - 1
         _check(self._lib, self._lib.fx_corpus_set_cells(self._h, inv.ctypes.data, inv.size, off.ctypes.data, n_cells))
         return n_cells
 

@@ -344,3 +344,67 @@ def test_warm_spec(tmp_path, monkeypatch):
     assert seen == [4, 6]
     assert shards.warm(root, "a:vector") == ["a:vector"] and seen == [4, 6]           # cached: no second upload
     shards.invalidate(root)
+
+
+def test_cells_csr_groups_rows_by_cell():
+    """The inverted index fx_corpus_set_cells takes: rows grouped by cell, ascending inside a cell, empty cells allowed."""
+    from fenix_b200 import knn
+
+    cell = np.array([2, 0, 2, 5, 0, 2], dtype=np.int64)
+    inv, off = knn.cells_csr(cell)
+    assert inv.dtype == np.int32 and off.dtype == np.int64
+    assert off.tolist() == [0, 2, 2, 5, 5, 5, 6]
+    assert inv.tolist() == [1, 4, 0, 2, 5, 3]
+    inv0, off0 = knn.cells_csr(np.zeros(0, np.int64))
+    assert inv0.size == 0 and off0.tolist() == [0]
+    with pytest.raises(ValueError):
+        knn.cells_csr(np.array([0, -1]))
+
+
+def test_batched_ivf_host_glue_maps_probe_codes_to_cells():
+    """io.index._search_cells: composite probe codes -> dense cell numbers of the codes present in the sidecar (absent and
+    repeated codes become -1), the inverted index installed once per (coding, sidecar version), `more_than` short-circuit."""
+    calls = {"set": 0, "search": []}
+
+    class FakeCorpus:
+        n_rows = 8
+
+        def set_cells(self, dense):
+            calls["set"] += 1
+            calls["dense"] = np.asarray(dense).tolist()
+            return int(np.max(dense)) + 1
+
+        def search_cells(self, queries, metric, k, probes, mask):
+            calls["search"].append((np.asarray(probes).tolist(), k, None if mask is None else np.asarray(mask).tolist()))
+            return np.zeros((len(queries), k), np.int64), np.zeros((len(queries), k), np.float32)
+
+    class FakeShard:
+        import threading as _t
+        corpora = [FakeCorpus()]
+        _cells = None
+        _cells_lock = _t.Lock()
+
+    from fenix_b200 import knn
+
+    codes = np.array([70, 10, 70, 33, 10, 10, 70, 99], dtype=np.int64)       # cells: 10 -> 0, 33 -> 1, 70 -> 2, 99 -> 3
+    queries = np.zeros((2, 4), np.float32)
+    probe_codes = np.array([[70, 5, 70], [99, 33, 10]], dtype=np.int64)     # 5 is in no row; 70 repeats
+    shard = FakeShard()
+    out = ix._search_cells(shard, ("cb", 1), codes, queries, "l2", 3, probe_codes, None, knn.PREC_FP32)
+    assert out is not None and calls["set"] == 1 and calls["dense"] == [2, 0, 2, 1, 0, 0, 2, 3]
+    probes, k, mask = calls["search"][-1]
+    assert k == 3 and mask is None
+    assert sorted(probes[0]) == [-1, -1, 2] and probes[1] == [3, 1, 0]
+    # same key: the inverted index is reused; another key replaces it
+    ix._search_cells(shard, ("cb", 1), codes, queries, "l2", 3, probe_codes, None, knn.PREC_FP32)
+    assert calls["set"] == 1
+    ix._search_cells(shard, ("cb", 2), codes, queries, "l2", 3, probe_codes, None, knn.PREC_FP32)
+    assert calls["set"] == 2
+    # more_than: the first query's probed cells hold 3 rows (cell 2) -> nothing to select when maxval >= 3
+    n_before = len(calls["search"])
+    assert ix._search_cells(shard, ("cb", 2), codes, queries[:1], "l2", 3, probe_codes[:1], None, knn.PREC_FP32, more_than=3) is None
+    assert len(calls["search"]) == n_before
+    assert ix._search_cells(shard, ("cb", 2), codes, queries[:1], "l2", 2, probe_codes[:1], None, knn.PREC_FP32, more_than=2) is not None
+    # shapes the one-launch path does not take
+    assert ix._search_cells(shard, ("cb", 2), codes, queries, "l2", None, probe_codes, None, knn.PREC_FP32) is None
+    assert ix._search_cells(shard, ("cb", 2), codes, queries, "l2", 3, probe_codes, None, knn.PREC_BF16) is None
