@@ -68,6 +68,32 @@ def test_index_call_has_no_cpu_fallback(built_library, tmp_path):
         fenix.io.index.call(str(tmp_path), None, "t", "vector", corpus[0], metric="l2", maxval=3)
 
 
+def build_c_demo(built_library, out_dir) -> str:
+    """gcc examples/knn_demo.c against include/fenix_knn.h and the built library: a plain-C host, no Python, no torch."""
+    exe = os.path.join(str(out_dir), "knn_demo")
+    lib_dir = os.path.dirname(built_library)
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "knn_demo.c"),
+           "-L", lib_dir, "-lfenix_knn", f"-Wl,-rpath,{lib_dir}", "-Wl,--allow-shlib-undefined", "-lm", "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_c_host_compiles_against_the_header(built_library, tmp_path):
+    exe = build_c_demo(built_library, tmp_path)
+    if not _has_gpu():
+        # without a device the C host fails the documented way: FX_ECUDA from fx_init, message from fx_last_error
+        res = subprocess.run([exe], capture_output=True, text=True)
+        assert res.returncode == 2 and "no CPU fallback" in res.stderr, (res.returncode, res.stderr)
+
+
+@pytest.mark.gpu
+def test_c_host_runs_and_matches_its_brute_force(built_library, tmp_path):
+    res = subprocess.run([build_c_demo(built_library, tmp_path)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "KNN DEMO OK" in res.stdout, (res.stdout[-2000:], res.stderr[-2000:])
+    assert "path 3" in res.stdout and "path 2" in res.stdout       # the direct scan for one query, the tcgen05 filter for the batch
+
+
 def test_null_arguments_are_einval(built_library):
     lib = knn.load_library()
     assert lib.fx_init(0, None) == knn.FX_EINVAL
