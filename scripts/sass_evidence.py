@@ -1,7 +1,7 @@
 """cuobjdump -sass of libfenix_knn.so -> profiles/r02_sass_evidence.txt: per kernel the Blackwell-specific mnemonics it
 contains (tcgen05.mma = UTCHMMA / UTCQMMA, TMEM loads = LDTM, TMA = UTMALDG / UBLKCP, tcgen05.commit = UTCBAR, cluster
 barriers) with counts, and the head of the listing of the dominant kernels."""
-import collections, os, re, subprocess, sys
+import collections, os, re, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "fenix_b200", "libfenix_knn.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout

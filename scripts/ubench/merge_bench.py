@@ -1,7 +1,7 @@
 """fx_merge_topk on one GPU: W sorted lists of k (distance, row) pairs per query -> top-k; shared-memory sort against the
 rank merge (FENIX_MERGE_RANK_MIN), the C3 and C4 exchange shapes at 8 GPUs."""
 import sys, os, time
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.getcwd())
 from fenix_b200 import knn
 ctx = knn.Context(0)
