@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import functools
 import os
+import threading
 import pickle
 import shutil
 from dataclasses import dataclass
@@ -43,6 +44,20 @@ class Server(fl.FlightServerBase):
         # FENIX_WARM="table:column,...": device shards of those columns are uploaded before the first request
         if os.environ.get("FENIX_WARM"):
             io.shards.warm(self.root)
+        elif os.environ.get("FENIX_EAGER_INIT", "1") != "0":
+            # CUDA context + library initialisation (2 - 3 s on a fresh process) happen behind the server's start-up instead
+            # of inside the first do_put / search. No usable device: the request that needs one reports it.
+            def _init_devices() -> None:
+                try:
+                    devs = io.shards.devices()
+                    if len(devs) > 1:
+                        io.shards.group(devs)       # one process, several devices: contexts + NCCL communicators
+                    else:
+                        io.shards.context(devs[0])
+                except Exception:
+                    pass
+
+            threading.Thread(target=_init_devices, name="fenix-init", daemon=True).start()
 
     def get_flight_info(self, ctx, descriptor):
         raise NotImplementedError()
